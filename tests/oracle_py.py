@@ -140,8 +140,10 @@ def parse_query_line(line):
 
 def read_ref_results(path):
     """Parse ref_tool replay output -> list of (docs, scores, dfs)."""
+    import gzip
     out = []
-    with open(path) as f:
+    opener = gzip.open if path.endswith(".gz") else open
+    with opener(path, "rt") as f:
         for line in f:
             it = line.split()
             ne, nd = int(it[0]), int(it[1])

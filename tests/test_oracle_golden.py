@@ -1,0 +1,80 @@
+"""Pins the CPU oracle (oracle/wsr_oracle.cc) to the REFERENCE: known answers from the
+reference's own tests and outputs of the unmodified reference engine committed under
+tests/golden/ (see tests/golden/make_golden.py). Bit-exact, including tie order."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_py import OracleIndex, parse_query_line, read_ref_results
+
+FIXTURES = ["hello3", "abc3", "wiki4", "zipf2k"]
+
+
+def _queries(d):
+    return [parse_query_line(l)[0] for l in open(os.path.join(d, "queries.txt"))]
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+@pytest.mark.parametrize("k,fn", [(10, "ref_top10.txt.gz"), (3, "ref_top3.txt.gz"),
+                                  (1000000, "ref_full.txt.gz")])
+def test_search_matches_reference(golden_dir, name, k, fn):
+    d = os.path.join(golden_dir, name)
+    ix = OracleIndex(d)
+    ref = read_ref_results(os.path.join(d, fn))
+    qs = _queries(d)
+    assert len(ref) == len(qs)
+    for q, (docs, scores, dfs) in zip(qs, ref):
+        od, os_, odfs = ix.search(q, k)
+        assert np.array_equal(od, docs), q
+        assert np.array_equal(os_.view(np.uint64), scores.view(np.uint64)), q
+        assert odfs == dfs, q
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_decode_matches_reference_iterators(golden_dir, name):
+    d = os.path.join(golden_dir, name)
+    ix = OracleIndex(d)
+    z = np.load(os.path.join(d, "lists.npz"))
+    terms, offs = z["terms"], z["offsets"]
+    assert len(terms) == ix.term_count
+    for i, t in enumerate(terms):
+        docs, tfs = ix.decode_list(str(t))
+        assert np.array_equal(docs, z["docs"][offs[i]:offs[i + 1]]), t
+        assert np.array_equal(tfs, z["tfs"][offs[i]:offs[i + 1]]), t
+
+
+def test_known_answers_hello3(golden_dir):
+    """tests.cc:407-459 (3-digit ES-derived values) and the full-precision values the survey
+    reproduced from the reference."""
+    ix = OracleIndex(os.path.join(golden_dir, "hello3"))
+    d, s, dfs = ix.search(["wisconsin"], 5)
+    assert list(d) == [1] and s[0] == 1.0925692944940748 and dfs == [1]
+    d, s, dfs = ix.search(["hello"], 5)
+    assert len(d) == 3 and dfs == [3]
+    assert s[0] == s[1] == 0.14874382975896183 and s[2] == 0.11085625048073575
+    assert [f"{x:.3f}" for x in s] == ["0.149", "0.149", "0.111"]
+    d, s, dfs = ix.search(["hello", "world"], 5)
+    assert list(d) == [2, 0] and dfs == [3, 2]
+    assert s[0] == 0.67743596792765004 and s[1] == 0.67229217626054072
+
+
+def test_boundary_semantics(golden_dir):
+    """vacuum_engine.h:206-219: k==0 and missing terms give an empty result with no doc_freqs;
+    duplicate terms intersect the list with itself (score doubles)."""
+    ix = OracleIndex(os.path.join(golden_dir, "zipf2k"))
+    d, s, dfs = ix.search(["t0"], 0)
+    assert len(d) == 0 and dfs == []
+    d, s, dfs = ix.search(["t0", "nosuch"], 10)
+    assert len(d) == 0 and dfs == []
+    d1, s1, _ = ix.search(["t3"], 10)
+    d2, s2, dfs2 = ix.search(["t3", "t3"], 10)
+    assert np.array_equal(d1, d2) and np.array_equal(s2, s1 + s1) and dfs2[0] == dfs2[1]
+
+
+def test_char4_norm_examples(golden_dir):
+    """tests_8.cc:13-63 style: 87 -> byte 34 -> 80 ; 1000 -> 63 -> 960."""
+    ix = OracleIndex(os.path.join(golden_dir, "zipf2k"))
+    for doc in range(0, ix.num_docs, 97):
+        b = ix.norm_byte(doc)
+        assert 0 <= b < 128
