@@ -1,0 +1,162 @@
+/* wsr.h — C ABI of the B200-native query engine for WiSER/Vacuum's hot path:
+ * conjunctive posting-list intersection + fused BM25 scoring + top-k over an HBM-resident
+ * inverted index (libwsr.so, hand-written sm_100a CUDA kernels; no CPU fallback).
+ *
+ * The reference has no FFI for this path; its seam is the C++ abstract class
+ * SearchEngineServiceNew (reference src/qq_mem/src/engine_services.h:14-27) created by
+ * CreateSearchEngine (engine_factory.h:33-50). Each entry point below names the reference
+ * member it stands behind; the C++ adapter a maintainer adds on the reference side
+ * (class GpuVacuumEngine : SearchEngineServiceNew) is shown in INTEGRATION.md and shipped as
+ * wiser_b200/csrc/gpu_vacuum_engine.h.
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every in/out buffer, the
+ * library owns device memory and the handles. All functions return 0 on success or a
+ * negative wsr_status; wsr_last_error() gives the message for the calling thread.
+ * Thread-safety: a wsr_index is read-only after open; wsr_search / wsr_search_batch may be
+ * called concurrently from many threads (the reference's server calls Search from N threads
+ * on one shared engine with no lock, grpc_server_impl.h:309-328).
+ */
+#ifndef WSR_H
+#define WSR_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WSR_MAX_TERMS 8      /* QueryProcessor's phrase capacity, query_processing.h:695 */
+#define WSR_TERM_ABSENT 0xFFFFFFFFu
+
+typedef enum {
+  WSR_OK = 0,
+  WSR_ERR_ARG = -1,        /* bad argument */
+  WSR_ERR_IO = -2,         /* cannot read / parse the index directory */
+  WSR_ERR_CUDA = -3,       /* CUDA runtime error or no device */
+  WSR_ERR_UNSUPPORTED = -4 /* e.g. more than WSR_MAX_TERMS terms */
+} wsr_status;
+
+typedef struct wsr_index wsr_index;  /* one HBM-resident index (or document shard of one) */
+typedef struct wsr_batch wsr_batch;  /* device-resident query batch + result buffers */
+
+/* One result entry = SearchResultEntry{doc_id:int, doc_score:double} (types.h:259-263),
+ * snippet omitted (return_snippets=false on this path). 16 bytes. */
+typedef struct {
+  int32_t doc_id;
+  int32_t reserved;
+  double score;
+} wsr_hit;
+
+/* One query = SearchQuery{terms, n_results} (types.h:205-218) after term lookup.
+ * term_ids are in QUERY ORDER (BM25 partial scores are summed in that order, scoring.h:124-145).
+ * A term id of WSR_TERM_ABSENT, or k == 0, makes the result empty with n_doc_freqs == 0
+ * (vacuum_engine.h:206-215). */
+typedef struct {
+  uint32_t term_ids[WSR_MAX_TERMS];
+  uint32_t n_terms;
+  uint32_t k;      /* n_results */
+  uint32_t flags;  /* reserved (phrase bit later) */
+} wsr_query;
+
+/* Index statistics. */
+typedef struct {
+  int64_t n_docs;            /* DocLengthCharStore::Size(): global, all shards */
+  double avg_doc_len;        /* stored running mean from my.doc_length (never recomputed) */
+  int64_t n_terms;           /* VacuumEngine::TermCount() */
+  int64_t n_postings;        /* postings resident on THIS shard */
+  int64_t n_postings_global; /* postings of the whole index */
+  int64_t n_blocks;          /* 128-posting blocks on this shard */
+  int64_t hbm_bytes;         /* device memory held by the index */
+  int64_t payload_bytes;     /* packed doc-id + tf bitstreams */
+  int32_t shard, n_shards;
+  int32_t doc_lo, doc_hi;    /* this shard holds docs in [doc_lo, doc_hi) */
+  int32_t device;
+} wsr_index_info;
+
+const char *wsr_last_error(void);
+int wsr_device_count(void);
+/* Page-locked host memory: result/query buffers allocated here are DMA'd directly by
+ * wsr_search_batch / wsr_batch_fetch; other buffers go through an internal pinned stage. */
+void *wsr_host_alloc(size_t bytes);
+void wsr_host_free(void *p);
+
+/* ---- Load(): VacuumEngine::Load (vacuum_engine.h:144-180) --------------------------------
+ * Reads <dir>/my.tip, my.vacuum, my.doc_length and re-lays the posting lists into HBM on
+ * `device` as fixed 128-posting packed delta blocks with per-block skip metadata.
+ * Document partitioning: shard s of n_shards keeps the postings whose doc id falls in
+ * [s*N/n, (s+1)*N/n); idf and doc_freqs keep using GLOBAL N and df. Use (0,1) for no
+ * sharding. */
+wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_shards,
+                          int loader_threads, char *err, size_t errlen);
+void wsr_index_close(wsr_index *idx);
+int wsr_index_get_info(const wsr_index *idx, wsr_index_info *info);
+
+/* ---- term dictionary: TermTrieIndex::Find (term_index.h:136-144) -------------------------
+ * Returns 0 and fills term_id / df (GLOBAL document frequency = posting-list size,
+ * VacuumEngine::PostinglistSizes) or 1 if the term is absent. */
+int wsr_term_lookup(const wsr_index *idx, const char *term, size_t len, uint32_t *term_id,
+                    uint32_t *df);
+/* i-th term in my.tip order; returns its length (copies at most cap bytes), <0 on error. */
+int wsr_term_at(const wsr_index *idx, uint32_t term_id, char *buf, size_t cap, uint32_t *df);
+
+/* ---- decode: VacuumPostingListIterator walk (flash_iterators.h:985-1016) -----------------
+ * Decodes this shard's part of a posting list on the GPU into HOST buffers (doc ids and
+ * term frequencies in list order). *n receives the number of postings on this shard; at
+ * most cap are written. */
+int wsr_decode_list(wsr_index *idx, uint32_t term_id, uint32_t *docs, uint32_t *tfs,
+                    size_t cap, size_t *n);
+/* Bench/ncu entry: decodes EVERY block of the shard into a device scratch checksum without
+ * copying results back; *checksum = sum of all doc ids + tfs (mod 2^64). */
+int wsr_decode_all(wsr_index *idx, uint64_t *checksum, float *kernel_ms);
+
+/* ---- Search(): VacuumEngine::Search (vacuum_engine.h:201-258) ----------------------------
+ * String-term single query, blocking. hits must hold k entries, doc_freqs n_terms entries.
+ * *n_doc_freqs is 0 when the reference returns early with an empty result, else n_terms. */
+int wsr_search(wsr_index *idx, const char *const *terms, const size_t *term_lens, int n_terms,
+               int k, wsr_hit *hits, int *n_hits, uint32_t *doc_freqs, int *n_doc_freqs);
+
+/* Batched Search over HOST buffers: the query batch is copied to the device, processed by
+ * the batch scheduler in one pass, and the results copied back (all inside the call).
+ * hits: n * k_stride entries (query i at hits[i*k_stride]); n_hits: n entries;
+ * doc_freqs (may be NULL): n * WSR_MAX_TERMS entries, n_doc_freqs (may be NULL): n entries. */
+int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stride,
+                     wsr_hit *hits, int32_t *n_hits, uint32_t *doc_freqs,
+                     int32_t *n_doc_freqs);
+
+/* ---- device-resident batches (replay driver, multi-GPU merge, benchmarking) --------------
+ * wsr_batch_create uploads and plans a batch once; wsr_batch_run launches the kernels on the
+ * batch's stream (no host<->device copies); results stay in device memory until fetched. */
+wsr_batch *wsr_batch_create(wsr_index *idx, const wsr_query *queries, int n, int k_stride);
+void wsr_batch_destroy(wsr_batch *b);
+int wsr_batch_run(wsr_batch *b);                       /* asynchronous on the batch stream */
+int wsr_batch_sync(wsr_batch *b);
+int wsr_batch_fetch(wsr_batch *b, wsr_hit *hits, int32_t *n_hits); /* D2H + sync */
+/* Device pointers of the result arrays (n*k_stride wsr_hit, n int32) and the CUDA stream
+ * (cudaStream_t) — for NCCL allgather of per-shard top-k by the caller. */
+int wsr_batch_device_results(wsr_batch *b, void **d_hits, void **d_n_hits, void **stream);
+/* Timed run: launches the batch `iters` times back to back and reports the average device
+ * time per iteration measured with CUDA events on the batch stream. */
+int wsr_batch_time(wsr_batch *b, int iters, float *ms_per_iter);
+
+/* Counters of the LAST run of this batch (read back from the device). */
+typedef struct {
+  uint64_t listed_postings;   /* sum over valid queries of sum_i df_i (shard-local lists) */
+  uint64_t decoded_postings;  /* 128 x doc-id blocks actually decoded */
+  uint64_t touched_bytes;     /* algorithmic bytes of the blocks actually read (+16 B meta each) */
+  uint64_t listed_bytes;      /* algorithmic bytes of every block of every listed list */
+  uint64_t matches;           /* intersection hits scored */
+  uint64_t work_units;        /* warp work units scheduled */
+  uint32_t kernel_launches;   /* launches per run */
+} wsr_batch_stats;
+int wsr_batch_get_stats(wsr_batch *b, wsr_batch_stats *s);
+
+/* Cross-shard merge: gathered = n_shards consecutive result arrays as produced
+ * by wsr_batch_device_results on every shard (after an all-gather), all DEVICE pointers.
+ * Writes the global top-k per query, ordered (score desc, doc id asc). */
+int wsr_merge_topk_device(const void *d_gathered_hits, const void *d_gathered_n_hits,
+                          int n_shards, int n_queries, int k_stride, void *d_out_hits,
+                          void *d_out_n_hits, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,138 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+the CPU oracle and the committed reference outputs on the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle_py import OracleIndex, parse_query_line, read_ref_results
+from parity import check_full, check_topk
+
+pytestmark = pytest.mark.gpu
+
+FIXTURES = ["hello3", "abc3", "wiki4", "zipf2k"]
+
+
+@pytest.fixture(scope="module")
+def engines(golden_dir):
+    from wiser_b200 import GpuVacuumEngine
+    out = {}
+    for name in FIXTURES:
+        d = os.path.join(golden_dir, name)
+        out[name] = (GpuVacuumEngine(d).Load(), OracleIndex(d), d)
+    yield out
+    for e, _, _ in out.values():
+        e.close()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_decode_every_list(engines, name):
+    """K1: every posting list decodes to the (doc id, tf) sequence of the reference iterators."""
+    eng, _, d = engines[name]
+    z = np.load(os.path.join(d, "lists.npz"))
+    terms, offs = z["terms"], z["offsets"]
+    assert eng.TermCount() == len(terms)
+    for i, t in enumerate(terms):
+        docs, tfs = eng.decode_list(str(t))
+        assert np.array_equal(docs, z["docs"][offs[i]:offs[i + 1]]), t
+        assert np.array_equal(tfs, z["tfs"][offs[i]:offs[i + 1]]), t
+    info = eng.info()
+    checksum, _ = eng.decode_all()
+    assert checksum == int(z["docs"].astype(np.uint64).sum() + z["tfs"].astype(np.uint64).sum())
+    assert info.n_postings == len(z["docs"])
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+@pytest.mark.parametrize("k,fn", [(10, "ref_top10.txt.gz"), (3, "ref_top3.txt.gz")])
+def test_topk_vs_reference(engines, name, k, fn):
+    from wiser_b200 import SearchQuery
+    eng, _, d = engines[name]
+    ref = read_ref_results(os.path.join(d, fn))
+    full = read_ref_results(os.path.join(d, "ref_full.txt.gz"))
+    qs = [SearchQuery(parse_query_line(l)[0], n_results=k) for l in open(os.path.join(d, "queries.txt"))]
+    res = eng.SearchBatch(qs)
+    assert len(res) == len(ref)
+    for q, r, (rd, rs, rdf), (fd, fs, _) in zip(qs, res, ref, full):
+        assert r.doc_freqs == rdf, q.terms
+        check_topk(rd, rs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], fd, fs,
+                   what=" ".join(q.terms))
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_full_intersection_vs_reference(engines, name):
+    """k = 10^6 (collect path): bit-exact intersection doc-id sets and scores."""
+    from wiser_b200 import SearchQuery
+    eng, _, d = engines[name]
+    full = read_ref_results(os.path.join(d, "ref_full.txt.gz"))
+    lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
+    qs = [SearchQuery(parse_query_line(l)[0], n_results=1000000) for l in lines]
+    # collect-mode segments are sized by the shortest list; keep batches modest
+    for lo in range(0, len(qs), 512):
+        chunk = qs[lo:lo + 512]
+        hits_needed = max(1, max(min([eng.PostinglistSizes([t]).get(t, 0) for t in q.terms] or [0])
+                                 for q in chunk))
+        for q in chunk:
+            q.n_results = max(hits_needed, 33)
+        res = eng.SearchBatch(chunk)
+        for q, r, (fd, fs, fdf) in zip(chunk, res, full[lo:lo + 512]):
+            assert r.doc_freqs == fdf
+            check_full(fd, fs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries],
+                       what=" ".join(q.terms))
+
+
+def test_single_query_api_and_known_answers(engines):
+    from wiser_b200 import SearchQuery
+    eng, _, _ = engines["hello3"]
+    r = eng.Search(SearchQuery(["wisconsin"]))
+    assert [e.doc_id for e in r.entries] == [1] and r.entries[0].doc_score == 1.0925692944940748
+    r = eng.Search(SearchQuery(["hello", "world"]))
+    assert [e.doc_id for e in r.entries] == [2, 0] and r.doc_freqs == [3, 2]
+    assert r.entries[0].doc_score == 0.67743596792765004
+    assert r.entries[1].doc_score == 0.67229217626054072
+    r = eng.Search(SearchQuery(["hello"], n_results=0))
+    assert r.Size() == 0 and r.doc_freqs == []
+    r = eng.Search(SearchQuery(["hello", "nosuchterm"]))
+    assert r.Size() == 0 and r.doc_freqs == []
+    assert eng.PostinglistSizes(["hello", "world", "zzz"]) == {"hello": 3, "world": 2}
+    assert eng.TermCount() == 4
+
+
+@pytest.mark.parametrize("n_shards", [2, 3])
+def test_document_partitioned_shards_merge(golden_dir, n_shards):
+    """SURVEY §8e on ONE GPU: each shard is its own index; per-shard top-k lists merged by the
+    cross-shard merge kernel must equal the unsharded result bit-for-bit."""
+    import ctypes as C
+    import torch
+    from wiser_b200 import Batch, GpuVacuumEngine, SearchQuery
+    from wiser_b200.capi import HIT_DTYPE, check, lib
+    d = os.path.join(golden_dir, "zipf2k")
+    lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
+    qs = [SearchQuery(parse_query_line(l)[0], n_results=10) for l in lines]
+    whole = GpuVacuumEngine(d).Load()
+    qarr = whole.make_queries(qs)
+    ref_hits, ref_n, _, _ = whole.search_batch(qarr, 10)
+    n = len(qs)
+    gathered = torch.zeros((n_shards, n, 10, 16), dtype=torch.uint8, device="cuda")
+    gathered_n = torch.zeros((n_shards, n), dtype=torch.int32, device="cuda")
+    shards = []
+    for s in range(n_shards):
+        e = GpuVacuumEngine(d, shard=s, n_shards=n_shards).Load()
+        b = Batch(e, qarr, 10)
+        b.run()
+        b.sync()
+        h, nh = b.fetch()
+        gathered[s] = torch.from_numpy(h.view(np.uint8).reshape(n, 10, 16)).cuda()
+        gathered_n[s] = torch.from_numpy(nh).cuda()
+        shards.append((e, b))
+    out = torch.zeros((n, 10, 16), dtype=torch.uint8, device="cuda")
+    out_n = torch.zeros(n, dtype=torch.int32, device="cuda")
+    check(lib().wsr_merge_topk_device(gathered.data_ptr(), gathered_n.data_ptr(), n_shards, n, 10,
+                                      out.data_ptr(), out_n.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(n, 160).view(HIT_DTYPE).reshape(n, 10)
+    got_n = out_n.cpu().numpy()
+    assert np.array_equal(got_n, ref_n)
+    for i in range(n):
+        k = ref_n[i]
+        assert np.array_equal(got["doc_id"][i, :k], ref_hits["doc_id"][i, :k]), lines[i]
+        assert np.array_equal(got["score"][i, :k].view(np.uint64), ref_hits["score"][i, :k].view(np.uint64))

@@ -1,0 +1,443 @@
+// Index loader: vacuum directory -> HostIndex (see host_index.h for the layout).
+// File formats follow SURVEY.md §5.1; the reference readers they replace are cited inline
+// (paths relative to the reference's src/qq_mem/src/).
+#include "host_index.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+namespace wsr {
+namespace {
+
+struct FileView {
+  const uint8_t *data = nullptr;
+  size_t size = 0;
+  ~FileView() { if (data) munmap((void *)data, size); }
+  bool Map(const std::string &path) {
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    bool ok = fstat(fd, &st) == 0;
+    if (ok && st.st_size > 0) {
+      void *m = mmap(nullptr, st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      ok = m != MAP_FAILED;
+      if (ok) { data = (const uint8_t *)m; size = st.st_size; }
+    }
+    close(fd);
+    return ok;
+  }
+};
+
+// LEB128 reader with bounds (utils.h:230-266 is the reference decoder).
+struct ByteCursor {
+  const uint8_t *p, *end;
+  bool ok = true;
+  uint64_t Varint() {
+    uint64_t v = 0;
+    for (int shift = 0; shift < 64; shift += 7) {
+      if (p >= end) { ok = false; return 0; }
+      uint8_t b = *p++;
+      v |= (uint64_t)(b & 0x7f) << shift;
+      if (!(b & 0x80)) return v;
+    }
+    ok = false;
+    return 0;
+  }
+};
+
+inline int BitWidth(uint32_t v) { return v ? 32 - __builtin_clz(v) : 0; }
+
+// Reads one blob of the doc-id or tf column into out[0..n): a 128-value pack
+// (0xD6, bits, 16*bits bytes: LittlePackedIntsReader, packed_value.h:184-235) or the VInts
+// tail (0x9B, varint n_bytes, LEB128 values: VIntsIterator, packed_value.h:400-460).
+bool ReadBlob(const uint8_t *file, size_t file_size, uint64_t off, int n, uint32_t *out) {
+  if (off + 2 > file_size) return false;
+  const uint8_t *b = file + off;
+  if (b[0] == 0xD6) {
+    const int bits = b[1];
+    if (bits > 32 || off + 2 + 16ull * bits > file_size) return false;
+    const uint8_t *s = b + 2;
+    const size_t nbytes = 16ull * bits;
+    const uint64_t mask = bits == 32 ? 0xffffffffull : ((1ull << bits) - 1);
+    uint64_t bitpos = 0;
+    for (int i = 0; i < n; i++, bitpos += bits) {
+      const size_t byte = bitpos >> 3;
+      uint64_t w;
+      if (byte + 8 <= nbytes) {
+        memcpy(&w, s + byte, 8);
+      } else {
+        w = 0;
+        memcpy(&w, s + byte, nbytes - byte);
+      }
+      out[i] = (uint32_t)((w >> (bitpos & 7)) & mask);
+    }
+    return true;
+  }
+  if (b[0] == 0x9B) {
+    ByteCursor c{b + 1, file + file_size};
+    uint64_t nbytes = c.Varint();
+    if (!c.ok || c.p + nbytes > file + file_size) return false;
+    c.end = c.p + nbytes;
+    for (int i = 0; i < n; i++) out[i] = (uint32_t)c.Varint();
+    return c.ok;
+  }
+  return false;
+}
+
+// Appends n values as an LSB-first b-bit stream padded to 16 bytes.
+void PackStream(const uint32_t *v, int n, int bits, std::vector<uint8_t> *out) {
+  const size_t nbytes = StreamBytes(n, bits);
+  const size_t at = out->size();
+  out->resize(at + nbytes, 0);
+  uint8_t *d = out->data() + at;
+  uint64_t acc = 0;
+  int have = 0;
+  size_t w = 0;
+  for (int i = 0; i < n; i++) {
+    acc |= (uint64_t)v[i] << have;
+    have += bits;
+    while (have >= 8) {
+      d[w++] = (uint8_t)acc;
+      acc >>= 8;
+      have -= 8;
+    }
+  }
+  if (have > 0) d[w++] = (uint8_t)acc;
+}
+
+struct Chunk {               // output of one slice of terms
+  size_t term_begin = 0, term_end = 0;
+  std::vector<ListInfo> lists;
+  std::vector<uint64_t> list_alg_bytes;
+  std::vector<BlockInfo> blk_info;
+  std::vector<uint32_t> blk_last;
+  std::vector<uint8_t> payload;
+  int64_t postings = 0, postings_global = 0;
+  std::string err;
+};
+
+struct Builder {
+  const FileView &vac;
+  const std::vector<uint64_t> &list_offs;
+  const HostIndex &ix;      // norms / cache already filled
+  const float *tfn_tab;     // [64][256] exact-rounded-up tfn for tf < 64
+  uint32_t doc_lo, doc_hi;
+
+  float TfnUpper(uint32_t tf, uint8_t norm) const {
+    if (tf < 64) return tfn_tab[tf * 256 + norm];
+    double x = (tf * (1.2 + 1)) / (tf + ix.cache[norm]);
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+  }
+
+  bool BuildList(uint64_t off, Chunk *c, std::vector<uint32_t> *docs, std::vector<uint32_t> *tfs) {
+    // Posting-list header: VacuumPostingListIterator::ResetWithZoneInfo, flash_iterators.h:903-956
+    if (off + 10 > vac.size || vac.data[off] != 0xF4) { c->err = "bad posting-list magic"; return false; }
+    ByteCursor cur{vac.data + off + 1, vac.data + vac.size};
+    const uint64_t df = cur.Varint();
+    cur.p += 8;  // two reserved Bloom skip-list offsets
+    // Skip list: SkipList::Load, flash_containers.h:354-391
+    if (!cur.ok || cur.p >= cur.end || *cur.p != 0xA3) { c->err = "bad skip-list magic"; return false; }
+    cur.p++;
+    const uint64_t n_rows = cur.Varint();
+    if (n_rows != (df + kBlock - 1) / kBlock) { c->err = "skip rows != ceil(df/128)"; return false; }
+    docs->resize(df);
+    tfs->resize(df);
+    uint64_t prev_doc = 0, docid_off = 0, tf_off = 0;
+    for (uint64_t r = 0; r < n_rows; r++) {
+      prev_doc += cur.Varint();
+      docid_off += cur.Varint();
+      tf_off += cur.Varint();
+      cur.Varint(); cur.Varint(); cur.Varint(); cur.Varint();  // position / offset columns
+      if (!cur.ok) { c->err = "truncated skip list"; return false; }
+      const int n = (int)std::min<uint64_t>(kBlock, df - r * kBlock);
+      uint32_t *d = docs->data() + r * kBlock;
+      if (!ReadBlob(vac.data, vac.size, docid_off, n, d) ||
+          !ReadBlob(vac.data, vac.size, tf_off, n, tfs->data() + r * kBlock)) {
+        c->err = "bad doc-id/tf blob";
+        return false;
+      }
+      // deltas are taken over the whole list; each block restarts from the skip row's
+      // previous_doc_id (DeltaEncodedPackedIntsIterator::Reset, packed_value.h:328-333)
+      uint32_t run = (uint32_t)prev_doc;
+      for (int i = 0; i < n; i++) { run += d[i]; d[i] = run; }
+    }
+    // shard filter: contiguous doc-id range
+    size_t a = 0, b = df;
+    if (ix.n_shards > 1) {
+      a = std::lower_bound(docs->begin(), docs->end(), doc_lo) - docs->begin();
+      b = std::lower_bound(docs->begin(), docs->end(), doc_hi) - docs->begin();
+    }
+    ListInfo li;
+    li.first_block = (uint32_t)c->blk_info.size();
+    li.df_shard = (uint32_t)(b - a);
+    li.df_global = (uint32_t)df;
+    li.n_blocks = (uint32_t)((b - a + kBlock - 1) / kBlock);
+    uint64_t alg = 0;
+    uint32_t base = doc_lo;  // shard 0: 0, as in the reference
+    uint32_t delta[kBlock];
+    for (size_t s = a; s < b; s += kBlock) {
+      const int n = (int)std::min<size_t>(kBlock, b - s);
+      uint32_t dmax = 0, tmax = 0, p = base;
+      float mx = 0.f;
+      for (int i = 0; i < n; i++) {
+        const uint32_t doc = (*docs)[s + i], tf = (*tfs)[s + i];
+        const bool first = (s == a && i == 0);
+        if (doc >= ix.norms.size() || (first ? doc < p : doc <= p)) {
+          c->err = "doc ids not strictly increasing or out of range";
+          return false;
+        }
+        delta[i] = doc - p;
+        p = doc;
+        dmax |= delta[i];
+        tmax |= tf;
+        mx = std::max(mx, TfnUpper(tf, ix.norms[doc]));
+      }
+      const int dbits = std::max(1, BitWidth(dmax)), tbits = std::max(1, BitWidth(tmax));
+      BlockInfo bi;
+      bi.base_doc = base;
+      bi.payload_off16 = (uint32_t)(c->payload.size() / 16);
+      bi.bits = PackBits(dbits, tbits, n);
+      bi.max_tfn = mx;
+      PackStream(delta, n, dbits, &c->payload);
+      PackStream(tfs->data() + s, n, tbits, &c->payload);
+      c->blk_info.push_back(bi);
+      c->blk_last.push_back(p);
+      alg += StreamBytes(n, dbits) + StreamBytes(n, tbits) + 16;
+      base = p;
+    }
+    c->lists.push_back(li);
+    c->list_alg_bytes.push_back(alg);
+    c->postings += (int64_t)(b - a);
+    c->postings_global += (int64_t)df;
+    return true;
+  }
+
+  void BuildChunk(Chunk *c) {
+    std::vector<uint32_t> docs, tfs;
+    for (size_t t = c->term_begin; t < c->term_end; t++)
+      if (!BuildList(list_offs[t], c, &docs, &tfs)) return;
+  }
+};
+
+}  // namespace
+
+uint64_t TermDict::Hash(const char *s, size_t len) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (size_t i = 0; i < len; i++) { h ^= (uint8_t)s[i]; h *= 0x100000001b3ull; }
+  return h ^ (h >> 29);
+}
+
+void TermDict::Build(const std::vector<char> *arena, const std::vector<uint64_t> *offs) {
+  arena_ = arena;
+  offs_ = offs;
+  const size_t n = offs->size() - 1;
+  size_t cap = 16;
+  while (cap < 2 * n) cap <<= 1;
+  mask_ = cap - 1;
+  slots_.assign(cap, 0xFFFFFFFFu);
+  for (size_t t = 0; t < n; t++) {
+    const char *s = arena->data() + (*offs)[t];
+    const size_t len = (*offs)[t + 1] - (*offs)[t];
+    uint64_t h = Hash(s, len) & mask_;
+    while (slots_[h] != 0xFFFFFFFFu) h = (h + 1) & mask_;   // later duplicates never shadow
+    slots_[h] = (uint32_t)t;
+  }
+}
+
+uint32_t TermDict::Find(const char *s, size_t len) const {
+  if (!offs_) return 0xFFFFFFFFu;
+  uint64_t h = Hash(s, len) & mask_;
+  for (;;) {
+    const uint32_t t = slots_[h];
+    if (t == 0xFFFFFFFFu) return t;
+    const uint64_t a = (*offs_)[t], b = (*offs_)[t + 1];
+    if (b - a == len && memcmp(arena_->data() + a, s, len) == 0) return t;
+    h = (h + 1) & mask_;
+  }
+}
+
+bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
+                   HostIndex *out, std::string *err) {
+  HostIndex &ix = *out;
+  if (n_shards < 1 || shard < 0 || shard >= n_shards) { *err = "bad shard/n_shards"; return false; }
+  ix.shard = shard;
+  ix.n_shards = n_shards;
+
+  // ---- my.doc_length: DocLengthCharStore::Deserialize, doc_length_store.h:164-190
+  {
+    FileView f;
+    if (!f.Map(dir + "/my.doc_length") || f.size < 12) { *err = "cannot read my.doc_length"; return false; }
+    int32_t count;
+    memcpy(&count, f.data, 4);
+    memcpy(&ix.avg_len, f.data + 4, 8);
+    if (count < 0 || 12 + 5ull * count > f.size) { *err = "my.doc_length truncated"; return false; }
+    ix.norms.assign(count, 0);
+    ix.n_docs = 0;
+    const uint8_t *p = f.data + 12;
+    for (int i = 0; i < count; i++, p += 5) {
+      int32_t id;
+      memcpy(&id, p, 4);
+      if (id < 0) { *err = "negative doc id in my.doc_length"; return false; }
+      if ((size_t)id >= ix.norms.size()) ix.norms.resize(id + 1, 0);
+      ix.norms[id] = p[4];
+      ix.n_docs++;
+    }
+    // The reference indexes its 256-entry cache with a SIGNED char (scoring.h:65-69): norm
+    // bytes >= 128 (doc length >= 2^19 tokens) are undefined behaviour there; reject them.
+    for (uint8_t b : ix.norms)
+      if (b >= 128) { *err = "doc length >= 2^19 tokens is undefined in the reference"; return false; }
+  }
+  // Bm25Similarity::BuildCache, scoring.h:85-90 — k1*(1 - b + b*len/avg), left to right.
+  {
+    const double k1 = 1.2, b = 0.75;
+    for (int i = 0; i < 256; i++) {
+      const uint32_t m = i & 7;
+      const int sh = (i >> 3) - 1;
+      const uint32_t len = sh < 0 ? m : (m | 8u) << sh;   // Char4ToUint, utils.h:317-329
+      ix.cache[i] = k1 * (1 - b + b * len / ix.avg_len);
+    }
+  }
+  const int64_t N = (int64_t)ix.norms.size();
+  ix.doc_lo = (int32_t)(N * shard / n_shards);
+  ix.doc_hi = (int32_t)(N * (shard + 1) / n_shards);
+
+  // ---- my.tip: TermTrieIndex::Load, term_index.h:106-159; value = zone pages << 48 | offset
+  std::vector<uint64_t> list_offs;
+  {
+    FileView f;
+    if (!f.Map(dir + "/my.tip")) { *err = "cannot read my.tip"; return false; }
+    const uint8_t *p = f.data, *e = f.data + f.size;
+    ix.term_off.assign(1, 0);
+    while (p < e) {
+      if (p + 4 > e) { *err = "my.tip truncated"; return false; }
+      uint32_t len;
+      memcpy(&len, p, 4);
+      if (p + 4 + len + 8 > e) { *err = "my.tip truncated"; return false; }
+      ix.term_arena.insert(ix.term_arena.end(), p + 4, p + 4 + len);
+      ix.term_off.push_back(ix.term_arena.size());
+      uint64_t v;
+      memcpy(&v, p + 4 + len, 8);
+      list_offs.push_back(v & 0xffffffffffffull);
+      p += 4 + len + 8;
+    }
+  }
+  ix.dict.Build(&ix.term_arena, &ix.term_off);
+  const size_t n_terms = list_offs.size();
+
+  // ---- my.vacuum
+  FileView vac;
+  if (!vac.Map(dir + "/my.vacuum") || vac.size < 100 || vac.data[0] != 0x88) {
+    *err = "cannot read my.vacuum (or bad magic 0x88)";
+    return false;
+  }
+
+  std::vector<float> tfn_tab(64 * 256, 0.f);
+  for (int tf = 1; tf < 64; tf++)
+    for (int nb = 0; nb < 256; nb++) {
+      double x = (tf * (1.2 + 1)) / (tf + ix.cache[nb]);
+      float fl = (float)x;
+      if ((double)fl < x) fl = nextafterf(fl, INFINITY);
+      tfn_tab[tf * 256 + nb] = fl;
+    }
+
+  // Slice the terms into chunks of roughly equal FILE bytes (lists are laid out in my.tip
+  // order), processed by a dynamic pool so one huge list does not serialise the load.
+  std::vector<Chunk> chunks;
+  {
+    const uint64_t target = std::max<uint64_t>(1 << 20, vac.size / 1024);
+    size_t begin = 0;
+    while (begin < n_terms) {
+      size_t end = begin + 1;
+      while (end < n_terms && list_offs[end] - list_offs[begin] < target && end - begin < 65536) end++;
+      Chunk c;
+      c.term_begin = begin;
+      c.term_end = end;
+      chunks.push_back(std::move(c));
+      begin = end;
+    }
+  }
+  Builder builder{vac, list_offs, ix, tfn_tab.data(), (uint32_t)ix.doc_lo, (uint32_t)ix.doc_hi};
+  if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+  threads = (int)std::min<size_t>(threads, std::max<size_t>(1, chunks.size()));
+  std::atomic<size_t> next{0};
+  auto worker = [&]() {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= chunks.size()) return;
+      builder.BuildChunk(&chunks[i]);
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+  }
+  size_t tot_blocks = 0, tot_payload = 0;
+  for (auto &c : chunks) {
+    if (!c.err.empty()) { *err = c.err; return false; }
+    tot_blocks += c.blk_info.size();
+    tot_payload += c.payload.size();
+  }
+  if (tot_payload / 16 > 0xFFFFFFF0ull) { *err = "payload exceeds 64 GiB addressable by u32 offsets"; return false; }
+
+  // ---- concatenate chunk outputs (block indices and payload offsets re-based)
+  ix.lists.resize(n_terms);
+  ix.list_alg_bytes.resize(n_terms);
+  ix.blk_info.resize(tot_blocks);
+  ix.blk_last.resize(tot_blocks);
+  ix.payload.assign(tot_payload + 64, 0);   // tail pad: decoders may read one granule past
+  std::vector<size_t> blk_base(chunks.size()), pay_base(chunks.size());
+  size_t bb = 0, pb = 0;
+  for (size_t i = 0; i < chunks.size(); i++) {
+    blk_base[i] = bb;
+    pay_base[i] = pb;
+    bb += chunks[i].blk_info.size();
+    pb += chunks[i].payload.size();
+    ix.n_postings += chunks[i].postings;
+    ix.n_postings_global += chunks[i].postings_global;
+  }
+  next = 0;
+  auto merger = [&]() {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= chunks.size()) return;
+      Chunk &c = chunks[i];
+      const uint32_t b0 = (uint32_t)blk_base[i], p0 = (uint32_t)(pay_base[i] / 16);
+      for (size_t j = 0; j < c.lists.size(); j++) {
+        ListInfo li = c.lists[j];
+        li.first_block += b0;
+        ix.lists[c.term_begin + j] = li;
+        ix.list_alg_bytes[c.term_begin + j] = c.list_alg_bytes[j];
+      }
+      for (size_t j = 0; j < c.blk_info.size(); j++) {
+        BlockInfo bi = c.blk_info[j];
+        bi.payload_off16 += p0;
+        ix.blk_info[b0 + j] = bi;
+      }
+      if (!c.blk_last.empty())
+        memcpy(ix.blk_last.data() + b0, c.blk_last.data(), c.blk_last.size() * 4);
+      if (!c.payload.empty()) memcpy(ix.payload.data() + pay_base[i], c.payload.data(), c.payload.size());
+      Chunk().payload.swap(c.payload);
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(merger);
+    merger();
+    for (auto &t : pool) t.join();
+  }
+  return true;
+}
+
+}  // namespace wsr

@@ -1,0 +1,89 @@
+// Device-side structures shared by kernels.cu and wsr_capi.cu.
+#ifndef WSR_KERNELS_CUH
+#define WSR_KERNELS_CUH
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/wsr.h"
+
+namespace wsr {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreadsPerCta = kWarpsPerCta * 32;
+constexpr int kMaxFastK = 32;      // top-k held one entry per lane
+constexpr int kUnitBlocks = 16;    // driver-list blocks per warp work unit
+
+// Read-only view of the HBM-resident index (layout: host_index.h).
+struct DevIndexView {
+  const uint4 *payload;       // 16 B granules
+  const uint4 *blk_info;      // {base_doc, payload_off16, bits, max_tfn}
+  const uint32_t *blk_last;
+  const uint4 *lists;         // {first_block, n_blocks, df_shard, df_global}
+  const uint8_t *norms;
+  const double *cache;        // 256 entries
+  const double *idf;          // per term, calc_es_idf(N_global, df_global)
+  uint32_t n_terms;
+  uint32_t n_docs;
+};
+
+// One planned query. unit_begin = index of its first work unit in its class queue.
+struct DevQuery {
+  uint32_t term[WSR_MAX_TERMS];  // query order
+  uint32_t n_terms;              // 0 => produces nothing
+  uint32_t k;
+  uint32_t unit_begin;
+  uint32_t n_units;
+  uint32_t driver;               // position (query order) of the shortest list
+  uint32_t out_slot;             // index of the query in the caller's batch
+  uint32_t seg_begin;            // collect mode: first entry of its match segment
+  uint32_t cand_begin;           // multi-unit queries: first candidate slot (in units)
+};
+static_assert(sizeof(DevQuery) == 64, "DevQuery is 64 bytes");
+
+struct DevCounters {
+  unsigned long long decoded_postings;
+  unsigned long long touched_bytes;
+  unsigned long long matches;
+  unsigned long long units;
+  unsigned int next_unit[4];      // one dynamic queue per query class
+};
+
+struct BatchView {
+  const DevQuery *queries;     // class-sorted; class c occupies [class_begin[c], class_begin[c+1])
+  uint32_t class_begin[5];
+  uint32_t class_units[4];
+  wsr_hit *hits;               // n * k_stride
+  int32_t *n_hits;             // n
+  wsr_hit *cand;               // kMaxFastK entries per unit of every multi-unit query
+  int32_t *cand_n;             // one per such unit
+  unsigned long long *thr;     // per planned query: best known k-th score (double bits)
+  DevCounters *counters;
+  uint32_t k_stride;
+  // collect mode (k > kMaxFastK): every match is appended to the query's segment
+  int32_t *seg_doc;
+  double *seg_score;
+  uint32_t *seg_count;         // per planned query
+};
+
+// class ids
+enum { kClassOne = 0, kClassTwo = 1, kClassMany = 2, kClassCollect = 3 };
+
+void LaunchSearch(const DevIndexView &ix, const BatchView &b, int sm_count, cudaStream_t s);
+void LaunchMerge(const BatchView &b, const uint32_t *multi_queries, uint32_t n_multi,
+                 cudaStream_t s);
+void LaunchDecodeList(const DevIndexView &ix, uint32_t first_block, uint32_t n_blocks,
+                      uint32_t *docs, uint32_t *tfs, cudaStream_t s);
+void LaunchDecodeAll(const DevIndexView &ix, uint32_t n_blocks, unsigned long long *checksum,
+                     int sm_count, cudaStream_t s);
+void LaunchMergeShards(const wsr_hit *gathered, const int32_t *gathered_n, int n_shards,
+                       int n_queries, int k_stride, wsr_hit *out, int32_t *out_n,
+                       cudaStream_t s);
+// Collect mode epilogue: per query segment sort by (score desc, doc asc) and copy the first k.
+// seg_begin/seg_end: device arrays [n_collect]; tmp buffers sized like the segment arrays.
+size_t CollectSortTempBytes(uint32_t n_entries, uint32_t n_collect);
+void LaunchCollectFinish(const BatchView &b, uint32_t n_collect, uint32_t n_entries,
+                         uint32_t *seg_begin, uint32_t *seg_end, int32_t *tmp_doc,
+                         double *tmp_score, void *cub_tmp, size_t cub_tmp_bytes, cudaStream_t s);
+
+}  // namespace wsr
+#endif

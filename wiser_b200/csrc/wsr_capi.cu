@@ -1,0 +1,671 @@
+// C ABI of libwsr.so (include/wsr.h): index residency in HBM, the batched query scheduler
+// (host-side planning of warp work units + device queues), and result marshalling.
+// There is no CPU execution path: every search runs the CUDA kernels in kernels.cu, and every
+// entry point fails with WSR_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/wsr.h"
+#include "host_index.h"
+#include "kernels.cuh"
+
+using namespace wsr;
+
+namespace {
+
+thread_local std::string g_err;
+
+int Fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess)                                                            \
+      return Fail(WSR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));  \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t Ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+};
+
+template <typename T>
+struct PinnedBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t Ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 16;
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+};
+
+bool IsPinned(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+struct wsr_index {
+  HostIndex host;                 // dictionary + per-list metadata stay on the host
+  std::vector<double> idf;        // calc_es_idf per term (scoring.h:21-25), libm log on the host
+  int device = 0;
+  int sm_count = 148;
+  DevBuf<uint4> d_payload;
+  DevBuf<uint4> d_blk_info;
+  DevBuf<uint32_t> d_blk_last;
+  DevBuf<uint4> d_lists;
+  DevBuf<uint8_t> d_norms;
+  DevBuf<double> d_cache;
+  DevBuf<double> d_idf;
+  DevIndexView view;
+  int64_t n_blocks = 0, payload_bytes = 0, hbm_bytes = 0;
+  std::mutex pool_mu;
+  std::vector<wsr_batch *> pool;  // reusable batches for wsr_search / wsr_search_batch
+};
+
+struct wsr_batch {
+  wsr_index *idx = nullptr;
+  int n = 0;
+  int k_stride = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // host plan
+  std::vector<DevQuery> planned;
+  std::vector<uint32_t> multi;       // planned indices of multi-unit queries
+  uint32_t class_begin[5] = {0, 0, 0, 0, 0};
+  uint32_t class_units[4] = {0, 0, 0, 0};
+  uint32_t n_cand_units = 0, n_seg_entries = 0, n_collect = 0;
+  uint64_t listed_postings = 0, listed_bytes = 0;
+  uint32_t launches = 0;
+  // device
+  DevBuf<DevQuery> d_queries;
+  DevBuf<wsr_hit> d_hits;
+  DevBuf<int32_t> d_n_hits;
+  DevBuf<wsr_hit> d_cand;
+  DevBuf<int32_t> d_cand_n;
+  DevBuf<unsigned long long> d_thr;
+  DevBuf<DevCounters> d_counters;
+  DevBuf<uint32_t> d_multi;
+  DevBuf<int32_t> d_seg_doc, d_seg_doc_tmp;
+  DevBuf<double> d_seg_score, d_seg_score_tmp;
+  DevBuf<uint32_t> d_seg_count, d_seg_begin, d_seg_end;
+  DevBuf<uint8_t> d_cub_tmp;
+  size_t cub_tmp_bytes = 0;
+  // pinned staging for the host-buffer API
+  PinnedBuf<DevQuery> h_queries;
+  PinnedBuf<wsr_hit> h_hits;
+  PinnedBuf<int32_t> h_n_hits;
+  PinnedBuf<uint32_t> h_multi;
+  BatchView view;
+};
+
+namespace {
+
+// Host-side half of the batch scheduler: validates queries, picks each query's driver list,
+// cuts it into warp work units and groups queries into kernel classes.
+int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
+  wsr_index *ix = b->idx;
+  const uint32_t n_terms_index = (uint32_t)ix->host.lists.size();
+  b->n = n;
+  b->k_stride = k_stride;
+  b->planned.clear();
+  b->multi.clear();
+  b->listed_postings = b->listed_bytes = 0;
+  std::vector<DevQuery> cls[4];
+  for (int i = 0; i < n; i++) {
+    const wsr_query &q = queries[i];
+    if (q.n_terms > WSR_MAX_TERMS)
+      return Fail(WSR_ERR_UNSUPPORTED, "query has more than WSR_MAX_TERMS terms");
+    if ((int)q.k > k_stride) return Fail(WSR_ERR_ARG, "query k exceeds k_stride");
+    if (q.k == 0 || q.n_terms == 0) continue;            // vacuum_engine.h:206-208
+    bool ok = true;
+    uint32_t best = 0, best_df = 0xffffffffu;
+    for (uint32_t t = 0; t < q.n_terms; t++) {
+      const uint32_t id = q.term_ids[t];
+      if (id == WSR_TERM_ABSENT) { ok = false; break; }   // vacuum_engine.h:213-215
+      if (id >= n_terms_index) return Fail(WSR_ERR_ARG, "term id out of range");
+      const ListInfo &li = ix->host.lists[id];
+      if (li.df_shard == 0) ok = false;                   // nothing of this list on this shard
+      if (li.df_shard < best_df) { best_df = li.df_shard; best = t; }
+    }
+    if (!ok) continue;
+    DevQuery dq;
+    memset(&dq, 0, sizeof(dq));
+    for (uint32_t t = 0; t < q.n_terms; t++) {
+      dq.term[t] = q.term_ids[t];
+      b->listed_postings += ix->host.lists[q.term_ids[t]].df_shard;
+      b->listed_bytes += ix->host.list_alg_bytes[q.term_ids[t]];
+    }
+    dq.n_terms = q.n_terms;
+    dq.k = q.k;
+    dq.driver = best;
+    dq.out_slot = (uint32_t)i;
+    const ListInfo &drv = ix->host.lists[q.term_ids[best]];
+    dq.n_units = (drv.n_blocks + kUnitBlocks - 1) / kUnitBlocks;
+    int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
+            : q.n_terms == 1 ? kClassOne : q.n_terms == 2 ? kClassTwo : kClassMany;
+    cls[c].push_back(dq);
+  }
+  uint32_t cand = 0, seg = 0;
+  for (int c = 0; c < 4; c++) {
+    b->class_begin[c] = (uint32_t)b->planned.size();
+    uint32_t units = 0;
+    for (DevQuery &dq : cls[c]) {
+      dq.unit_begin = units;
+      units += dq.n_units;
+      if (c == kClassCollect) {
+        dq.seg_begin = seg;
+        const uint64_t cap = ix->host.lists[dq.term[dq.driver]].df_shard;
+        if ((uint64_t)seg + cap > 0xfffffff0ull) return Fail(WSR_ERR_UNSUPPORTED, "collect-mode batch too large");
+        seg += (uint32_t)cap;
+      } else if (dq.n_units > 1) {
+        dq.cand_begin = cand;
+        cand += dq.n_units;
+        b->multi.push_back((uint32_t)b->planned.size());
+      }
+      b->planned.push_back(dq);
+    }
+    b->class_units[c] = units;
+  }
+  b->class_begin[4] = (uint32_t)b->planned.size();
+  b->n_cand_units = cand;
+  b->n_seg_entries = seg;
+  b->n_collect = b->class_begin[4] - b->class_begin[kClassCollect];
+  return WSR_OK;
+}
+
+int UploadBatch(wsr_batch *b) {
+  const size_t np = b->planned.size();
+  CU(b->d_queries.Ensure(np + 1));
+  CU(b->d_hits.Ensure((size_t)b->n * b->k_stride + 1));
+  CU(b->d_n_hits.Ensure((size_t)b->n + 1));
+  CU(b->d_cand.Ensure((size_t)b->n_cand_units * kMaxFastK + 1));
+  CU(b->d_cand_n.Ensure((size_t)b->n_cand_units + 1));
+  CU(b->d_thr.Ensure(np + 1));
+  CU(b->d_counters.Ensure(1));
+  CU(b->d_multi.Ensure(b->multi.size() + 1));
+  if (b->n_collect) {
+    CU(b->d_seg_doc.Ensure(b->n_seg_entries + 1));
+    CU(b->d_seg_doc_tmp.Ensure(b->n_seg_entries + 1));
+    CU(b->d_seg_score.Ensure(b->n_seg_entries + 1));
+    CU(b->d_seg_score_tmp.Ensure(b->n_seg_entries + 1));
+    CU(b->d_seg_begin.Ensure(b->n_collect + 1));
+    CU(b->d_seg_end.Ensure(b->n_collect + 1));
+    b->cub_tmp_bytes = CollectSortTempBytes(b->n_seg_entries, b->n_collect);
+    CU(b->d_cub_tmp.Ensure(b->cub_tmp_bytes + 16));
+  }
+  CU(b->d_seg_count.Ensure(np + 1));
+  CU(b->h_queries.Ensure(np + 1));
+  CU(b->h_multi.Ensure(b->multi.size() + 1));
+  if (np) memcpy(b->h_queries.p, b->planned.data(), np * sizeof(DevQuery));
+  if (!b->multi.empty()) memcpy(b->h_multi.p, b->multi.data(), b->multi.size() * 4);
+  if (np) CU(cudaMemcpyAsync(b->d_queries.p, b->h_queries.p, np * sizeof(DevQuery),
+                             cudaMemcpyHostToDevice, b->stream));
+  if (!b->multi.empty())
+    CU(cudaMemcpyAsync(b->d_multi.p, b->h_multi.p, b->multi.size() * 4, cudaMemcpyHostToDevice,
+                       b->stream));
+  BatchView &v = b->view;
+  v.queries = b->d_queries.p;
+  for (int c = 0; c < 5; c++) v.class_begin[c] = b->class_begin[c];
+  for (int c = 0; c < 4; c++) v.class_units[c] = b->class_units[c];
+  v.hits = b->d_hits.p;
+  v.n_hits = b->d_n_hits.p;
+  v.cand = b->d_cand.p;
+  v.cand_n = b->d_cand_n.p;
+  v.thr = b->d_thr.p;
+  v.counters = b->d_counters.p;
+  v.k_stride = (uint32_t)b->k_stride;
+  v.seg_doc = b->d_seg_doc.p;
+  v.seg_score = b->d_seg_score.p;
+  v.seg_count = b->d_seg_count.p;
+  return WSR_OK;
+}
+
+// Enqueues one pass of the batch on its stream: counters reset, search kernels per class,
+// unit merge, collect-mode epilogue. No host<->device copies.
+int EnqueueRun(wsr_batch *b) {
+  const size_t np = b->planned.size();
+  uint32_t launches = 0;
+  CU(cudaMemsetAsync(b->d_n_hits.p, 0, (size_t)b->n * sizeof(int32_t) + 4, b->stream));
+  CU(cudaMemsetAsync(b->d_counters.p, 0, sizeof(DevCounters), b->stream));
+  if (!b->multi.empty()) CU(cudaMemsetAsync(b->d_thr.p, 0, np * 8, b->stream));
+  if (b->n_collect) CU(cudaMemsetAsync(b->d_seg_count.p, 0, np * 4, b->stream));
+  LaunchSearch(b->idx->view, b->view, b->idx->sm_count, b->stream);
+  for (int c = 0; c < 4; c++) launches += b->class_units[c] ? 1 : 0;
+  if (!b->multi.empty()) {
+    LaunchMerge(b->view, b->d_multi.p, (uint32_t)b->multi.size(), b->stream);
+    launches++;
+  }
+  if (b->n_collect) {
+    LaunchCollectFinish(b->view, b->n_collect, b->n_seg_entries, b->d_seg_begin.p, b->d_seg_end.p,
+                        b->d_seg_doc_tmp.p, b->d_seg_score_tmp.p, b->d_cub_tmp.p,
+                        b->cub_tmp_bytes, b->stream);
+    launches += 2;
+  }
+  b->launches = launches;
+  CU(cudaGetLastError());
+  return WSR_OK;
+}
+
+wsr_batch *NewBatch(wsr_index *idx) {
+  if (cudaSetDevice(idx->device) != cudaSuccess) return nullptr;
+  std::unique_ptr<wsr_batch> b(new wsr_batch);
+  b->idx = idx;
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess) return nullptr;
+  return b.release();
+}
+
+void FreeBatch(wsr_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->idx->device);
+  if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  delete b;
+}
+
+wsr_batch *AcquirePooled(wsr_index *idx) {
+  {
+    std::lock_guard<std::mutex> g(idx->pool_mu);
+    if (!idx->pool.empty()) {
+      wsr_batch *b = idx->pool.back();
+      idx->pool.pop_back();
+      return b;
+    }
+  }
+  return NewBatch(idx);
+}
+void ReleasePooled(wsr_index *idx, wsr_batch *b) {
+  std::lock_guard<std::mutex> g(idx->pool_mu);
+  idx->pool.push_back(b);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *wsr_last_error(void) { return g_err.c_str(); }
+
+int wsr_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void *wsr_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    Fail(WSR_ERR_CUDA, "cudaMallocHost failed");
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void wsr_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_shards,
+                          int loader_threads, char *err, size_t errlen) {
+  auto fail = [&](const std::string &m) -> wsr_index * {
+    g_err = m;
+    if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
+    return nullptr;
+  };
+  if (!vacuum_dir) return fail("vacuum_dir is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail("no CUDA device: libwsr has no CPU path");
+  }
+  if (device < 0 || device >= ndev) return fail("bad device ordinal");
+  std::unique_ptr<wsr_index> ix(new wsr_index);
+  std::string e;
+  if (!LoadVacuumDir(vacuum_dir, shard, n_shards, loader_threads, &ix->host, &e))
+    return fail(std::string(vacuum_dir) + ": " + e);
+  HostIndex &h = ix->host;
+  // idf per term: calc_es_idf(doc_count, doc_freq), scoring.h:21-25 — GLOBAL N and df
+  ix->idf.resize(h.lists.size());
+  for (size_t t = 0; t < h.lists.size(); t++) {
+    const int doc_count = h.n_docs, doc_freq = (int)h.lists[t].df_global;
+    ix->idf[t] = log(1 + (doc_count - doc_freq + 0.5) / (doc_freq + 0.5));
+  }
+  ix->device = device;
+  auto cu = [&](cudaError_t c, const char *what) -> bool {
+    if (c == cudaSuccess) return true;
+    e = std::string(what) + ": " + cudaGetErrorString(c);
+    return false;
+  };
+  cudaDeviceProp prop;
+  if (!cu(cudaSetDevice(device), "cudaSetDevice") ||
+      !cu(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"))
+    return fail(e);
+  ix->sm_count = prop.multiProcessorCount;
+  const size_t n_gran = h.payload.size() / 16;
+  if (!cu(ix->d_payload.Ensure(n_gran), "cudaMalloc payload") ||
+      !cu(ix->d_blk_info.Ensure(h.blk_info.size() + 1), "cudaMalloc blk_info") ||
+      !cu(ix->d_blk_last.Ensure(h.blk_last.size() + 1), "cudaMalloc blk_last") ||
+      !cu(ix->d_lists.Ensure(h.lists.size() + 1), "cudaMalloc lists") ||
+      !cu(ix->d_norms.Ensure(h.norms.size() + 1), "cudaMalloc norms") ||
+      !cu(ix->d_cache.Ensure(256), "cudaMalloc cache") ||
+      !cu(ix->d_idf.Ensure(ix->idf.size() + 1), "cudaMalloc idf"))
+    return fail(e);
+  if (!cu(cudaMemcpy(ix->d_payload.p, h.payload.data(), n_gran * 16, cudaMemcpyHostToDevice), "H2D payload") ||
+      !cu(cudaMemcpy(ix->d_blk_info.p, h.blk_info.data(), h.blk_info.size() * 16, cudaMemcpyHostToDevice), "H2D blk_info") ||
+      !cu(cudaMemcpy(ix->d_blk_last.p, h.blk_last.data(), h.blk_last.size() * 4, cudaMemcpyHostToDevice), "H2D blk_last") ||
+      !cu(cudaMemcpy(ix->d_lists.p, h.lists.data(), h.lists.size() * 16, cudaMemcpyHostToDevice), "H2D lists") ||
+      !cu(cudaMemcpy(ix->d_norms.p, h.norms.data(), h.norms.size(), cudaMemcpyHostToDevice), "H2D norms") ||
+      !cu(cudaMemcpy(ix->d_cache.p, h.cache, 256 * 8, cudaMemcpyHostToDevice), "H2D cache") ||
+      !cu(cudaMemcpy(ix->d_idf.p, ix->idf.data(), ix->idf.size() * 8, cudaMemcpyHostToDevice), "H2D idf"))
+    return fail(e);
+  ix->n_blocks = (int64_t)h.blk_info.size();
+  ix->payload_bytes = (int64_t)n_gran * 16;
+  ix->hbm_bytes = ix->payload_bytes + ix->n_blocks * 20 + (int64_t)h.lists.size() * 24 +
+                  (int64_t)h.norms.size() + 2048;
+  DevIndexView &v = ix->view;
+  v.payload = ix->d_payload.p;
+  v.blk_info = ix->d_blk_info.p;
+  v.blk_last = ix->d_blk_last.p;
+  v.lists = ix->d_lists.p;
+  v.norms = ix->d_norms.p;
+  v.cache = ix->d_cache.p;
+  v.idf = ix->d_idf.p;
+  v.n_terms = (uint32_t)h.lists.size();
+  v.n_docs = (uint32_t)h.n_docs;
+  // the block arrays now live in HBM only
+  std::vector<uint8_t>().swap(h.payload);
+  std::vector<BlockInfo>().swap(h.blk_info);
+  std::vector<uint32_t>().swap(h.blk_last);
+  return ix.release();
+}
+
+void wsr_index_close(wsr_index *idx) {
+  if (!idx) return;
+  cudaSetDevice(idx->device);
+  for (wsr_batch *b : idx->pool) FreeBatch(b);
+  delete idx;
+}
+
+int wsr_index_get_info(const wsr_index *idx, wsr_index_info *info) {
+  if (!idx || !info) return Fail(WSR_ERR_ARG, "null argument");
+  const HostIndex &h = idx->host;
+  info->n_docs = h.n_docs;
+  info->avg_doc_len = h.avg_len;
+  info->n_terms = (int64_t)h.lists.size();
+  info->n_postings = h.n_postings;
+  info->n_postings_global = h.n_postings_global;
+  info->n_blocks = idx->n_blocks;
+  info->hbm_bytes = idx->hbm_bytes;
+  info->payload_bytes = idx->payload_bytes;
+  info->shard = h.shard;
+  info->n_shards = h.n_shards;
+  info->doc_lo = h.doc_lo;
+  info->doc_hi = h.doc_hi;
+  info->device = idx->device;
+  return WSR_OK;
+}
+
+int wsr_term_lookup(const wsr_index *idx, const char *term, size_t len, uint32_t *term_id,
+                    uint32_t *df) {
+  if (!idx || !term) return Fail(WSR_ERR_ARG, "null argument");
+  const uint32_t t = idx->host.dict.Find(term, len);
+  if (term_id) *term_id = t;
+  if (t == WSR_TERM_ABSENT) {
+    if (df) *df = 0;
+    return 1;
+  }
+  if (df) *df = idx->host.lists[t].df_global;
+  return 0;
+}
+
+int wsr_term_at(const wsr_index *idx, uint32_t term_id, char *buf, size_t cap, uint32_t *df) {
+  if (!idx) return Fail(WSR_ERR_ARG, "null argument");
+  const HostIndex &h = idx->host;
+  if (term_id >= h.lists.size()) return Fail(WSR_ERR_ARG, "term id out of range");
+  const size_t a = h.term_off[term_id], b = h.term_off[term_id + 1];
+  if (buf) memcpy(buf, h.term_arena.data() + a, std::min(cap, b - a));
+  if (df) *df = h.lists[term_id].df_global;
+  return (int)(b - a);
+}
+
+int wsr_decode_list(wsr_index *idx, uint32_t term_id, uint32_t *docs, uint32_t *tfs, size_t cap,
+                    size_t *n) {
+  if (!idx || !n) return Fail(WSR_ERR_ARG, "null argument");
+  if (term_id >= idx->host.lists.size()) return Fail(WSR_ERR_ARG, "term id out of range");
+  CU(cudaSetDevice(idx->device));
+  const ListInfo li = idx->host.lists[term_id];
+  *n = li.df_shard;
+  if (li.n_blocks == 0 || cap == 0 || (!docs && !tfs)) return WSR_OK;
+  DevBuf<uint32_t> d_docs, d_tfs;
+  CU(d_docs.Ensure((size_t)li.n_blocks * 128));
+  CU(d_tfs.Ensure((size_t)li.n_blocks * 128));
+  LaunchDecodeList(idx->view, li.first_block, li.n_blocks, d_docs.p, d_tfs.p, 0);
+  CU(cudaGetLastError());
+  const size_t m = std::min<size_t>(cap, li.df_shard);
+  if (docs && m) CU(cudaMemcpy(docs, d_docs.p, m * 4, cudaMemcpyDeviceToHost));
+  if (tfs && m) CU(cudaMemcpy(tfs, d_tfs.p, m * 4, cudaMemcpyDeviceToHost));
+  CU(cudaDeviceSynchronize());
+  return WSR_OK;
+}
+
+int wsr_decode_all(wsr_index *idx, uint64_t *checksum, float *kernel_ms) {
+  if (!idx) return Fail(WSR_ERR_ARG, "null argument");
+  CU(cudaSetDevice(idx->device));
+  DevBuf<unsigned long long> d_sum;
+  CU(d_sum.Ensure(1));
+  CU(cudaMemset(d_sum.p, 0, 8));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, 0));
+  LaunchDecodeAll(idx->view, (uint32_t)idx->n_blocks, d_sum.p, idx->sm_count, 0);
+  CU(cudaEventRecord(e1, 0));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaGetLastError());
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  unsigned long long s = 0;
+  CU(cudaMemcpy(&s, d_sum.p, 8, cudaMemcpyDeviceToHost));
+  if (checksum) *checksum = s;
+  if (kernel_ms) *kernel_ms = ms;
+  return WSR_OK;
+}
+
+wsr_batch *wsr_batch_create(wsr_index *idx, const wsr_query *queries, int n, int k_stride) {
+  if (!idx || (!queries && n > 0) || n < 0 || k_stride < 1) {
+    Fail(WSR_ERR_ARG, "bad argument");
+    return nullptr;
+  }
+  wsr_batch *b = NewBatch(idx);
+  if (!b) { Fail(WSR_ERR_CUDA, "cannot create CUDA stream"); return nullptr; }
+  if (PlanBatch(b, queries, n, k_stride) != WSR_OK || UploadBatch(b) != WSR_OK ||
+      cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    FreeBatch(b);
+    return nullptr;
+  }
+  return b;
+}
+
+void wsr_batch_destroy(wsr_batch *b) { FreeBatch(b); }
+
+int wsr_batch_run(wsr_batch *b) {
+  if (!b) return Fail(WSR_ERR_ARG, "null batch");
+  CU(cudaSetDevice(b->idx->device));
+  return EnqueueRun(b);
+}
+
+int wsr_batch_sync(wsr_batch *b) {
+  if (!b) return Fail(WSR_ERR_ARG, "null batch");
+  CU(cudaSetDevice(b->idx->device));
+  CU(cudaStreamSynchronize(b->stream));
+  return WSR_OK;
+}
+
+int wsr_batch_fetch(wsr_batch *b, wsr_hit *hits, int32_t *n_hits) {
+  if (!b) return Fail(WSR_ERR_ARG, "null batch");
+  CU(cudaSetDevice(b->idx->device));
+  const size_t nh = (size_t)b->n * b->k_stride;
+  if (hits && nh) {
+    if (IsPinned(hits)) {
+      CU(cudaMemcpyAsync(hits, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+    } else {
+      CU(b->h_hits.Ensure(nh));
+      CU(cudaMemcpyAsync(b->h_hits.p, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+    }
+  }
+  if (n_hits && b->n) {
+    CU(b->h_n_hits.Ensure(b->n));
+    CU(cudaMemcpyAsync(b->h_n_hits.p, b->d_n_hits.p, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+  }
+  CU(cudaStreamSynchronize(b->stream));
+  if (hits && nh && !IsPinned(hits)) memcpy(hits, b->h_hits.p, nh * sizeof(wsr_hit));
+  if (n_hits && b->n) memcpy(n_hits, b->h_n_hits.p, (size_t)b->n * 4);
+  return WSR_OK;
+}
+
+int wsr_batch_device_results(wsr_batch *b, void **d_hits, void **d_n_hits, void **stream) {
+  if (!b) return Fail(WSR_ERR_ARG, "null batch");
+  if (d_hits) *d_hits = b->d_hits.p;
+  if (d_n_hits) *d_n_hits = b->d_n_hits.p;
+  if (stream) *stream = (void *)b->stream;
+  return WSR_OK;
+}
+
+int wsr_batch_time(wsr_batch *b, int iters, float *ms_per_iter) {
+  if (!b || iters < 1) return Fail(WSR_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(b->idx->device));
+  CU(cudaStreamSynchronize(b->stream));
+  CU(cudaEventRecord(b->ev0, b->stream));
+  for (int i = 0; i < iters; i++) {
+    int rc = EnqueueRun(b);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(b->ev1, b->stream));
+  CU(cudaEventSynchronize(b->ev1));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+  if (ms_per_iter) *ms_per_iter = ms / iters;
+  return WSR_OK;
+}
+
+int wsr_batch_get_stats(wsr_batch *b, wsr_batch_stats *s) {
+  if (!b || !s) return Fail(WSR_ERR_ARG, "null argument");
+  CU(cudaSetDevice(b->idx->device));
+  DevCounters c;
+  CU(cudaMemcpyAsync(&c, b->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  s->listed_postings = b->listed_postings;
+  s->listed_bytes = b->listed_bytes;
+  s->decoded_postings = c.decoded_postings;
+  s->touched_bytes = c.touched_bytes;
+  s->matches = c.matches;
+  s->work_units = c.units;
+  s->kernel_launches = b->launches;
+  return WSR_OK;
+}
+
+int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stride,
+                     wsr_hit *hits, int32_t *n_hits, uint32_t *doc_freqs,
+                     int32_t *n_doc_freqs) {
+  if (!idx || (!queries && n > 0) || n < 0 || k_stride < 1 || !hits || !n_hits)
+    return Fail(WSR_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(idx->device));
+  // doc_freqs: df of term i in query order, empty on the early-out paths (vacuum_engine.h:206-219)
+  if (doc_freqs || n_doc_freqs) {
+    for (int i = 0; i < n; i++) {
+      const wsr_query &q = queries[i];
+      bool ok = q.k > 0 && q.n_terms > 0 && q.n_terms <= WSR_MAX_TERMS;
+      for (uint32_t t = 0; ok && t < q.n_terms; t++)
+        ok = q.term_ids[t] != WSR_TERM_ABSENT && q.term_ids[t] < idx->host.lists.size();
+      if (n_doc_freqs) n_doc_freqs[i] = ok ? (int32_t)q.n_terms : 0;
+      if (doc_freqs && ok)
+        for (uint32_t t = 0; t < q.n_terms; t++)
+          doc_freqs[(size_t)i * WSR_MAX_TERMS + t] = idx->host.lists[q.term_ids[t]].df_global;
+    }
+  }
+  wsr_batch *b = AcquirePooled(idx);
+  if (!b) return Fail(WSR_ERR_CUDA, "cannot create batch");
+  int rc = PlanBatch(b, queries, n, k_stride);
+  if (rc == WSR_OK) rc = UploadBatch(b);
+  if (rc == WSR_OK) rc = EnqueueRun(b);
+  if (rc == WSR_OK) rc = wsr_batch_fetch(b, hits, n_hits);
+  ReleasePooled(idx, b);
+  return rc;
+}
+
+int wsr_search(wsr_index *idx, const char *const *terms, const size_t *term_lens, int n_terms,
+               int k, wsr_hit *hits, int *n_hits, uint32_t *doc_freqs, int *n_doc_freqs) {
+  if (!idx || n_terms < 0 || k < 0 || !n_hits) return Fail(WSR_ERR_ARG, "bad argument");
+  if (n_terms > WSR_MAX_TERMS) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
+  *n_hits = 0;
+  if (n_doc_freqs) *n_doc_freqs = 0;
+  if (k == 0 || n_terms == 0) return WSR_OK;               // vacuum_engine.h:206-215
+  wsr_query q;
+  memset(&q, 0, sizeof(q));
+  q.n_terms = (uint32_t)n_terms;
+  q.k = (uint32_t)k;
+  for (int t = 0; t < n_terms; t++) {
+    uint32_t id, df;
+    if (wsr_term_lookup(idx, terms[t], term_lens[t], &id, &df) != 0) return WSR_OK;  // missing term
+    q.term_ids[t] = id;
+  }
+  uint32_t dfs[WSR_MAX_TERMS];
+  int32_t ndf = 0, nh = 0;
+  int rc = wsr_search_batch(idx, &q, 1, k, hits, &nh, dfs, &ndf);
+  if (rc) return rc;
+  *n_hits = nh;
+  if (n_doc_freqs) *n_doc_freqs = ndf;
+  if (doc_freqs) for (int t = 0; t < ndf; t++) doc_freqs[t] = dfs[t];
+  return WSR_OK;
+}
+
+int wsr_merge_topk_device(const void *d_gathered_hits, const void *d_gathered_n_hits, int n_shards,
+                          int n_queries, int k_stride, void *d_out_hits, void *d_out_n_hits,
+                          void *stream) {
+  if (!d_gathered_hits || !d_gathered_n_hits || !d_out_hits || !d_out_n_hits || n_shards < 1 ||
+      n_queries < 0 || k_stride < 1)
+    return Fail(WSR_ERR_ARG, "bad argument");
+  LaunchMergeShards((const wsr_hit *)d_gathered_hits, (const int32_t *)d_gathered_n_hits, n_shards,
+                    n_queries, k_stride, (wsr_hit *)d_out_hits, (int32_t *)d_out_n_hits,
+                    (cudaStream_t)stream);
+  CU(cudaGetLastError());
+  return WSR_OK;
+}
+
+}  // extern "C"
