@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py — BM25 AND top-10 throughput of the GPU engine on a synthetic Zipf corpus.
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): English-Wikipedia-scale synthetic corpus
+(5M docs, ~1B postings, Zipf s=1 over 5M terms) written in the reference's vacuum format by
+wiser_b200/wsr_gen_corpus; query log = 100k unique two-term AND queries generated like the
+reference's gen_synthetic_log.py (tools/gen_query_log.py two_term), n_results = 10.
+One STEP = one pass of the whole query log through the engine.
+
+value  = listed postings/s (unit of SURVEY §8d: sum of the df of every query term), inputs
+         resident in HBM, device-timed with CUDA events on the launching stream.
+e2e    = the same metric through the host-buffer C-ABI call: query-log text -> term lookup ->
+         wsr_search_batch (H2D of the planned batch, kernels, D2H of the top-k) per step.
+roofline = algorithmic bytes of the blocks the dominant kernel actually read (B_touched,
+         SURVEY §8d) / its CUDA-event duration, against the measured HBM copy bandwidth.
+cpu_baseline = the unmodified reference engine (oracle/_ref/ref_tool, kind "reference"; the
+         CPU oracle port if that binary is absent) timed on the host cores on a bounded
+         sample of the same log against the same index directory.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GEN = os.path.join(ROOT, "wiser_b200", "wsr_gen_corpus")
+REF_TOOL = os.path.join(ROOT, "oracle", "_ref", "ref_tool")
+METRIC = "bm25_and_top10_listed_postings_per_s"
+UNIT = "postings/s"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--docs", type=int, default=5_000_000, help="documents PER GPU (weak scaling)")
+    ap.add_argument("--vocab", type=int, default=5_000_000)
+    ap.add_argument("--mu", type=float, default=5.34)
+    ap.add_argument("--queries", type=int, default=100_000)
+    ap.add_argument("--workload", default="two_term",
+                    choices=["two_term", "single_high", "single_low", "multi_term", "mix_aol"])
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--high-df", type=int, default=10000)
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="queries in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-sample", type=int, default=200)
+    ap.add_argument("--dir", default=os.environ.get("WSR_BENCH_DIR", "/tmp/wsr_bench"))
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+def ensure_corpus(a, part=0, n_parts=1):
+    """One partition of the corpus = a standalone vacuum index of a.docs documents."""
+    name = f"c_d{a.docs}_v{a.vocab}_mu{a.mu}_s{a.seed}_p{part}of{n_parts}"
+    d = os.path.join(a.dir, name)
+    done = os.path.join(d, "DONE.json")
+    if not os.path.exists(done):
+        os.makedirs(d, exist_ok=True)
+        if not os.path.exists(GEN):
+            raise RuntimeError(f"{GEN} missing: run __graft_entry__.build()")
+        t0 = time.time()
+        out = subprocess.check_output([GEN, "--out", d, "--docs", str(a.docs), "--vocab", str(a.vocab),
+                                       "--mu", str(a.mu), "--seed", str(a.seed * 1000 + part)])
+        info = json.loads(out.decode().strip().split("\n")[-1])
+        info["wall_s"] = time.time() - t0
+        with open(done, "w") as f:
+            json.dump(info, f)
+        log(f"generated {d}: {info}")
+    return d, json.load(open(done))
+
+
+def ensure_query_log(a, corpus_dir):
+    import gen_query_log
+    path = os.path.join(corpus_dir, f"q_{a.workload}_n{a.queries}_h{a.high_df}_s{a.seed}.txt")
+    if not os.path.exists(path):
+        t0 = time.time()
+        groups = gen_query_log.load_groups(os.path.join(corpus_dir, "terms.txt"), a.high_df)
+        qs = gen_query_log.generate(a.workload, groups, a.queries, a.seed)
+        with open(path + ".tmp", "w") as f:
+            for q in qs:
+                f.write(q + "\n")
+        os.replace(path + ".tmp", path)
+        log(f"query log {path}: {len(qs)} queries in {time.time() - t0:.1f}s "
+            f"(low={len(groups['low'])}, high={len(groups['high'])} terms)")
+    return path
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference_tool(corpus_dir, qlog, k, threads, reps, max_queries):
+    out = subprocess.run([REF_TOOL, "time", corpus_dir, qlog, str(k), str(threads), str(reps), str(max_queries)],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=1500)
+    for line in out.stdout.split("\n"):
+        if line.startswith("REF_TIME_JSON"):
+            return json.loads(line[len("REF_TIME_JSON"):])
+    raise RuntimeError("ref_tool produced no REF_TIME_JSON")
+
+
+def run_oracle_port(corpus_dir, qlog, k, threads, reps, max_queries):
+    """kind 'port': the CPU oracle restatement timed with its own multi-threaded replay."""
+    import ctypes as C
+    from oracle_py import OracleIndex, lib, parse_query_line
+    ix = OracleIndex(corpus_dir)
+    lines = open(qlog).read().split("\n")[:-1][:max_queries]
+    terms, offs = [], [0]
+    for l in lines:
+        terms += [t.encode() for t in parse_query_line(l)[0]]
+        offs.append(len(terms))
+    arr = (C.c_char_p * len(terms))(*terms)
+    lens = (C.c_size_t * len(terms))(*[len(t) for t in terms])
+    import numpy as np
+    qoff = np.array(offs, np.int64)
+    listed = C.c_uint64(0)
+    secs = []
+    for _ in range(reps):
+        secs.append(lib().wsr_oracle_time_batch(ix._h, arr, lens, qoff.ctypes.data, len(lines), k,
+                                                threads, C.byref(listed)))
+    best = min(secs)
+    return {"queries": len(lines), "threads": threads, "seconds": best, "qps": len(lines) / best,
+            "listed_postings": listed.value, "listed_postings_per_s": listed.value / best,
+            "rep_seconds": secs}
+
+
+def cpu_baseline(a, corpus_dir, qlog, reps=1):
+    threads = os.cpu_count() or 1
+    if os.path.exists(REF_TOOL):
+        kind, r = "reference", run_reference_tool(corpus_dir, qlog, a.k, threads, reps, a.cpu_sample)
+    else:
+        kind, r = "port", run_oracle_port(corpus_dir, qlog, a.k, threads, reps, a.cpu_sample)
+    return kind, threads, r
+
+
+def reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    corpus_dir, cinfo = ensure_corpus(a, 0, 1)
+    qlog = ensure_query_log(a, corpus_dir)
+    reps = a.warmup + a.steps
+    # keep the whole run within a few minutes: bound the sample by a quick probe
+    sample = a.cpu_sample
+    kind, threads, probe = cpu_baseline(argparse.Namespace(**{**vars(a), "cpu_sample": min(2000, sample)}),
+                                        corpus_dir, qlog, 1)
+    per_query = probe["seconds"] / max(1, probe["queries"])
+    budget_s = 150.0
+    sample = int(max(500, min(sample, budget_s / max(per_query, 1e-9) / reps)))
+    a2 = argparse.Namespace(**{**vars(a), "cpu_sample": sample})
+    kind, threads, r = cpu_baseline(a2, corpus_dir, qlog, reps)
+    timed = r["rep_seconds"][a.warmup:]
+    ms = 1000.0 * sum(timed) / len(timed)
+    value = r["listed_postings"] / (ms / 1000.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 scores / u32 doc ids", "data": "synthetic",
+        "config": workload_config(a, cinfo, sample_queries=sample),
+        "queries_per_s": r["queries"] / (ms / 1000.0),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"first {r['queries']} queries of the {a.workload} log per step, "
+                                   f"{threads} threads on one shared engine, index page-cache resident"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, cinfo, sample_queries=None, n_gpus=1):
+    return {
+        "workload": (f"C2 Wikipedia-scale synthetic Zipf corpus: {a.docs} docs x {n_gpus} GPU(s), "
+                     f"{cinfo['postings']} postings/partition, vocab {a.vocab}; "
+                     f"{a.workload} query log ({sample_queries or a.queries} queries/step, "
+                     f"gen_synthetic_log.py-style, high df >= {a.high_df}); BM25 AND top-{a.k}"),
+        "docs_per_gpu": a.docs, "postings_per_gpu": cinfo["postings"], "queries_per_step": sample_queries or a.queries,
+        "k": a.k, "partitioning": f"document-partitioned x{n_gpus}" if n_gpus > 1 else "single index",
+        "l2": "inputs larger than L2: one step streams GBs of distinct posting blocks (126 MB L2)",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+def ours(a, rank, world, local_rank):
+    import numpy as np
+    import torch
+    from wiser_b200 import Batch, GpuVacuumEngine
+    from wiser_b200.capi import HIT_DTYPE, PinnedArray
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    corpus_dir, cinfo = ensure_corpus(a, rank, world)
+    # every rank replays the SAME log (rank 0's), as every query goes to every shard
+    if world > 1:
+        objs = [None]
+        if rank == 0:
+            objs = [open(ensure_query_log(a, corpus_dir), "rb").read()]
+        dist.broadcast_object_list(objs, src=0)
+        text = objs[0]
+        qlog = None
+    else:
+        qlog = ensure_query_log(a, corpus_dir)
+        text = open(qlog, "rb").read()
+
+    t0 = time.time()
+    eng = GpuVacuumEngine(corpus_dir, device=local_rank).Load()
+    load_s = time.time() - t0
+    info = eng.info()
+    shard = None
+    if world > 1:
+        from wiser_b200.dist import ShardedSearch
+        shard = ShardedSearch(eng, rank, world)
+    qarr = eng.parse_query_log(text, a.k)
+    n = len(qarr)
+    batch = Batch(eng, qarr, a.k)
+    log(f"rank {rank}: index loaded in {load_s:.1f}s, {info.n_postings} postings, "
+        f"{info.hbm_bytes / 1e9:.2f} GB HBM, {n} queries")
+
+    def step():
+        batch.run()
+        if shard is not None:
+            shard.gather_merge(batch)
+
+    def sync_all():
+        batch.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(a.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stream = torch.cuda.ExternalStream(batch.device_results()[2])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_wall = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(a.steps):
+        step()
+    ev1.record(stream)
+    sync_all()
+    wall_ms = (time.perf_counter() - t_wall) * 1000.0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    ms_per_step = dev_ms / a.steps
+
+    st = batch.stats()
+    prof = batch.profile()
+    listed = int(st.listed_postings)
+    if world > 1:
+        t = torch.tensor([listed, int(st.touched_bytes), int(st.decoded_postings)], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        listed_all = int(t[0].item())
+    else:
+        listed_all = listed
+    value = listed_all / (ms_per_step / 1000.0)
+
+    # ---- roofline of the dominant kernel (this rank)
+    names = ["search_one_term", "search_two_term", "search_many_term", "search_collect", "merge_units"]
+    dom = max(range(4), key=lambda i: prof[i])
+    peak, peak_src = measured_peak_gbs()
+    achieved = st.touched_bytes / (prof[dom] / 1000.0) / 1e9 if prof[dom] > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": names[dom], "kernel_ms": prof[dom], "step_kernel_ms": prof,
+                "algorithmic_bytes_per_launch": int(st.touched_bytes), "peak_source": peak_src,
+                "listed_bytes_per_launch": int(st.listed_bytes),
+                "decoded_postings_per_s": st.decoded_postings / (prof[dom] / 1000.0) if prof[dom] > 0 else 0.0,
+                "bytes_per_decoded_posting": st.touched_bytes / max(1, st.decoded_postings)}
+
+    # ---- e2e through the host-buffer C ABI (term lookup + H2D + kernels + D2H every step)
+    hits_p = PinnedArray((n, a.k), HIT_DTYPE)
+    nh_p = PinnedArray((n,), np.int32)
+    e2e_steps = max(1, min(a.steps, 5))
+    for _ in range(2):
+        q2 = eng.parse_query_log(text, a.k)
+        eng.search_batch(q2, a.k, hits_p.array, nh_p.array)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        q2 = eng.parse_query_log(text, a.k)
+        eng.search_batch(q2, a.k, hits_p.array, nh_p.array)
+        if shard is not None:
+            shard.merge_host(hits_p.array, nh_p.array)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": listed_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 64 + 4 * n),
+           "d2h_bytes_per_step": int(n * a.k * 16 + n * 4), "ms_per_step": e2e_s * 1000.0,
+           "queries_per_s": n / e2e_s,
+           "path": "query-log text -> wsr_parse_query_log (term lookup) -> wsr_search_batch (pinned host buffers)"}
+
+    # ---- parity spot check against the CPU oracle (outside every timed region)
+    parity = None
+    if a.parity_sample > 0 and world == 1:
+        from oracle_py import OracleIndex, parse_query_line
+        from parity import check_topk
+        ora = OracleIndex(corpus_dir)
+        hits, nh = batch.fetch()
+        lines = text.decode().split("\n")
+        idxs = list(range(0, n, max(1, n // a.parity_sample)))[:a.parity_sample]
+        for i in idxs:
+            terms = parse_query_line(lines[i])[0]
+            rd, rs, _ = ora.search(terms, a.k)
+            fd, fs, _ = ora.search(terms, 1 << 30)
+            check_topk(rd, rs, hits["doc_id"][i, :nh[i]], hits["score"][i, :nh[i]], fd, fs, what=lines[i])
+        parity = {"queries_checked": len(idxs), "against": "CPU oracle (bit-exact scores, tie-aware docs)"}
+
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline and world == 1:
+        try:
+            kind, threads, r = cpu_baseline(a, corpus_dir, qlog, 1)
+            cpu = {"value": r["listed_postings_per_s"], "unit": UNIT, "cores": threads, "kind": kind,
+                   "queries_per_s": r["qps"], "seconds": r["seconds"],
+                   "sample": f"first {r['queries']} queries of the same log, {threads} threads on one shared "
+                             f"engine, same index directory (page-cache resident), k={a.k}"}
+        except Exception as e:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 scores / u32 doc ids", "data": "synthetic",
+            "config": workload_config(a, cinfo, n_gpus=world),
+            "queries_per_s": n / (ms_per_step / 1000.0),
+            "wall_ms_per_step": wall_ms / a.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(st.kernel_launches) * a.steps + (a.steps if world > 1 else 0),
+            "parity": parity,
+            "index": {"load_s": load_s, "hbm_bytes": int(info.hbm_bytes), "payload_bytes": int(info.payload_bytes),
+                      "blocks": int(info.n_blocks), "corpus_build_s": cinfo.get("wall_s")},
+            "matches_per_step": int(st.matches), "work_units_per_step": int(st.work_units),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.makedirs(a.dir, exist_ok=True)
+    if a.impl == "reference":
+        reference_arm(a, rank, world)
+        return
+    if world == 1 and a.gpus > 1:
+        log("--gpus > 1 expects a torchrun launch; running the single-GPU configuration")
+    ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -98,6 +98,13 @@ int wsr_term_lookup(const wsr_index *idx, const char *term, size_t len, uint32_t
 /* i-th term in my.tip order; returns its length (copies at most cap bytes), <0 on error. */
 int wsr_term_at(const wsr_index *idx, uint32_t term_id, char *buf, size_t cap, uint32_t *df);
 
+/* Query-log text -> wsr_query records (QueryProducerByLog's loader, query_pool.h:314-335):
+ * one query per line, terms separated by single spaces, a line wrapped in double quotes is a
+ * phrase (flags bit 0). Terms are looked up in the dictionary; absent terms get
+ * WSR_TERM_ABSENT. Every query gets n_results = k. */
+int wsr_parse_query_log(const wsr_index *idx, const char *text, size_t len, int k,
+                        wsr_query *out, int cap, int *n_out);
+
 /* ---- decode: VacuumPostingListIterator walk (flash_iterators.h:985-1016) -----------------
  * Decodes this shard's part of a posting list on the GPU into HOST buffers (doc ids and
  * term frequencies in list order). *n receives the number of postings on this shard; at
@@ -136,6 +143,11 @@ int wsr_batch_device_results(wsr_batch *b, void **d_hits, void **d_n_hits, void 
 /* Timed run: launches the batch `iters` times back to back and reports the average device
  * time per iteration measured with CUDA events on the batch stream. */
 int wsr_batch_time(wsr_batch *b, int iters, float *ms_per_iter);
+
+/* One pass with CUDA events around every launch group; ms[0..3] = search kernels of the
+ * single-term / two-term / 3+-term / collect classes, ms[4] = merge + collect epilogue,
+ * ms[5] = whole pass. */
+int wsr_batch_profile(wsr_batch *b, float ms[6]);
 
 /* Counters of the LAST run of this batch (read back from the device). */
 typedef struct {

@@ -1,0 +1,202 @@
+#include "gpu_vacuum_engine.h"
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+namespace wsr {
+
+namespace {
+[[noreturn]] void Fatal(const std::string &msg) {
+  // The reference reports misuse and corrupt input with LOG(FATAL), which aborts.
+  fprintf(stderr, "[F gpu_vacuum_engine] %s\n", msg.c_str());
+  abort();
+}
+}  // namespace
+
+struct GpuVacuumEngine::Pending {
+  wsr_query q;
+  std::vector<wsr_hit> hits;
+  int32_t n_hits = 0;
+  bool done = false;
+  int rc = 0;
+};
+
+GpuVacuumEngine::GpuVacuumEngine(const std::string engine_dir_path, int bloom_enable_factor,
+                                 GpuEngineOptions opt)
+    : dir_(engine_dir_path), bloom_enable_factor_(bloom_enable_factor), opt_(opt) {}
+
+GpuVacuumEngine::~GpuVacuumEngine() {
+  if (batcher_.joinable()) {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_submit_.notify_all();
+    batcher_.join();
+  }
+  if (idx_) wsr_index_close(idx_);
+}
+
+void GpuVacuumEngine::Load() {
+  if (idx_) Fatal("Engine is already loaded.");                     // vacuum_engine.h:145
+  char err[512] = {0};
+  idx_ = wsr_index_open(dir_.c_str(), opt_.device, opt_.shard, opt_.n_shards, opt_.loader_threads,
+                        err, sizeof(err));
+  if (!idx_) Fatal(std::string("wsr_index_open: ") + err);
+  batcher_ = std::thread([this]() { BatcherLoop(); });
+}
+
+int GpuVacuumEngine::TermCount() const {
+  wsr_index_info info;
+  if (!idx_ || wsr_index_get_info(idx_, &info) != 0) Fatal("Engine is not yet loaded");
+  return (int)info.n_terms;
+}
+
+std::map<std::string, int> GpuVacuumEngine::PostinglistSizes(const TermList &terms) {
+  std::map<std::string, int> ret;
+  for (auto &term : terms) {
+    uint32_t id, df;
+    if (wsr_term_lookup(idx_, term.data(), term.size(), &id, &df) == 0) ret[term] = (int)df;
+  }
+  return ret;
+}
+
+// Returns false when the reference would return the empty result early.
+bool GpuVacuumEngine::ToWsrQuery(const SearchQuery &q, wsr_query *out) const {
+  memset(out, 0, sizeof(*out));
+  if (q.n_results <= 0 || q.terms.empty()) return false;           // vacuum_engine.h:206-208
+  if (q.terms.size() > WSR_MAX_TERMS) Fatal("more than WSR_MAX_TERMS query terms");
+  if (q.is_phrase && q.terms.size() > 1) Fatal("phrase queries are not implemented on the GPU path yet");
+  out->n_terms = (uint32_t)q.terms.size();
+  out->k = (uint32_t)q.n_results;
+  for (size_t t = 0; t < q.terms.size(); t++) {
+    uint32_t id, df;
+    if (wsr_term_lookup(idx_, q.terms[t].data(), q.terms[t].size(), &id, &df) != 0)
+      return false;                                                  // vacuum_engine.h:213-215
+    out->term_ids[t] = id;
+  }
+  return true;
+}
+
+SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
+  SearchResult result;
+  if (!idx_) Fatal("Engine is not yet loaded");
+  Pending p;
+  if (!ToWsrQuery(query, &p.q)) return result;
+  for (size_t t = 0; t < query.terms.size(); t++) {                  // vacuum_engine.h:217-219
+    uint32_t id, df;
+    wsr_term_lookup(idx_, query.terms[t].data(), query.terms[t].size(), &id, &df);
+    result.doc_freqs.push_back((int)df);
+  }
+  p.hits.resize(p.q.k);
+  {
+    std::unique_lock<std::mutex> lk(mu_);
+    pending_.push_back(&p);
+    cv_submit_.notify_one();
+    cv_done_.wait(lk, [&]() { return p.done; });
+  }
+  if (p.rc != 0) Fatal(std::string("wsr_search_batch: ") + wsr_last_error());
+  for (int i = 0; i < p.n_hits; i++) {
+    SearchResultEntry e;
+    e.doc_id = p.hits[i].doc_id;
+    e.doc_score = p.hits[i].score;
+    result.entries.push_back(e);
+  }
+  return result;
+}
+
+// The batch scheduler's front half: gathers concurrent Search() callers for up to
+// coalesce_window_us (or coalesce_max_batch requests) and submits them as ONE GPU batch.
+void GpuVacuumEngine::BatcherLoop() {
+  std::vector<Pending *> take;
+  std::vector<wsr_query> qs;
+  std::vector<wsr_hit> hits;
+  std::vector<int32_t> n_hits;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_submit_.wait(lk, [&]() { return stop_ || !pending_.empty(); });
+      if (stop_ && pending_.empty()) return;
+      if ((int)pending_.size() < opt_.coalesce_max_batch && opt_.coalesce_window_us > 0) {
+        cv_submit_.wait_for(lk, std::chrono::microseconds(opt_.coalesce_window_us), [&]() {
+          return stop_ || (int)pending_.size() >= opt_.coalesce_max_batch;
+        });
+      }
+      take.swap(pending_);
+    }
+    uint32_t k_stride = 1;
+    qs.clear();
+    for (Pending *p : take) {
+      qs.push_back(p->q);
+      if (p->q.k > k_stride) k_stride = p->q.k;
+    }
+    hits.resize(qs.size() * (size_t)k_stride);
+    n_hits.assign(qs.size(), 0);
+    const int rc = wsr_search_batch(idx_, qs.data(), (int)qs.size(), (int)k_stride, hits.data(),
+                                    n_hits.data(), nullptr, nullptr);
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      for (size_t i = 0; i < take.size(); i++) {
+        Pending *p = take[i];
+        p->rc = rc;
+        p->n_hits = rc == 0 ? n_hits[i] : 0;
+        for (int j = 0; j < p->n_hits; j++) p->hits[j] = hits[i * (size_t)k_stride + j];
+        p->done = true;
+      }
+    }
+    cv_done_.notify_all();
+    take.clear();
+  }
+}
+
+std::vector<SearchResult> GpuVacuumEngine::SearchBatch(const std::vector<SearchQuery> &queries) {
+  std::vector<SearchResult> out(queries.size());
+  std::vector<wsr_query> qs(queries.size());
+  uint32_t k_stride = 1;
+  for (size_t i = 0; i < queries.size(); i++) {
+    if (ToWsrQuery(queries[i], &qs[i])) {
+      for (auto &t : queries[i].terms) {
+        uint32_t id, df;
+        wsr_term_lookup(idx_, t.data(), t.size(), &id, &df);
+        out[i].doc_freqs.push_back((int)df);
+      }
+      if (qs[i].k > k_stride) k_stride = qs[i].k;
+    } else {
+      memset(&qs[i], 0, sizeof(wsr_query));
+    }
+  }
+  std::vector<wsr_hit> hits(queries.size() * (size_t)k_stride);
+  std::vector<int32_t> n_hits(queries.size(), 0);
+  if (wsr_search_batch(idx_, qs.data(), (int)qs.size(), (int)k_stride, hits.data(), n_hits.data(),
+                       nullptr, nullptr) != 0)
+    Fatal(std::string("wsr_search_batch: ") + wsr_last_error());
+  for (size_t i = 0; i < queries.size(); i++)
+    for (int j = 0; j < n_hits[i]; j++) {
+      SearchResultEntry e;
+      e.doc_id = hits[i * (size_t)k_stride + j].doc_id;
+      e.doc_score = hits[i * (size_t)k_stride + j].score;
+      out[i].entries.push_back(e);
+    }
+  return out;
+}
+
+void GpuVacuumEngine::AddDocument(const DocInfo) { Fatal("Not implemented in VacuumEngine."); }
+int GpuVacuumEngine::LoadLocalDocuments(const std::string &, int, const std::string) {
+  Fatal("Not implemented in VacuumEngine.");
+}
+void GpuVacuumEngine::Serialize(std::string) const { Fatal("Not implemented in VacuumEngine."); }
+void GpuVacuumEngine::Deserialize(std::string) { Fatal("Not implemented in VacuumEngine."); }
+
+std::unique_ptr<SearchEngineServiceNew> CreateSearchEngine(std::string engine_type,
+                                                           int bloom_enable_factor) {
+  const std::string prefix = "gpu:vacuum_dump:";
+  if (engine_type.compare(0, prefix.size(), prefix) == 0)
+    return std::unique_ptr<SearchEngineServiceNew>(
+        new GpuVacuumEngine(engine_type.substr(prefix.size()), bloom_enable_factor));
+  throw std::runtime_error("Wrong engine type: " + engine_type);     // engine_factory.h:47
+}
+
+}  // namespace wsr

@@ -654,9 +654,10 @@ __global__ void SegEndKernel(const BatchView bv, uint32_t q_begin, uint32_t n_co
 
 }  // namespace
 
-void LaunchSearch(const DevIndexView &ix, const BatchView &b, int sm_count, cudaStream_t s) {
+void LaunchSearchClass(const DevIndexView &ix, const BatchView &b, int c, int sm_count,
+                       cudaStream_t s) {
   const int ctas_per_sm = 4;
-  for (int c = 0; c < 4; c++) {
+  {
     const uint32_t nu = b.class_units[c];
     if (nu) {
       const uint32_t want = (nu + kWarpsPerCta - 1) / kWarpsPerCta;

@@ -68,7 +68,8 @@ struct BatchView {
 // class ids
 enum { kClassOne = 0, kClassTwo = 1, kClassMany = 2, kClassCollect = 3 };
 
-void LaunchSearch(const DevIndexView &ix, const BatchView &b, int sm_count, cudaStream_t s);
+void LaunchSearchClass(const DevIndexView &ix, const BatchView &b, int cls, int sm_count,
+                       cudaStream_t s);
 void LaunchMerge(const BatchView &b, const uint32_t *multi_queries, uint32_t n_multi,
                  cudaStream_t s);
 void LaunchDecodeList(const DevIndexView &ix, uint32_t first_block, uint32_t n_blocks,

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -258,15 +259,21 @@ int UploadBatch(wsr_batch *b) {
 
 // Enqueues one pass of the batch on its stream: counters reset, search kernels per class,
 // unit merge, collect-mode epilogue. No host<->device copies.
-int EnqueueRun(wsr_batch *b) {
+int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr) {
+  // ev (optional, 6 events): [0] start, [1] after class one, [2] two, [3] many, [4] collect,
+  // [5] after merge + collect epilogue
   const size_t np = b->planned.size();
   uint32_t launches = 0;
   CU(cudaMemsetAsync(b->d_n_hits.p, 0, (size_t)b->n * sizeof(int32_t) + 4, b->stream));
   CU(cudaMemsetAsync(b->d_counters.p, 0, sizeof(DevCounters), b->stream));
   if (!b->multi.empty()) CU(cudaMemsetAsync(b->d_thr.p, 0, np * 8, b->stream));
   if (b->n_collect) CU(cudaMemsetAsync(b->d_seg_count.p, 0, np * 4, b->stream));
-  LaunchSearch(b->idx->view, b->view, b->idx->sm_count, b->stream);
-  for (int c = 0; c < 4; c++) launches += b->class_units[c] ? 1 : 0;
+  if (ev) CU(cudaEventRecord(ev[0], b->stream));
+  for (int c = 0; c < 4; c++) {
+    LaunchSearchClass(b->idx->view, b->view, c, b->idx->sm_count, b->stream);
+    if (ev) CU(cudaEventRecord(ev[1 + c], b->stream));
+    launches += b->class_units[c] ? 1 : 0;
+  }
   if (!b->multi.empty()) {
     LaunchMerge(b->view, b->d_multi.p, (uint32_t)b->multi.size(), b->stream);
     launches++;
@@ -277,6 +284,7 @@ int EnqueueRun(wsr_batch *b) {
                         b->cub_tmp_bytes, b->stream);
     launches += 2;
   }
+  if (ev) CU(cudaEventRecord(ev[5], b->stream));
   b->launches = launches;
   CU(cudaGetLastError());
   return WSR_OK;
@@ -581,6 +589,61 @@ int wsr_batch_time(wsr_batch *b, int iters, float *ms_per_iter) {
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
   if (ms_per_iter) *ms_per_iter = ms / iters;
+  return WSR_OK;
+}
+
+int wsr_batch_profile(wsr_batch *b, float ms[6]) {
+  if (!b || !ms) return Fail(WSR_ERR_ARG, "null argument");
+  CU(cudaSetDevice(b->idx->device));
+  cudaEvent_t ev[6];
+  for (int i = 0; i < 6; i++) CU(cudaEventCreate(&ev[i]));
+  int rc = EnqueueRun(b, ev);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(b->stream));
+  for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  CU(cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
+  for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
+  return WSR_OK;
+}
+
+int wsr_parse_query_log(const wsr_index *idx, const char *text, size_t len, int k,
+                        wsr_query *out, int cap, int *n_out) {
+  if (!idx || (!text && len) || !out || !n_out || k < 0) return Fail(WSR_ERR_ARG, "bad argument");
+  int n = 0;
+  size_t p = 0;
+  while (p < len) {
+    size_t e = p;
+    while (e < len && text[e] != '\n') e++;
+    // utils::trim + phrase quotes (query_pool.h:251-311)
+    size_t a = p, b = e;
+    while (a < b && isspace((unsigned char)text[a])) a++;
+    while (b > a && isspace((unsigned char)text[b - 1])) b--;
+    uint32_t flags = 0;
+    if (b - a >= 1 && text[a] == '"' && text[b - 1] == '"') {
+      flags = 1;
+      a++;
+      if (b > a) b--;
+    }
+    if (n >= cap) return Fail(WSR_ERR_ARG, "query buffer too small");
+    wsr_query &q = out[n];
+    memset(&q, 0, sizeof(q));
+    q.k = (uint32_t)k;
+    q.flags = flags;
+    size_t t = a;
+    while (t < b) {                      // utils::explode(line, ' '): empty pieces dropped
+      while (t < b && text[t] == ' ') t++;
+      size_t u = t;
+      while (u < b && text[u] != ' ') u++;
+      if (u > t) {
+        if (q.n_terms >= WSR_MAX_TERMS) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
+        q.term_ids[q.n_terms++] = idx->host.dict.Find(text + t, u - t);
+      }
+      t = u;
+    }
+    n++;
+    p = e + 1;
+  }
+  *n_out = n;
   return WSR_OK;
 }
 

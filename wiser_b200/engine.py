@@ -159,6 +159,15 @@ class GpuVacuumEngine:
             arr["k"][i] = q.n_results
         return arr
 
+    def parse_query_log(self, text: bytes, k: int) -> np.ndarray:
+        """wsr_parse_query_log: raw log text -> wsr_query records (term lookup in C)."""
+        cap = text.count(b"\n") + 2
+        arr = np.zeros(cap, QUERY_DTYPE)
+        n = C.c_int(0)
+        check(lib().wsr_parse_query_log(self._h, text, len(text), k, arr.ctypes.data, cap,
+                                        C.byref(n)))
+        return arr[:n.value]
+
     def search_batch(self, qarr: np.ndarray, k_stride: int, hits=None, n_hits=None,
                      want_doc_freqs=False):
         """wsr_search_batch over host buffers -> (hits[n,k_stride], n_hits[n], dfs, n_dfs)."""
@@ -265,6 +274,11 @@ class Batch:
             n_hits = np.zeros(self.n, np.int32)
         check(lib().wsr_batch_fetch(self._b, hits.ctypes.data, n_hits.ctypes.data))
         return hits, n_hits
+
+    def profile(self):
+        ms = (C.c_float * 6)()
+        check(lib().wsr_batch_profile(self._b, C.byref(ms)))
+        return [float(x) for x in ms]
 
     def stats(self) -> capi.BatchStats:
         s = capi.BatchStats()
