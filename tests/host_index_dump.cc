@@ -11,11 +11,33 @@
 
 using namespace wsr;
 
-static uint32_t GetBits(const uint8_t *s, uint64_t bit, int bits) {
-  uint64_t w = 0;
-  memcpy(&w, s + (bit >> 3), 8);   // payload has a 64-byte tail pad
-  uint64_t mask = bits == 32 ? 0xffffffffull : ((1ull << bits) - 1);
-  return (uint32_t)((w >> (bit & 7)) & mask);
+// Host restatement of the lane-major block layout documented in host_index.h (test only).
+static void DecodeBlock(const HostIndex &ix, const BlockInfo &bi, uint32_t *docs, uint32_t *tfs, int *n_out) {
+  const BlockShape sh = UnpackShape(bi.bits);
+  const uint8_t *p = ix.payload.data() + (size_t)bi.payload_off16 * 16;
+  const uint8_t *pt = p + sh.doc_bytes();
+  const int R = sh.rec_words();
+  const uint64_t m0 = sh.w0 == 32 ? 0xffffffffull : ((1ull << sh.w0) - 1);
+  const uint64_t mb = sh.b == 32 ? 0xffffffffull : ((1ull << sh.b) - 1);
+  for (int l = 0; l < sh.nl(); l++) {
+    unsigned __int128 x = 0;
+    for (int k = 0; k < R; k++) {
+      uint32_t w;
+      memcpy(&w, p + (size_t)(l * R + k) * 4, 4);
+      x |= (unsigned __int128)w << (32 * k);
+    }
+    uint32_t d = bi.base_doc + (uint32_t)((uint64_t)x & m0);
+    x >>= sh.w0;
+    for (int i = 0; i < 4; i++) {
+      if (i) { d += (uint32_t)((uint64_t)x & mb); x >>= sh.b; }
+      uint32_t tf;
+      if (sh.tcode == 0) { uint16_t v; memcpy(&v, pt + 2 * l, 2); tf = (v >> (4 * i)) & 15; }
+      else if (sh.tcode == 1) { uint32_t v; memcpy(&v, pt + 4 * l, 4); tf = (v >> (8 * i)) & 255; }
+      else { memcpy(&tf, pt + 16 * l + 4 * i, 4); }
+      if (4 * l + i < sh.n) { docs[4 * l + i] = d; tfs[4 * l + i] = tf; }
+    }
+  }
+  *n_out = sh.n;
 }
 
 int main(int argc, char **argv) {
@@ -36,16 +58,14 @@ int main(int argc, char **argv) {
     uint32_t total = 0;
     for (uint32_t b = 0; b < li.n_blocks; b++) {
       const BlockInfo &bi = ix.blk_info[li.first_block + b];
-      int dbits = bi.bits & 63, tbits = (bi.bits >> 6) & 63, n = ((bi.bits >> 12) & 127) + 1;
-      const uint8_t *p = ix.payload.data() + (size_t)bi.payload_off16 * 16;
-      const uint8_t *pt = p + StreamBytes(n, dbits);
-      uint32_t doc = bi.base_doc;
+      uint32_t docs[128], tfs[128];
+      int n;
+      DecodeBlock(ix, bi, docs, tfs, &n);
       for (int i = 0; i < n; i++) {
-        doc += GetBits(p, (uint64_t)i * dbits, dbits);
-        uint32_t rec[2] = {doc, GetBits(pt, (uint64_t)i * tbits, tbits)};
+        uint32_t rec[2] = {docs[i], tfs[i]};
         fwrite(rec, 4, 2, out);
       }
-      if (doc != ix.blk_last[li.first_block + b]) { fprintf(stderr, "blk_last mismatch\n"); return 3; }
+      if (docs[n - 1] != ix.blk_last[li.first_block + b]) { fprintf(stderr, "blk_last mismatch\n"); return 3; }
       total += n;
     }
     if (total != li.df_shard) { fprintf(stderr, "df mismatch\n"); return 4; }

@@ -92,25 +92,37 @@ bool ReadBlob(const uint8_t *file, size_t file_size, uint64_t off, int n, uint32
   return false;
 }
 
-// Appends n values as an LSB-first b-bit stream padded to 16 bytes.
-void PackStream(const uint32_t *v, int n, int bits, std::vector<uint8_t> *out) {
-  const size_t nbytes = StreamBytes(n, bits);
+// Appends the doc records of one block: per lane [f:w0][d1:b][d2:b][d3:b] LSB first in R words.
+void PackDocRecords(const uint32_t *first, const uint32_t (*deltas)[3], int nl, const BlockShape &sh,
+                    std::vector<uint8_t> *out) {
   const size_t at = out->size();
-  out->resize(at + nbytes, 0);
+  out->resize(at + sh.doc_bytes(), 0);
+  uint32_t *w = reinterpret_cast<uint32_t *>(out->data() + at);
+  const int R = sh.rec_words();
+  for (int l = 0; l < nl; l++) {
+    unsigned __int128 x = first[l];
+    int sft = sh.w0;
+    for (int i = 0; i < 3; i++) { x |= (unsigned __int128)deltas[l][i] << sft; sft += sh.b; }
+    for (int k = 0; k < R; k++) w[l * R + k] = (uint32_t)(x >> (32 * k));
+  }
+}
+
+// Appends the tf records of one block: 4 tfs per lane at 4 / 8 / 32 bits each.
+void PackTfRecords(const uint32_t (*tf)[4], int nl, const BlockShape &sh, std::vector<uint8_t> *out) {
+  const size_t at = out->size();
+  out->resize(at + sh.tf_bytes(), 0);
   uint8_t *d = out->data() + at;
-  uint64_t acc = 0;
-  int have = 0;
-  size_t w = 0;
-  for (int i = 0; i < n; i++) {
-    acc |= (uint64_t)v[i] << have;
-    have += bits;
-    while (have >= 8) {
-      d[w++] = (uint8_t)acc;
-      acc >>= 8;
-      have -= 8;
+  for (int l = 0; l < nl; l++) {
+    if (sh.tcode == 0) {
+      const uint16_t v = (uint16_t)(tf[l][0] | tf[l][1] << 4 | tf[l][2] << 8 | tf[l][3] << 12);
+      memcpy(d + 2 * l, &v, 2);
+    } else if (sh.tcode == 1) {
+      const uint32_t v = tf[l][0] | tf[l][1] << 8 | tf[l][2] << 16 | tf[l][3] << 24;
+      memcpy(d + 4 * l, &v, 4);
+    } else {
+      memcpy(d + 16 * l, tf[l], 16);
     }
   }
-  if (have > 0) d[w++] = (uint8_t)acc;
 }
 
 struct Chunk {               // output of one slice of terms
@@ -184,35 +196,50 @@ struct Builder {
     li.n_blocks = (uint32_t)((b - a + kBlock - 1) / kBlock);
     uint64_t alg = 0;
     uint32_t base = doc_lo;  // shard 0: 0, as in the reference
-    uint32_t delta[kBlock];
     for (size_t s = a; s < b; s += kBlock) {
       const int n = (int)std::min<size_t>(kBlock, b - s);
-      uint32_t dmax = 0, tmax = 0, p = base;
+      const int nl = (n + 3) / 4;
+      uint32_t first[32], deltas[32][3], tfr[32][4];
+      uint32_t fmax = 0, dmax = 0, tmax = 0, refmax = 0, p = base;
       float mx = 0.f;
       for (int i = 0; i < n; i++) {
         const uint32_t doc = (*docs)[s + i], tf = (*tfs)[s + i];
-        const bool first = (s == a && i == 0);
-        if (doc >= ix.norms.size() || (first ? doc < p : doc <= p)) {
+        const bool very_first = (s == a && i == 0);
+        if (doc >= ix.norms.size() || (very_first ? doc < p : doc <= p)) {
           c->err = "doc ids not strictly increasing or out of range";
           return false;
         }
-        delta[i] = doc - p;
-        p = doc;
-        dmax |= delta[i];
+        refmax |= doc - p;                      // the reference packs consecutive deltas
+        if ((i & 3) == 0) { first[i >> 2] = doc - base; fmax |= doc - base; }
+        else { deltas[i >> 2][(i & 3) - 1] = doc - p; dmax |= doc - p; }
+        tfr[i >> 2][i & 3] = tf;
         tmax |= tf;
+        p = doc;
         mx = std::max(mx, TfnUpper(tf, ix.norms[doc]));
       }
-      const int dbits = std::max(1, BitWidth(dmax)), tbits = std::max(1, BitWidth(tmax));
+      for (int i = n; i < 4 * nl; i++) {         // pad the last record with the last posting
+        deltas[i >> 2][(i & 3) - 1] = 0;
+        tfr[i >> 2][i & 3] = (*tfs)[s + n - 1];
+      }
+      BlockShape sh;
+      sh.w0 = std::max(1, BitWidth(fmax));
+      sh.b = std::max(1, BitWidth(dmax));
+      sh.n = n;
+      const int rec_bits = sh.w0 + 3 * sh.b;
+      sh.rcode = rec_bits <= 32 ? 0 : rec_bits <= 64 ? 1 : 2;
+      sh.tcode = tmax < 16 ? 0 : tmax < 256 ? 1 : 2;
+      sh.ref_dbits = std::max(1, BitWidth(refmax));
+      sh.ref_tbits = std::max(1, BitWidth(tmax));
       BlockInfo bi;
       bi.base_doc = base;
       bi.payload_off16 = (uint32_t)(c->payload.size() / 16);
-      bi.bits = PackBits(dbits, tbits, n);
+      bi.bits = PackShape(sh);
       bi.max_tfn = mx;
-      PackStream(delta, n, dbits, &c->payload);
-      PackStream(tfs->data() + s, n, tbits, &c->payload);
+      PackDocRecords(first, deltas, nl, sh, &c->payload);
+      PackTfRecords(tfr, nl, sh, &c->payload);
       c->blk_info.push_back(bi);
       c->blk_last.push_back(p);
-      alg += StreamBytes(n, dbits) + StreamBytes(n, tbits) + 16;
+      alg += AlgorithmicBytes(sh);
       base = p;
     }
     c->lists.push_back(li);
@@ -390,13 +417,14 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
     tot_payload += c.payload.size();
   }
   if (tot_payload / 16 > 0xFFFFFFF0ull) { *err = "payload exceeds 64 GiB addressable by u32 offsets"; return false; }
+  if (tot_blocks >= (1ull << 25)) { *err = "more than 2^25 blocks on one shard (hit records pack block<<7|slot)"; return false; }
 
   // ---- concatenate chunk outputs (block indices and payload offsets re-based)
   ix.lists.resize(n_terms);
   ix.list_alg_bytes.resize(n_terms);
   ix.blk_info.resize(tot_blocks);
   ix.blk_last.resize(tot_blocks);
-  ix.payload.assign(tot_payload + 64, 0);   // tail pad: decoders may read one granule past
+  ix.payload.assign(tot_payload + 1024, 0);  // tail pad: prefetchers read up to 512 B past a block
   std::vector<size_t> blk_base(chunks.size()), pay_base(chunks.size());
   size_t bb = 0, pb = 0;
   for (size_t i = 0; i < chunks.size(); i++) {

@@ -1,16 +1,29 @@
 // Host-side image of the HBM index layout, and the loader that builds it from a vacuum
 // index directory (my.tip / my.vacuum / my.doc_length).
 //
-// HBM layout (all arrays flat, one cudaMalloc each):
-//   payload   u8[]      per block: doc-id delta bitstream then tf bitstream, each the
-//                       reference's LSB-first little-endian b-bit stream (value i at bit i*b,
-//                       packed_value.h:87-128), each padded to 16 B; full blocks are 16*b B.
-//   blk_info  uint4[]   {base_doc, payload_off/16, bits(dbits|tbits<<6|(n-1)<<12), max_tfn f32}
-//                       base_doc = doc id the first delta is relative to (skip row
-//                       previous_doc_id, flash_containers.h:22-30; shard lower bound for the
-//                       first block of a shard); max_tfn = upper bound of
+// HBM layout (all arrays flat, one cudaMalloc each). A block holds up to 128 postings and is
+// LANE-MAJOR: lane l of the decoding warp owns postings 4l..4l+3, so a block decodes with one
+// coalesced record load per lane and three lane-local adds — no shared-memory staging and no
+// cross-lane prefix sum (ncu on the first, reference-layout kernel showed the path is bound
+// by instruction issue, not HBM: ~70 warp instructions per block went into unpack + scan).
+//   payload   u8[]      per block, 16 B aligned:
+//                         doc records  nl = ceil(n/4) records of R words (R in {1,2,4}); record l =
+//                                      [f : w0 bits][d1 : b][d2 : b][d3 : b] LSB first, where
+//                                      f  = doc[4l] - base_doc, d_i = doc[4l+i] - doc[4l+i-1];
+//                                      padded to 16 B
+//                         tf records   nl records of 16 / 32 / 128 bits = 4 tfs of 4 / 8 / 32 bits;
+//                                      padded to 16 B
+//                       slots past n in the last record repeat the last posting (delta 0, same tf)
+//   blk_info  uint4[]   {base_doc, payload_off/16, bits, max_tfn f32}; bits =
+//                       (w0-1) | (b-1)<<5 | (n-1)<<10 | rcode<<17 | tcode<<19 |
+//                       (ref_dbits-1)<<21 | (ref_tbits-1)<<26
+//                       base_doc = doc id the block is relative to (the reference's skip-row
+//                       previous_doc_id, flash_containers.h:22-30; shard lower bound for a
+//                       shard's first block); ref_dbits/ref_tbits = the widths the REFERENCE's
+//                       128-value packs use for this block (packed_value.h:87-128) — they define
+//                       the algorithmic bytes of the roofline; max_tfn = upper bound of
 //                       tf*(k1+1)/(tf+cache[norm]) over the block (block-max metadata).
-//   blk_last  u32[]     last doc id of each block (binary-searched when skipping)
+//   blk_last  u32[]     last doc id of each block (searched when skipping)
 //   lists     uint4[]   per term {first_block, n_blocks, df_shard, df_global}
 //   norms     u8[]      DocLengthCharStore bytes indexed by GLOBAL doc id
 //   cache     f64[256]  Bm25Similarity::cache_ (scoring.h:85-90)
@@ -27,7 +40,7 @@ constexpr int kBlock = 128;
 struct BlockInfo {       // 16 B, mirrors a device uint4
   uint32_t base_doc;
   uint32_t payload_off16;
-  uint32_t bits;         // dbits | tbits << 6 | (n-1) << 12
+  uint32_t bits;         // PackShape()
   float max_tfn;
 };
 static_assert(sizeof(BlockInfo) == 16, "BlockInfo must be 16 bytes");
@@ -40,12 +53,38 @@ struct ListInfo {        // 16 B, mirrors a device uint4
 };
 static_assert(sizeof(ListInfo) == 16, "ListInfo must be 16 bytes");
 
-inline uint32_t PackBits(int dbits, int tbits, int n) {
-  return (uint32_t)dbits | ((uint32_t)tbits << 6) | ((uint32_t)(n - 1) << 12);
+struct BlockShape {      // decoded view of BlockInfo::bits
+  int w0, b, n, rcode, tcode, ref_dbits, ref_tbits;
+  int nl() const { return (n + 3) / 4; }
+  int rec_words() const { return 1 << rcode; }                   // 1, 2, 4
+  int tf_bits() const { return tcode == 0 ? 4 : tcode == 1 ? 8 : 32; }
+  uint32_t doc_bytes() const { return (uint32_t)((nl() * rec_words() * 4 + 15) / 16 * 16); }
+  uint32_t tf_bytes() const { return (uint32_t)((nl() * tf_bits() / 2 + 15) / 16 * 16); }
+};
+inline uint32_t PackShape(const BlockShape &s) {
+  return (uint32_t)(s.w0 - 1) | ((uint32_t)(s.b - 1) << 5) | ((uint32_t)(s.n - 1) << 10) |
+         ((uint32_t)s.rcode << 17) | ((uint32_t)s.tcode << 19) |
+         ((uint32_t)(s.ref_dbits - 1) << 21) | ((uint32_t)(s.ref_tbits - 1) << 26);
 }
-// Bytes of one b-bit stream holding n values, padded to the 16 B load granule.
-inline uint32_t StreamBytes(int n, int bits) {
+inline BlockShape UnpackShape(uint32_t bits) {
+  BlockShape s;
+  s.w0 = (int)(bits & 31) + 1;
+  s.b = (int)((bits >> 5) & 31) + 1;
+  s.n = (int)((bits >> 10) & 127) + 1;
+  s.rcode = (int)((bits >> 17) & 3);
+  s.tcode = (int)((bits >> 19) & 3);
+  s.ref_dbits = (int)((bits >> 21) & 31) + 1;
+  s.ref_tbits = (int)((bits >> 26) & 31) + 1;
+  return s;
+}
+// Algorithmic bytes of a block: the reference's pack sizes for its n postings
+// (16*bits bytes for a full pack; a tail re-packed at its own width, padded to 16 B) + 16 B
+// of block metadata.
+inline uint32_t RefStreamBytes(int n, int bits) {
   return (uint32_t)(((uint64_t)n * bits + 127) / 128 * 16);
+}
+inline uint32_t AlgorithmicBytes(const BlockShape &s) {
+  return RefStreamBytes(s.n, s.ref_dbits) + RefStreamBytes(s.n, s.ref_tbits) + 16;
 }
 
 // Open-addressing string -> term id table over one arena (replaces the reference's hat-trie,

@@ -1,12 +1,18 @@
 // Hand-written sm_100a kernels for the WiSER/Vacuum hot path: packed-block decode, conjunctive
 // intersection with skip metadata, fused BM25 scoring and per-query top-k.
 //
-// Execution model: one WARP owns one work unit = (query, range of <=kUnitBlocks blocks of the
-// query's shortest list). Units of a whole query batch sit in per-class dynamic queues
-// (atomic counter) drained by a persistent grid sized to the SM count. A block is staged
-// with one coalesced 128-bit load per lane, unpacked from shared memory with funnel shifts,
-// and prefix-summed with warp shuffles. Everything on the path is integer/byte work bound by
-// HBM bandwidth and the integer issue rate; tensor cores are not used.
+// Execution model: one WARP owns one work unit = (query, range of blocks of the query's
+// shortest list). Units of a whole query batch sit in per-class dynamic queues (an atomic
+// counter each) drained by a persistent grid sized to the SM count x resident CTAs. Blocks are
+// LANE-MAJOR (host_index.h): lane l loads one 32/64/128-bit record holding postings 4l..4l+3
+// and reconstructs their doc ids with three adds. Intersection is galloping PER LANE: the
+// driver (shortest) list's block is decoded into registers, and every lane probes the longer
+// lists for its own four candidates — per-block last-doc skip metadata picks the block, a
+// 5-step search over the block's record heads picks the 4-posting record, one record decode
+// settles membership — so probe lists are never decoded wholesale and the work per driver
+// block does not grow with the length ratio of the lists. Everything on the path is
+// integer/byte work bound by instruction issue, memory latency and HBM bandwidth; tensor cores
+// are not used (nothing here is a dense contraction).
 //
 // Reference semantics restated here (paths relative to the reference's src/qq_mem/src/):
 //   block decode      LittlePackedIntsReader / DeltaEncodedPackedIntsIterator, packed_value.h:184-235, 320-369
@@ -25,121 +31,134 @@ namespace wsr {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kNoDoc = 0xffffffffu;
 constexpr double kK1Plus1 = 1.2 + 1;   // (k1_ + 1) evaluated in double, scoring.h:68
+constexpr int kTabSlots = 2048;        // position table keyed by doc & (kTabSlots - 1)
+constexpr int kLoserCap = 24;          // table collisions kept in a side list per staged block
+constexpr int kHitCap = 160;           // 31 queued + 128 new hits of one pass
 
-struct __align__(16) WarpScratch {
-  uint32_t stage[136];   // packed words of one stream (<=128) + zero pad for the hi word
-  uint32_t docs[128];    // doc ids of the most recently decoded probe-side block
-};
-
-struct CtaShared {
-  double cache[256];
-  float cache32[256];
-  WarpScratch warp[kWarpsPerCta];
-};
-
-__device__ __forceinline__ uint32_t BlkN(uint32_t bits) { return ((bits >> 12) & 127u) + 1u; }
-__device__ __forceinline__ uint32_t BlkDBits(uint32_t bits) { return bits & 63u; }
-__device__ __forceinline__ uint32_t BlkTBits(uint32_t bits) { return (bits >> 6) & 63u; }
-__device__ __forceinline__ uint32_t Granules(uint32_t n, uint32_t bits) { return (n * bits + 127u) >> 7; }
-
-// Copies `nvec` 16-byte granules of one packed stream into the warp's staging buffer with one
-// coalesced 128-bit load per lane; lanes past the stream store zeros (zero pad).
-__device__ __forceinline__ void StageStream(const uint4 *__restrict__ src, uint32_t nvec,
-                                            WarpScratch *ws, int lane) {
-  __syncwarp();   // previous readers of the staging buffer are done
-  uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if ((uint32_t)lane < nvec) v = __ldg(src + lane);
-  reinterpret_cast<uint4 *>(ws->stage)[lane] = v;
-  if (lane == 0) ws->stage[128] = 0u;
-  __syncwarp();
+// ---- block shape (host_index.h PackShape) --------------------------------------------------
+__device__ __forceinline__ uint32_t ShW0(uint32_t b) { return (b & 31u) + 1u; }
+__device__ __forceinline__ uint32_t ShB(uint32_t b) { return ((b >> 5) & 31u) + 1u; }
+__device__ __forceinline__ uint32_t ShN(uint32_t b) { return ((b >> 10) & 127u) + 1u; }
+__device__ __forceinline__ uint32_t ShRcode(uint32_t b) { return (b >> 17) & 3u; }
+__device__ __forceinline__ uint32_t ShTcode(uint32_t b) { return (b >> 19) & 3u; }
+__device__ __forceinline__ uint32_t ShRefD(uint32_t b) { return ((b >> 21) & 31u) + 1u; }
+__device__ __forceinline__ uint32_t ShRefT(uint32_t b) { return ((b >> 26) & 31u) + 1u; }
+// 16-byte granules of the doc-record stream of a block
+__device__ __forceinline__ uint32_t DocGranules(uint32_t bits) {
+  const uint32_t nl = (ShN(bits) + 3u) >> 2;
+  return ((nl << ShRcode(bits)) + 3u) >> 2;
+}
+// Algorithmic bytes of a block: the reference's pack sizes + 16 B metadata
+__device__ __forceinline__ uint32_t AlgBytes(uint32_t bits, bool with_tf) {
+  const uint32_t n = ShN(bits);
+  uint32_t g = (n * ShRefD(bits) + 127u) >> 7;
+  if (with_tf) g += (n * ShRefT(bits) + 127u) >> 7;
+  return 16u * g + 16u;
 }
 
-// Lane l extracts elements 4l..4l+3 of the staged b-bit LSB-first stream.
-__device__ __forceinline__ void Unpack4(const WarpScratch *ws, uint32_t bits, int lane,
-                                        uint32_t v[4]) {
-  const uint32_t mask = bits >= 32u ? 0xffffffffu : ((1u << bits) - 1u);
-  uint32_t bit = 4u * (uint32_t)lane * bits;
+// ---- K1: block decode ------------------------------------------------------------------------
+// Doc ids of the four postings of record `rec` = [f:w0][d1:b][d2:b][d3:b] (host_index.h).
+// Padded slots of a block's last record repeat its last doc.
+__device__ __forceinline__ void DecodeRecord(const DevIndexView &ix, const uint4 info, uint32_t rec,
+                                             uint32_t d[4]) {
+  const uint32_t bits = info.z;
+  const uint32_t w0 = ShW0(bits), b = ShB(bits), rc = ShRcode(bits);
+  const uint4 *src = ix.payload + info.y;
+  uint32_t r0, r1 = 0, r2 = 0, r3 = 0;
+  if (rc == 0) {
+    r0 = __ldg(reinterpret_cast<const uint32_t *>(src) + rec);
+  } else if (rc == 1) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src) + rec);
+    r0 = v.x; r1 = v.y;
+  } else {
+    const uint4 v = __ldg(src + rec);
+    r0 = v.x; r1 = v.y; r2 = v.z; r3 = v.w;
+  }
+  const uint32_t m0 = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
+  const uint32_t mb = b >= 32u ? 0xffffffffu : ((1u << b) - 1u);
+  uint32_t f, d1, d2, d3;
+  if (rc <= 1) {
+    unsigned long long x = ((unsigned long long)r1 << 32) | r0;
+    f = (uint32_t)x & m0;
+    x >>= w0;
+    d1 = (uint32_t)x & mb;
+    x >>= b;
+    d2 = (uint32_t)x & mb;
+    x >>= b;
+    d3 = (uint32_t)x & mb;
+  } else {
+    // 128-bit record: fields may straddle words
+    f = r0 & m0;
+    uint32_t o = w0;
+    uint32_t out[3];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const uint32_t w = bit >> 5;
-    const uint32_t lo = ws->stage[w], hi = ws->stage[w + 1];
-    v[i] = __funnelshift_r(lo, hi, bit & 31u) & mask;
-    bit += bits;
+    for (int i = 0; i < 3; i++) {
+      const uint32_t wi = o >> 5, sh = o & 31u;
+      const uint32_t lo = wi == 0 ? r0 : wi == 1 ? r1 : wi == 2 ? r2 : r3;
+      const uint32_t hi = wi == 0 ? r1 : wi == 1 ? r2 : wi == 2 ? r3 : 0u;
+      out[i] = __funnelshift_r(lo, hi, sh) & mb;
+      o += b;
+    }
+    d1 = out[0]; d2 = out[1]; d3 = out[2];
+  }
+  d[0] = info.x + f;
+  d[1] = d[0] + d1;
+  d[2] = d[1] + d2;
+  d[3] = d[2] + d3;
+}
+
+// Whole block: lane l decodes record l (postings 4l..4l+3); lanes past the records get kNoDoc.
+__device__ __forceinline__ void DecodeDocs(const DevIndexView &ix, const uint4 info, int lane,
+                                           uint32_t d[4]) {
+  const uint32_t nl = (ShN(info.z) + 3u) >> 2;
+  d[0] = d[1] = d[2] = d[3] = kNoDoc;
+  if ((uint32_t)lane < nl) DecodeRecord(ix, info, (uint32_t)lane, d);
+}
+
+// tfs of postings 4l..4l+3 (0 for lanes past the block's records)
+__device__ __forceinline__ void DecodeTfs(const DevIndexView &ix, const uint4 info, int lane,
+                                          uint32_t tf[4]) {
+  const uint32_t bits = info.z;
+  const uint32_t nl = (ShN(bits) + 3u) >> 2, tc = ShTcode(bits);
+  const uint4 *src = ix.payload + info.y + DocGranules(bits);
+  tf[0] = tf[1] = tf[2] = tf[3] = 0;
+  if ((uint32_t)lane < nl) {
+    if (tc == 0) {
+      const uint32_t v = __ldg(reinterpret_cast<const unsigned short *>(src) + lane);
+      tf[0] = v & 15u; tf[1] = (v >> 4) & 15u; tf[2] = (v >> 8) & 15u; tf[3] = v >> 12;
+    } else if (tc == 1) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src) + lane);
+      tf[0] = v & 255u; tf[1] = (v >> 8) & 255u; tf[2] = (v >> 16) & 255u; tf[3] = v >> 24;
+    } else {
+      const uint4 v = __ldg(src + lane);
+      tf[0] = v.x; tf[1] = v.y; tf[2] = v.z; tf[3] = v.w;
+    }
   }
 }
 
-__device__ __forceinline__ uint32_t WarpInclusiveScan(uint32_t x, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(kFull, x, o);
-    if (lane >= o) x += t;
-  }
-  return x;
+// tf of posting `pos` = (global block index << 7) | slot — random access for intersection hits.
+__device__ __forceinline__ uint32_t TfAt(const DevIndexView &ix, uint32_t pos) {
+  const uint4 info = __ldg(&ix.blk_info[pos >> 7]);
+  const uint32_t bits = info.z, tc = ShTcode(bits), slot = pos & 127u;
+  const uint4 *src = ix.payload + info.y + DocGranules(bits);
+  if (tc == 0)
+    return (__ldg(reinterpret_cast<const unsigned short *>(src) + (slot >> 2)) >> (4u * (slot & 3u))) & 15u;
+  if (tc == 1)
+    return (__ldg(reinterpret_cast<const uint32_t *>(src) + (slot >> 2)) >> (8u * (slot & 3u))) & 255u;
+  return __ldg(reinterpret_cast<const uint32_t *>(src) + slot);
 }
 
-// Decodes the doc-id stream of one block: lane l gets doc ids of elements 4l..4l+3
-// (0xFFFFFFFF past the block's n postings). Doc ids are base + running sum of the deltas.
-__device__ __forceinline__ void DecodeDocs4(const DevIndexView &ix, const uint4 info,
-                                            WarpScratch *ws, int lane, uint32_t d[4]) {
-  const uint32_t n = BlkN(info.z), dbits = BlkDBits(info.z);
-  StageStream(ix.payload + info.y, Granules(n, dbits), ws, lane);
-  Unpack4(ws, dbits, lane, d);
-  d[1] += d[0];
-  d[2] += d[1];
-  d[3] += d[2];
-  const uint32_t incl = WarpInclusiveScan(d[3], lane);
-  const uint32_t off = info.x + incl - d[3];
-#pragma unroll
-  for (int i = 0; i < 4; i++) d[i] = (4u * lane + i < n) ? d[i] + off : 0xffffffffu;
-}
-
-// Decodes the tf stream of one block (elements 4l..4l+3 per lane).
-__device__ __forceinline__ void DecodeTfs4(const DevIndexView &ix, const uint4 info,
-                                           WarpScratch *ws, int lane, uint32_t tf[4]) {
-  const uint32_t n = BlkN(info.z), dbits = BlkDBits(info.z), tbits = BlkTBits(info.z);
-  StageStream(ix.payload + info.y + Granules(n, dbits), Granules(n, tbits), ws, lane);
-  Unpack4(ws, tbits, lane, tf);
-}
-
-// Random access to one tf of a block straight from HBM/L2 (used for intersection hits only).
-__device__ __forceinline__ uint32_t ExtractTf(const DevIndexView &ix, const uint4 info, uint32_t pos) {
-  const uint32_t n = BlkN(info.z), dbits = BlkDBits(info.z), tbits = BlkTBits(info.z);
-  const uint32_t *w = reinterpret_cast<const uint32_t *>(ix.payload + info.y + Granules(n, dbits));
-  const uint32_t bit = pos * tbits;
-  const uint32_t lo = __ldg(w + (bit >> 5)), hi = __ldg(w + (bit >> 5) + 1);
-  const uint32_t mask = tbits >= 32u ? 0xffffffffu : ((1u << tbits) - 1u);
-  return __funnelshift_r(lo, hi, bit & 31u) & mask;
-}
-
-// First block index in [lo, hi) whose last doc id is >= x, or hi.
-__device__ __forceinline__ uint32_t LowerBoundBlock(const uint32_t *__restrict__ last, uint32_t lo,
-                                                    uint32_t hi, uint32_t x) {
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(last + mid) < x) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// Position of the first doc id >= x among the 128 staged doc ids (sentinel-padded).
-__device__ __forceinline__ uint32_t LowerBound128(const uint32_t *docs, uint32_t x) {
-  uint32_t pos = 0;
-#pragma unroll
-  for (uint32_t step = 64; step; step >>= 1)
-    if (docs[pos + step - 1] < x) pos += step;
-  return pos;
-}
-
-// TfNormLossy + one term of CalcDocScoreLossy with every operation rounded separately
-// (the reference build has no FMA contraction).
+// TfNormLossy + one term of CalcDocScoreLossy, every operation rounded separately (the
+// reference build has no FMA contraction).
 __device__ __forceinline__ double TermScore(double idf, uint32_t tf, double cache_norm) {
   const double f = (double)tf;
   const double tfnorm = __ddiv_rn(__dmul_rn(f, kK1Plus1), __dadd_rn(f, cache_norm));
   return __dmul_rn(idf, tfnorm);
 }
 
-// ---- per-warp top-k: lane r holds the rank-r entry, ordered (score desc, doc asc) --------
+// ---- per-warp top-k: lane r holds the rank-r entry, ordered (score desc, doc asc) ------------
 struct TopK {
   double s;
   int d;
@@ -178,24 +197,36 @@ struct UnitStats {
   unsigned long long decoded, bytes, matches;
 };
 
+struct CtaShared {
+  double cache[256];
+  float cache32[256];
+};
+
+struct HitRec {
+  uint32_t doc;
+  uint32_t pos_a;   // (global block index << 7) | slot
+  uint32_t pos_b;
+};
+
+// Per-warp scratch of the intersecting kernels.
+struct __align__(16) ProbeScratch {
+  uint32_t win[32];              // the probe list's blk_last window, for per-lane block lookup
+  HitRec hits[kHitCap];
+};
+struct __align__(16) NoScratch { uint32_t unused; };
+
 // Emits one unit's result: straight to the caller's hit array when the query has one unit,
-// else to the unit's candidate slot for the merge pass.
+// else to the unit's candidate slot for the merge pass. doc ids leave as GLOBAL ids.
 __device__ __forceinline__ void EmitTopK(const BatchView &bv, const DevQuery &q, uint32_t local,
                                          const TopK &t, int lane) {
-  const uint32_t gunit = q.cand_begin + local;
+  wsr_hit h;
+  h.doc_id = t.d + (int)bv.doc_base; h.reserved = 0; h.score = t.s;
   if (q.n_units == 1) {
-    if (lane < t.count) {
-      wsr_hit h;
-      h.doc_id = t.d; h.reserved = 0; h.score = t.s;
-      bv.hits[(size_t)q.out_slot * bv.k_stride + lane] = h;
-    }
+    if (lane < t.count) bv.hits[(size_t)q.out_slot * bv.k_stride + lane] = h;
     if (lane == 0) bv.n_hits[q.out_slot] = t.count;
   } else {
-    if (lane < t.count) {
-      wsr_hit h;
-      h.doc_id = t.d; h.reserved = 0; h.score = t.s;
-      bv.cand[(size_t)gunit * kMaxFastK + lane] = h;
-    }
+    const uint32_t gunit = q.cand_begin + local;
+    if (lane < t.count) bv.cand[(size_t)gunit * kMaxFastK + lane] = h;
     if (lane == 0) bv.cand_n[gunit] = t.count;
   }
 }
@@ -210,19 +241,42 @@ __device__ __forceinline__ void CollectAppend(const BatchView &bv, const DevQuer
   base = __shfl_sync(kFull, base, 0);
   if (has) {
     const uint32_t at = q.seg_begin + base + __popc(m & ((1u << lane) - 1u));
-    bv.seg_doc[at] = doc;
+    bv.seg_doc[at] = doc + (int)bv.doc_base;
     bv.seg_score[at] = score;
   }
 }
 
-// ---- single-term units: SingleTermQueryProcessor::Process, query_processing.h:632-641 ----
-// Every posting is a hit. Blocks whose block-max score cannot reach the running k-th score
-// are skipped without touching their payload; surviving postings are pre-filtered with an
-// fp32 upper bound and only candidates are re-scored in exact fp64.
+// Offers scored candidates (one per lane) to the unit's top-k and publishes the new k-th score.
+__device__ __forceinline__ void OfferToTopK(const BatchView &bv, uint32_t qi, bool multi, int k, bool has,
+                                            double s, int doc, TopK &top, double &published, int lane) {
+  double thr = 0.0;
+  if (multi) thr = __longlong_as_double((long long)__ldcg(&bv.thr[qi]));
+  const double kth = top.count == k ? TopKKth(top, k) : -1.0;
+  // a score strictly below another unit's k-th score can never reach the final top-k; ties stay
+  unsigned m = __ballot_sync(kFull, has && !(s < thr) && !(s < kth));
+  if (!m) return;
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    TopKInsert(top, k, __shfl_sync(kFull, s, src), __shfl_sync(kFull, doc, src), lane);
+  }
+  if (multi && top.count == k) {
+    const double nk = TopKKth(top, k);
+    if (nk > published) {
+      published = nk;
+      if (lane == 0) atomicMax(&bv.thr[qi], (unsigned long long)__double_as_longlong(nk));
+    }
+  }
+}
+
+// ---- single-term units: SingleTermQueryProcessor::Process, query_processing.h:632-641 --------
+// Every posting is a hit. Blocks whose block-max score cannot reach the running k-th score are
+// skipped without touching their payload; surviving postings are pre-filtered with an fp32
+// upper bound and only candidates are re-scored in exact fp64.
 template <bool COLLECT>
 __device__ void ProcessOneTerm(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
                                uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
-                               CtaShared *sh, WarpScratch *ws, int lane, UnitStats &st) {
+                               const CtaShared *sh, int lane, UnitStats &st) {
   const uint32_t term = q.term[0];
   const uint4 li = __ldg(&ix.lists[term]);
   const double idf = __ldg(&ix.idf[term]);
@@ -231,29 +285,27 @@ __device__ void ProcessOneTerm(const DevIndexView &ix, const BatchView &bv, cons
   const bool multi = q.n_units > 1;
   TopK top;
   TopKInit(top);
-  double thr_shared = 0.0;
-  double published = 0.0;
+  double thr_shared = 0.0, published = 0.0;
 
+  uint4 info = __ldg(&ix.blk_info[li.x + b0]);
   for (uint32_t j = b0; j < b1; j++) {
-    const uint4 info = __ldg(&ix.blk_info[li.x + j]);
-    const uint32_t n = BlkN(info.z);
+    const uint4 cur = info;
+    if (j + 1 < b1) info = __ldg(&ix.blk_info[li.x + j + 1]);
+    const uint32_t n = ShN(cur.z);
     double kth = -1.0;
     if (!COLLECT) {
-      if (multi) {
-        const unsigned long long tb = __ldcg(&bv.thr[qi]);
-        thr_shared = fmax(thr_shared, __longlong_as_double((long long)tb));
-      }
+      if (multi) thr_shared = fmax(thr_shared, __longlong_as_double((long long)__ldcg(&bv.thr[qi])));
       const bool full = top.count == k;
       kth = full ? TopKKth(top, k) : -1.0;
       // upper bound of every exact score in the block (rounded up at each step)
-      const double ub = (double)(idf_up * __uint_as_float(info.w) * 1.00001f);
+      const double ub = (double)(idf_up * __uint_as_float(cur.w) * 1.00001f);
       if (ub < thr_shared || (full && ub <= kth)) continue;
     }
     uint32_t d[4], tf[4];
-    DecodeDocs4(ix, info, ws, lane, d);
-    DecodeTfs4(ix, info, ws, lane, tf);
+    DecodeDocs(ix, cur, lane, d);
+    DecodeTfs(ix, cur, lane, tf);
     st.decoded += n;
-    st.bytes += 16ull * (Granules(n, BlkDBits(info.z)) + Granules(n, BlkTBits(info.z))) + 16ull;
+    st.bytes += AlgBytes(cur.z, true) + n;   // + one norm byte per posting
     st.matches += n;
 
     bool pass[4];
@@ -268,12 +320,10 @@ __device__ void ProcessOneTerm(const DevIndexView &ix, const BatchView &bv, cons
         if (!COLLECT) {
           const float f = (float)tf[i];
           const float s32 = idf_up * __fdividef(f * 2.2f, f + sh->cache32[nb]) * 1.00001f;
-          const double thr_eff = fmax(thr_shared, kth);
-          pass[i] = (double)s32 >= thr_eff;
+          pass[i] = (double)s32 >= fmax(thr_shared, kth);
         }
         if (pass[i]) {
-          s64[i] = TermScore(idf, tf[i], sh->cache[nb]);
-          s64[i] = __dadd_rn(0.0, s64[i]);
+          s64[i] = __dadd_rn(0.0, TermScore(idf, tf[i], sh->cache[nb]));
           if (!COLLECT) pass[i] = !(s64[i] < thr_shared) && !(s64[i] < kth);
         }
       }
@@ -282,193 +332,341 @@ __device__ void ProcessOneTerm(const DevIndexView &ix, const BatchView &bv, cons
 #pragma unroll
       for (int i = 0; i < 4; i++) CollectAppend(bv, q, qi, pass[i], (int)d[i], s64[i], lane);
     } else {
-      bool inserted = false;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        unsigned m = __ballot_sync(kFull, pass[i]);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const double s = __shfl_sync(kFull, s64[i], src);
-          const int dd = (int)__shfl_sync(kFull, d[i], src);
-          TopKInsert(top, k, s, dd, lane);
-          inserted = true;
-        }
-      }
-      if (multi && inserted && top.count == k) {
-        const double nk = TopKKth(top, k);
-        if (nk > published) {
-          published = nk;
-          if (lane == 0) atomicMax(&bv.thr[qi], (unsigned long long)__double_as_longlong(nk));
-        }
-      }
+      for (int i = 0; i < 4; i++)
+        OfferToTopK(bv, qi, multi, k, pass[i], s64[i], (int)d[i], top, published, lane);
     }
   }
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
 }
 
-// ---- multi-term units: shortest list drives, the other lists are probed through their
-// per-block last-doc skip metadata; only blocks that can contain a candidate are decoded.
+// ---- probe-list machinery shared by the intersecting kernels ---------------------------------
+// Walk state of one probe list. A 32-entry window of its blk_last lives in registers (lane l
+// holds last[wbase + l]); it moves forward with the driver, by a 32-ary cooperative search when
+// the next candidate lies beyond it.
+struct ProbeList {
+  const uint32_t *last;   // blk_last of this list
+  uint32_t first, nb;     // first global block, block count
+  uint32_t wbase, wl;
+};
+
+__device__ __forceinline__ void ProbeInit(ProbeList &p, const DevIndexView &ix, const uint4 li, int lane) {
+  p.first = li.x;
+  p.nb = li.y;
+  p.last = ix.blk_last + li.x;
+  p.wbase = 0;
+  p.wl = (uint32_t)lane < p.nb ? __ldg(p.last + lane) : kNoDoc;
+}
+
+// Moves the window so that it contains the first block j with last[j] >= x; returns j, or kNoDoc
+// when the list has no doc >= x.
+__device__ __forceinline__ uint32_t ProbeFind(ProbeList &p, uint32_t x, int lane) {
+  if (x > __shfl_sync(kFull, p.wl, 31)) {
+    uint32_t lo = p.wbase + 32u, hi = p.nb;
+    if (lo >= hi) return kNoDoc;
+    while (hi - lo > 32u) {
+      const uint32_t step = (hi - lo + 31u) >> 5;
+      const uint32_t idx = min(lo + ((uint32_t)lane + 1u) * step - 1u, hi - 1u);
+      const int c = __popc(__ballot_sync(kFull, __ldg(p.last + idx) < x));
+      if (c == 32) return kNoDoc;
+      lo += (uint32_t)c * step;
+      hi = min(lo + step, hi);
+    }
+    p.wbase = lo;
+    p.wl = lo + lane < p.nb ? __ldg(p.last + lo + lane) : kNoDoc;
+  }
+  const int c = __popc(__ballot_sync(kFull, p.wl < x));
+  const uint32_t j = p.wbase + (uint32_t)c;
+  return (c == 32 || j >= p.nb) ? kNoDoc : j;
+}
+
+// Galloping probe of one list for the lane's four candidates d[i] (alive[i] says which to test).
+// On return alive[i] tells whether d[i] is in the list and pos[i] = (global block << 7) | slot.
+// Returns false when the list has nothing at or after the smallest candidate (nothing later in
+// the driver can match either).
+__device__ __forceinline__ bool ProbeCandidates(const DevIndexView &ix, ProbeList &p, uint32_t *win,
+                                                const uint32_t d[4], bool alive[4], uint32_t pos[4],
+                                                int lane, UnitStats &st) {
+  uint32_t mn = kNoDoc, mx = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    if (alive[i]) { mn = min(mn, d[i]); mx = max(mx, d[i]); }
+  mn = __reduce_min_sync(kFull, mn);
+  if (mn == kNoDoc) return true;                       // nothing to test
+  mx = __reduce_max_sync(kFull, mx);
+  const uint32_t j_lo = ProbeFind(p, mn, lane);
+  if (j_lo == kNoDoc) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) alive[i] = false;
+    return false;
+  }
+  // ---- block of every candidate
+  uint32_t j[4];
+  if (mx <= __shfl_sync(kFull, p.wl, 31)) {
+    // all candidates fall inside the window: count window entries < d (5-step search in smem)
+    __syncwarp();
+    win[lane] = p.wl;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t c = 0;
+#pragma unroll
+      for (uint32_t s = 16; s; s >>= 1)
+        if (win[c + s - 1] < d[i]) c += s;
+      c += win[c] < d[i];
+      j[i] = p.wbase + c;
+      if (c >= 32u || j[i] >= p.nb) alive[i] = false;
+    }
+  } else {
+    // skewed lists: the driver block spans more than a window of probe blocks
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t lo = j_lo, hi = p.nb;
+      if (alive[i]) {
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (__ldg(p.last + mid) < d[i]) lo = mid + 1; else hi = mid;
+        }
+      }
+      j[i] = lo;
+      if (lo >= p.nb) alive[i] = false;
+    }
+  }
+  // ---- record of every candidate: last record whose first doc <= d (step-major for ILP)
+  uint4 info[4];
+  uint32_t rec[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    info[i] = make_uint4(0u, 0u, 0u, 0u);
+    rec[i] = 0;
+    if (alive[i]) info[i] = __ldg(&ix.blk_info[p.first + j[i]]);
+  }
+#pragma unroll
+  for (uint32_t s = 16; s; s >>= 1) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t bits = info[i].z;
+      const uint32_t mid = rec[i] + s;
+      if (alive[i] && mid < ((ShN(bits) + 3u) >> 2)) {
+        const uint32_t w0 = ShW0(bits);
+        const uint32_t m0 = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
+        const uint32_t head = __ldg(reinterpret_cast<const uint32_t *>(ix.payload + info[i].y) +
+                                    (mid << ShRcode(bits)));
+        if (info[i].x + (head & m0) <= d[i]) rec[i] = mid;
+      }
+    }
+  }
+  // ---- decode that record and compare
+  uint32_t touched_n = 0, touched_b = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (alive[i]) {
+      uint32_t e[4];
+      DecodeRecord(ix, info[i], rec[i], e);
+      const uint32_t x = d[i];
+      const int slot = e[0] == x ? 0 : e[1] == x ? 1 : e[2] == x ? 2 : e[3] == x ? 3 : -1;
+      alive[i] = slot >= 0;
+      pos[i] = ((p.first + j[i]) << 7) | (4u * rec[i] + (uint32_t)max(slot, 0));
+    }
+  }
+  // ---- accounting: every distinct probe block touched counts once (candidates are sorted by
+  // (lane, slot), so a block is new when it differs from the previous candidate's)
+  {
+    uint32_t prev = __shfl_up_sync(kFull, j[3], 1);
+    if (lane == 0) prev = kNoDoc;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const bool has = info[i].z != 0u || info[i].y != 0u || info[i].x != 0u;
+      if (has && j[i] != prev) {
+        touched_n += ShN(info[i].z);
+        touched_b += AlgBytes(info[i].z, false);
+      }
+      if (has) prev = j[i];
+    }
+    // j[3] of the previous lane may be stale when that lane had dead slots; the count is
+    // bookkeeping for the roofline, never used for results
+    st.decoded += __reduce_add_sync(kFull, touched_n);
+    st.bytes += __reduce_add_sync(kFull, touched_b);
+  }
+  return true;
+}
+
+// ---- two-term units (the headline path): TwoTermNonPhraseQueryProcessor::Process -------------
+// Driver blocks are walked in order; for the smallest unresolved candidate the probe block is
+// located, staged once, and every candidate that falls inside it is resolved in the same pass.
+// Hits are queued in shared memory and scored 32 at a time (one lane per hit) so the divergent,
+// latency-heavy tf / norm gathers and the fp64 divisions stay off the per-block path.
+template <bool COLLECT>
+__device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const DevQuery &q, uint32_t qi,
+                          const CtaShared *sh, ProbeScratch *ws, int nq, int drv, double idf0,
+                          double idf1, TopK &top, double &published, bool multi, int lane,
+                          UnitStats &st) {
+  __syncwarp();
+  for (int base = 0; base < nq; base += 32) {
+    const bool has = base + lane < nq;
+    double s = 0.0;
+    int doc = 0;
+    if (has) {
+      const HitRec h = ws->hits[base + lane];
+      doc = (int)h.doc;
+      const uint32_t tfa = TfAt(ix, h.pos_a), tfb = TfAt(ix, h.pos_b);
+      const double cn = sh->cache[__ldg(ix.norms + h.doc)];
+      // query order: term 0 first (scoring.h:124-145)
+      s = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? tfa : tfb, cn));
+      s = __dadd_rn(s, TermScore(idf1, drv == 0 ? tfb : tfa, cn));
+    }
+    if (COLLECT) CollectAppend(bv, q, qi, has, doc, s, lane);
+    else OfferToTopK(bv, qi, multi, (int)q.k, has, s, doc, top, published, lane);
+  }
+  st.matches += nq;
+  st.bytes += 17ull * nq;   // per hit: 2 x 8 B of tf record words + 1 norm byte
+  __syncwarp();
+}
+
+template <bool COLLECT>
+__device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
+                           uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
+                           const CtaShared *sh, ProbeScratch *ws, int lane, UnitStats &st) {
+  const int drv = (int)q.driver, oth = 1 - drv;
+  const uint4 la = __ldg(&ix.lists[q.term[drv]]);
+  const uint4 lb = __ldg(&ix.lists[q.term[oth]]);
+  const double idf0 = __ldg(&ix.idf[q.term[0]]), idf1 = __ldg(&ix.idf[q.term[1]]);
+  const uint32_t first_a = la.x;
+  const bool multi = q.n_units > 1;
+  TopK top;
+  TopKInit(top);
+  double published = 0.0;
+  ProbeList pb;
+  ProbeInit(pb, ix, lb, lane);
+  int nq = 0;
+
+  uint4 info_a = __ldg(&ix.blk_info[first_a + b0]);
+  for (uint32_t ja = b0; ja < b1; ja++) {
+    const uint4 cur = info_a;
+    if (ja + 1 < b1) info_a = __ldg(&ix.blk_info[first_a + ja + 1]);
+    uint32_t d[4], pos[4];
+    DecodeDocs(ix, cur, lane, d);
+    const uint32_t na = ShN(cur.z);
+    st.decoded += na;
+    st.bytes += AlgBytes(cur.z, false);
+    bool alive[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) alive[i] = 4u * lane + i < na;   // padded slots repeat the last doc
+    const bool more = ProbeCandidates(ix, pb, ws->win, d, alive, pos, lane, st);
+    const uint32_t ga = (first_a + ja) << 7;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const unsigned m = __ballot_sync(kFull, alive[i]);
+      if (m) {
+        if (alive[i]) {
+          HitRec h;
+          h.doc = d[i];
+          h.pos_a = ga | (4u * lane + i);
+          h.pos_b = pos[i];
+          ws->hits[nq + __popc(m & ((1u << lane) - 1u))] = h;
+        }
+        nq += __popc(m);
+      }
+    }
+    if (nq >= 32) {
+      FlushHits<COLLECT>(ix, bv, q, qi, sh, ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
+      nq = 0;
+    }
+    if (!more) break;   // probe list exhausted: nothing further can match
+  }
+  if (nq) FlushHits<COLLECT>(ix, bv, q, qi, sh, ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
+  if (!COLLECT) EmitTopK(bv, q, local, top, lane);
+}
+
+// ---- 3..8-term units: QueryProcessor::ProcessMultipleTerms, query_processing.h:710-728 -------
+// The shortest list drives; the other lists are probed in query order with the same machinery,
+// candidates dying as soon as one list lacks them. Survivors are scored in place.
 template <int M, bool COLLECT>
 __device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
                              uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
-                             CtaShared *sh, WarpScratch *ws, int lane, UnitStats &st) {
+                             const CtaShared *sh, ProbeScratch *ws, int lane, UnitStats &st) {
   const int m = (int)q.n_terms;
   const int drv = (int)q.driver;
   const int k = (int)q.k;
   const bool multi = q.n_units > 1;
-  uint32_t first[M], nblk[M], cur[M];
+  ProbeList pl[M];
   double idf[M];
   uint32_t first_a = 0;
 #pragma unroll
   for (int t = 0; t < M; t++) {
-    first[t] = nblk[t] = cur[t] = 0;
     idf[t] = 0.0;
     if (t < m) {
       const uint4 li = __ldg(&ix.lists[q.term[t]]);
-      first[t] = li.x;
-      nblk[t] = li.y;
       idf[t] = __ldg(&ix.idf[q.term[t]]);
+      ProbeInit(pl[t], ix, li, lane);
       if (t == drv) first_a = li.x;
     }
   }
   TopK top;
   TopKInit(top);
   double published = 0.0;
-  uint32_t cached_blk = 0xffffffffu;
-  uint4 cached_info = make_uint4(0u, 0u, 0u, 0u);
+  bool exhausted = false;
 
-  for (uint32_t ja = b0; ja < b1; ja++) {
-    const uint4 info_a = __ldg(&ix.blk_info[first_a + ja]);
-    const uint32_t na = BlkN(info_a.z);
+  for (uint32_t ja = b0; ja < b1 && !exhausted; ja++) {
+    const uint4 cur = __ldg(&ix.blk_info[first_a + ja]);
     uint32_t d[4];
-    DecodeDocs4(ix, info_a, ws, lane, d);
+    DecodeDocs(ix, cur, lane, d);
+    const uint32_t na = ShN(cur.z);
     st.decoded += na;
-    st.bytes += 16ull * Granules(na, BlkDBits(info_a.z)) + 16ull;
+    st.bytes += AlgBytes(cur.z, false);
     bool al[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) al[i] = 4u * lane + i < na;
-    uint32_t tfv[M][4];
+    uint32_t posv[M][4];
 
 #pragma unroll
     for (int t = 0; t < M; t++) {
       if (t >= m || t == drv) continue;
-      // warp-wide doc-id range still alive
-      uint32_t mn = 0xffffffffu, mx = 0u;
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (al[i]) { mn = min(mn, d[i]); mx = max(mx, d[i]); }
-      mn = __reduce_min_sync(kFull, mn);
-      mx = __reduce_max_sync(kFull, mx);
-      if (mn == 0xffffffffu) continue;   // nothing alive
-      const uint32_t *last = ix.blk_last + first[t];
-      const uint32_t jlo = LowerBoundBlock(last, cur[t], nblk[t], mn);
-      cur[t] = jlo;
-      uint32_t jhi = jlo < nblk[t] ? LowerBoundBlock(last, jlo, nblk[t], mx) : jlo;
-      jhi = min(jhi + 1u, nblk[t]);
-      uint32_t jb[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        jb[i] = 0xffffffffu;
-        if (al[i]) {
-          const uint32_t j = LowerBoundBlock(last, jlo, jhi, d[i]);
-          if (j >= nblk[t]) al[i] = false; else jb[i] = j;
-        }
-      }
-      for (;;) {
-        uint32_t jm = min(min(jb[0], jb[1]), min(jb[2], jb[3]));
-        jm = __reduce_min_sync(kFull, jm);
-        if (jm == 0xffffffffu) break;
-        const uint32_t gblk = first[t] + jm;
-        if (cached_blk != gblk) {
-          cached_info = __ldg(&ix.blk_info[gblk]);
-          uint32_t e[4];
-          DecodeDocs4(ix, cached_info, ws, lane, e);
-          __syncwarp();
-          reinterpret_cast<uint4 *>(ws->docs)[lane] = make_uint4(e[0], e[1], e[2], e[3]);
-          __syncwarp();
-          cached_blk = gblk;
-          const uint32_t nbk = BlkN(cached_info.z);
-          st.decoded += nbk;
-          st.bytes += 16ull * Granules(nbk, BlkDBits(cached_info.z)) + 16ull;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          if (jb[i] == jm) {
-            const uint32_t pos = LowerBound128(ws->docs, d[i]);
-            if (ws->docs[pos] == d[i]) {
-              tfv[t][i] = ExtractTf(ix, cached_info, pos);
-              st.bytes += 8ull;
-            } else {
-              al[i] = false;
-            }
-            jb[i] = 0xffffffffu;
-          }
-        }
-        __syncwarp();
-      }
+      if (!ProbeCandidates(ix, pl[t], ws->win, d, al, posv[t], lane, st)) exhausted = true;
     }
 
     // survivors matched every list: score in QUERY order, fp64, one rounding per operation
     bool hit[4];
     double s64[4];
-    bool any = false;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       hit[i] = al[i];
       s64[i] = 0.0;
       if (al[i]) {
-        const uint32_t tfa = ExtractTf(ix, info_a, 4u * lane + i);
         const double cn = sh->cache[__ldg(ix.norms + d[i])];
         double s = 0.0;
 #pragma unroll
         for (int t = 0; t < M; t++) {
-          if (t < m) s = __dadd_rn(s, TermScore(idf[t], t == drv ? tfa : tfv[t][i], cn));
+          if (t < m) {
+            const uint32_t pos = t == drv ? (((first_a + ja) << 7) | (4u * lane + i)) : posv[t][i];
+            s = __dadd_rn(s, TermScore(idf[t], TfAt(ix, pos), cn));
+          }
         }
         s64[i] = s;
-        any = true;
       }
     }
-    const unsigned anym = __ballot_sync(kFull, any);
-    if (!anym) continue;
-    st.matches += __popc(__ballot_sync(kFull, hit[0])) + __popc(__ballot_sync(kFull, hit[1])) +
-                  __popc(__ballot_sync(kFull, hit[2])) + __popc(__ballot_sync(kFull, hit[3]));
-    if (COLLECT) {
 #pragma unroll
-      for (int i = 0; i < 4; i++) CollectAppend(bv, q, qi, hit[i], (int)d[i], s64[i], lane);
-    } else {
-      double thr_shared = 0.0;
-      if (multi) thr_shared = __longlong_as_double((long long)__ldcg(&bv.thr[qi]));
-      bool inserted = false;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        unsigned mm = __ballot_sync(kFull, hit[i] && !(s64[i] < thr_shared));
-        while (mm) {
-          const int src = __ffs(mm) - 1;
-          mm &= mm - 1;
-          const double s = __shfl_sync(kFull, s64[i], src);
-          const int dd = (int)__shfl_sync(kFull, d[i], src);
-          TopKInsert(top, k, s, dd, lane);
-          inserted = true;
-        }
-      }
-      if (multi && inserted && top.count == k) {
-        const double nk = TopKKth(top, k);
-        if (nk > published) {
-          published = nk;
-          if (lane == 0) atomicMax(&bv.thr[qi], (unsigned long long)__double_as_longlong(nk));
-        }
-      }
+    for (int i = 0; i < 4; i++) {
+      const unsigned hm = __ballot_sync(kFull, hit[i]);
+      if (!hm) continue;
+      st.matches += __popc(hm);
+      st.bytes += (8ull * m + 1ull) * __popc(hm);
+      if (COLLECT) CollectAppend(bv, q, qi, hit[i], (int)d[i], s64[i], lane);
+      else OfferToTopK(bv, qi, multi, k, hit[i], s64[i], (int)d[i], top, published, lane);
     }
   }
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
 }
 
+template <int CLASS> struct ScratchOf { typedef ProbeScratch type; };
+template <> struct ScratchOf<kClassOne> { typedef NoScratch type; };
+
 // Persistent search kernel of one query class: warps drain the class's unit queue.
 template <int CLASS>
-__global__ void __launch_bounds__(kThreadsPerCta)
+__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? 3 : 1)
 SearchKernel(const DevIndexView ix, const BatchView bv) {
   __shared__ CtaShared sh;
+  __shared__ typename ScratchOf<CLASS>::type scratch[kWarpsPerCta];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     const double c = ix.cache[i];
     sh.cache[i] = c;
@@ -476,7 +674,8 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  WarpScratch *ws = &sh.warp[threadIdx.x >> 5];
+  auto *ws = &scratch[threadIdx.x >> 5];
+  (void)ws;
   const uint32_t q_lo = bv.class_begin[CLASS], q_hi = bv.class_begin[CLASS + 1];
   const uint32_t n_units = bv.class_units[CLASS];
   UnitStats st = {0ull, 0ull, 0ull};
@@ -491,16 +690,17 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
     const uint32_t local = u - q.unit_begin;
     // driver list block range of this unit
     const uint4 li = __ldg(&ix.lists[q.term[q.driver]]);
-    const uint32_t b0 = local * kUnitBlocks;
-    const uint32_t b1 = min(b0 + kUnitBlocks, li.y);
-    if (CLASS == kClassOne) {
-      ProcessOneTerm<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
-    } else if (CLASS == kClassTwo) {
-      ProcessMulti<2, false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
-    } else if (CLASS == kClassMany) {
+    const uint32_t b0 = local * q.unit_blocks;
+    const uint32_t b1 = min(b0 + q.unit_blocks, li.y);
+    if constexpr (CLASS == kClassOne) {
+      ProcessOneTerm<false>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
+    } else if constexpr (CLASS == kClassTwo) {
+      ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
+    } else if constexpr (CLASS == kClassMany) {
       ProcessMulti<WSR_MAX_TERMS, false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     } else {
-      if (q.n_terms == 1) ProcessOneTerm<true>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
+      if (q.n_terms == 1) ProcessOneTerm<true>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
+      else if (q.n_terms == 2) ProcessTwo<true>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
       else ProcessMulti<WSR_MAX_TERMS, true>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     }
     units++;
@@ -546,20 +746,18 @@ MergeUnitsKernel(const BatchView bv, const uint32_t *__restrict__ multi, uint32_
   if (lane == 0) bv.n_hits[q.out_slot] = top.count;
 }
 
-// ---- K1: block decode ---------------------------------------------------------------------
+// ---- K1 entry points -----------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreadsPerCta)
 DecodeListKernel(const DevIndexView ix, uint32_t first_block, uint32_t n_blocks,
                  uint32_t *__restrict__ docs, uint32_t *__restrict__ tfs) {
-  __shared__ WarpScratch wsh[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
-  WarpScratch *ws = &wsh[threadIdx.x >> 5];
   const uint32_t b = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   if (b >= n_blocks) return;
   const uint4 info = __ldg(&ix.blk_info[first_block + b]);
-  const uint32_t n = BlkN(info.z);
+  const uint32_t n = ShN(info.z);
   uint32_t d[4], tf[4];
-  DecodeDocs4(ix, info, ws, lane, d);
-  DecodeTfs4(ix, info, ws, lane, tf);
+  DecodeDocs(ix, info, lane, d);
+  DecodeTfs(ix, info, lane, tf);
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const uint32_t e = 4u * lane + i;
@@ -572,17 +770,18 @@ DecodeListKernel(const DevIndexView ix, uint32_t first_block, uint32_t n_blocks,
 
 __global__ void __launch_bounds__(kThreadsPerCta)
 DecodeAllKernel(const DevIndexView ix, uint32_t n_blocks, unsigned long long *checksum) {
-  __shared__ WarpScratch wsh[kWarpsPerCta];
   const int lane = threadIdx.x & 31;
-  WarpScratch *ws = &wsh[threadIdx.x >> 5];
   const uint32_t warps = gridDim.x * kWarpsPerCta;
   unsigned long long sum = 0;
-  for (uint32_t b = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); b < n_blocks; b += warps) {
-    const uint4 info = __ldg(&ix.blk_info[b]);
-    const uint32_t n = BlkN(info.z);
+  uint32_t b = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  uint4 info = b < n_blocks ? __ldg(&ix.blk_info[b]) : make_uint4(0u, 0u, 0u, 0u);
+  for (; b < n_blocks; b += warps) {
+    const uint4 cur = info;
+    if (b + warps < n_blocks) info = __ldg(&ix.blk_info[b + warps]);
+    const uint32_t n = ShN(cur.z);
     uint32_t d[4], tf[4];
-    DecodeDocs4(ix, info, ws, lane, d);
-    DecodeTfs4(ix, info, ws, lane, tf);
+    DecodeDocs(ix, cur, lane, d);
+    DecodeTfs(ix, cur, lane, tf);
 #pragma unroll
     for (int i = 0; i < 4; i++)
       if (4u * lane + i < n) sum += (unsigned long long)d[i] + tf[i];
@@ -592,7 +791,34 @@ DecodeAllKernel(const DevIndexView ix, uint32_t n_blocks, unsigned long long *ch
   if (lane == 0 && sum) atomicAdd(checksum, sum);
 }
 
-// ---- cross-shard merge: rank of every gathered entry among all shards' entries -----------
+// Block-max refresh after the global statistics changed (document-partitioned load): recomputes
+// every block's upper bound of tf*(k1+1)/(tf+cache[norm]) with the new cache.
+__global__ void __launch_bounds__(kThreadsPerCta)
+RefreshBlockMaxKernel(const DevIndexView ix, uint32_t n_blocks, uint4 *blk_info_rw) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = gridDim.x * kWarpsPerCta;
+  for (uint32_t b = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); b < n_blocks; b += warps) {
+    const uint4 info = blk_info_rw[b];
+    const uint32_t n = ShN(info.z);
+    uint32_t d[4], tf[4];
+    DecodeDocs(ix, info, lane, d);
+    DecodeTfs(ix, info, lane, tf);
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (4u * lane + i < n) {
+        const double f = (double)tf[i];
+        const double x = (f * kK1Plus1) / (f + ix.cache[__ldg(ix.norms + d[i])]);
+        mx = fmaxf(mx, __double2float_ru(x));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    if (lane == 0) blk_info_rw[b].w = __float_as_uint(mx);
+  }
+}
+
+// ---- cross-shard merge: rank of every gathered entry among all shards' entries ---------------
 __device__ __forceinline__ bool HitBefore(double s1, int d1, double s2, int d2) {
   return s1 > s2 || (s1 == s2 && d1 < d2);
 }
@@ -627,7 +853,7 @@ __global__ void MergeShardsKernel(const wsr_hit *__restrict__ g, const int32_t *
   if (rank < k_stride) out[(size_t)q * k_stride + rank] = me;
 }
 
-// ---- collect mode epilogue -----------------------------------------------------------------
+// ---- collect mode epilogue ---------------------------------------------------------------------
 __global__ void CollectCopyKernel(const BatchView bv, uint32_t q_begin, uint32_t n_collect,
                                   const int32_t *__restrict__ doc, const double *__restrict__ score) {
   const uint32_t w = blockIdx.x;
@@ -652,23 +878,31 @@ __global__ void SegEndKernel(const BatchView bv, uint32_t q_begin, uint32_t n_co
   seg_end[i] = b + bv.seg_count[q_begin + i];
 }
 
+template <int CLASS>
+void LaunchClass(const DevIndexView &ix, const BatchView &b, int sm_count, cudaStream_t s) {
+  const uint32_t nu = b.class_units[CLASS];
+  if (!nu) return;
+  // persistent grid = resident CTAs per SM (occupancy query, cached) x SM count
+  static int occ = 0;
+  if (!occ) {
+    int o = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, SearchKernel<CLASS>, kThreadsPerCta, 0);
+    occ = o > 0 ? o : 1;
+  }
+  const uint32_t want = (nu + kWarpsPerCta - 1) / kWarpsPerCta;
+  const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sm_count * occ));
+  SearchKernel<CLASS><<<grid, kThreadsPerCta, 0, s>>>(ix, b);
+}
+
 }  // namespace
 
 void LaunchSearchClass(const DevIndexView &ix, const BatchView &b, int c, int sm_count,
                        cudaStream_t s) {
-  const int ctas_per_sm = 4;
-  {
-    const uint32_t nu = b.class_units[c];
-    if (nu) {
-      const uint32_t want = (nu + kWarpsPerCta - 1) / kWarpsPerCta;
-      const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sm_count * ctas_per_sm));
-      switch (c) {
-        case kClassOne: SearchKernel<kClassOne><<<grid, kThreadsPerCta, 0, s>>>(ix, b); break;
-        case kClassTwo: SearchKernel<kClassTwo><<<grid, kThreadsPerCta, 0, s>>>(ix, b); break;
-        case kClassMany: SearchKernel<kClassMany><<<grid, kThreadsPerCta, 0, s>>>(ix, b); break;
-        default: SearchKernel<kClassCollect><<<grid, kThreadsPerCta, 0, s>>>(ix, b); break;
-      }
-    }
+  switch (c) {
+    case kClassOne: LaunchClass<kClassOne>(ix, b, sm_count, s); break;
+    case kClassTwo: LaunchClass<kClassTwo>(ix, b, sm_count, s); break;
+    case kClassMany: LaunchClass<kClassMany>(ix, b, sm_count, s); break;
+    default: LaunchClass<kClassCollect>(ix, b, sm_count, s); break;
   }
 }
 
@@ -690,8 +924,16 @@ void LaunchDecodeAll(const DevIndexView &ix, uint32_t n_blocks, unsigned long lo
                      int sm_count, cudaStream_t s) {
   if (!n_blocks) return;
   const uint32_t grid = std::min<uint32_t>((n_blocks + kWarpsPerCta - 1) / kWarpsPerCta,
-                                      (uint32_t)(sm_count * 8));
+                                           (uint32_t)(sm_count * 8));
   DecodeAllKernel<<<grid, kThreadsPerCta, 0, s>>>(ix, n_blocks, checksum);
+}
+
+void LaunchRefreshBlockMax(const DevIndexView &ix, uint32_t n_blocks, uint4 *blk_info_rw,
+                           int sm_count, cudaStream_t s) {
+  if (!n_blocks) return;
+  const uint32_t grid = std::min<uint32_t>((n_blocks + kWarpsPerCta - 1) / kWarpsPerCta,
+                                           (uint32_t)(sm_count * 8));
+  RefreshBlockMaxKernel<<<grid, kThreadsPerCta, 0, s>>>(ix, n_blocks, blk_info_rw);
 }
 
 void LaunchMergeShards(const wsr_hit *gathered, const int32_t *gathered_n, int n_shards,

@@ -11,7 +11,7 @@ namespace wsr {
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kMaxFastK = 32;      // top-k held one entry per lane
-constexpr int kUnitBlocks = 16;    // driver-list blocks per warp work unit
+constexpr int kUnitBlocks = 16;    // max driver-list blocks per warp work unit
 
 // Read-only view of the HBM-resident index (layout: host_index.h).
 struct DevIndexView {
@@ -29,7 +29,8 @@ struct DevIndexView {
 // One planned query. unit_begin = index of its first work unit in its class queue.
 struct DevQuery {
   uint32_t term[WSR_MAX_TERMS];  // query order
-  uint32_t n_terms;              // 0 => produces nothing
+  uint16_t n_terms;
+  uint16_t unit_blocks;          // driver-list blocks per work unit of this query
   uint32_t k;
   uint32_t unit_begin;
   uint32_t n_units;
@@ -59,6 +60,7 @@ struct BatchView {
   unsigned long long *thr;     // per planned query: best known k-th score (double bits)
   DevCounters *counters;
   uint32_t k_stride;
+  uint32_t doc_base;           // added to every emitted doc id (document-partitioned shards)
   // collect mode (k > kMaxFastK): every match is appended to the query's segment
   int32_t *seg_doc;
   double *seg_score;
@@ -76,6 +78,8 @@ void LaunchDecodeList(const DevIndexView &ix, uint32_t first_block, uint32_t n_b
                       uint32_t *docs, uint32_t *tfs, cudaStream_t s);
 void LaunchDecodeAll(const DevIndexView &ix, uint32_t n_blocks, unsigned long long *checksum,
                      int sm_count, cudaStream_t s);
+void LaunchRefreshBlockMax(const DevIndexView &ix, uint32_t n_blocks, uint4 *blk_info_rw,
+                           int sm_count, cudaStream_t s);
 void LaunchMergeShards(const wsr_hit *gathered, const int32_t *gathered_n, int n_shards,
                        int n_queries, int k_stride, wsr_hit *out, int32_t *out_n,
                        cudaStream_t s);

@@ -95,6 +95,7 @@ struct wsr_index {
   DevBuf<double> d_idf;
   DevIndexView view;
   int64_t n_blocks = 0, payload_bytes = 0, hbm_bytes = 0;
+  uint32_t doc_base = 0;          // global id of this partition's doc 0
   std::mutex pool_mu;
   std::vector<wsr_batch *> pool;  // reusable batches for wsr_search / wsr_search_batch
 };
@@ -172,12 +173,20 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
       b->listed_postings += ix->host.lists[q.term_ids[t]].df_shard;
       b->listed_bytes += ix->host.list_alg_bytes[q.term_ids[t]];
     }
-    dq.n_terms = q.n_terms;
+    dq.n_terms = (uint16_t)q.n_terms;
     dq.k = q.k;
     dq.driver = best;
     dq.out_slot = (uint32_t)i;
     const ListInfo &drv = ix->host.lists[q.term_ids[best]];
-    dq.n_units = (drv.n_blocks + kUnitBlocks - 1) / kUnitBlocks;
+    // Unit size: a unit's work is its driver blocks plus the probe-list blocks they can reach,
+    // so skewed queries (long probe lists) get fewer driver blocks per unit.
+    uint64_t probe_blocks = 0;
+    for (uint32_t t = 0; t < q.n_terms; t++)
+      if (t != best) probe_blocks += ix->host.lists[q.term_ids[t]].n_blocks;
+    const uint64_t ratio = drv.n_blocks ? (probe_blocks + drv.n_blocks - 1) / drv.n_blocks : 0;
+    uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kUnitBlocks, 64 / (1 + ratio)));
+    dq.unit_blocks = (uint16_t)ub;
+    dq.n_units = (drv.n_blocks + ub - 1) / ub;
     int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
             : q.n_terms == 1 ? kClassOne : q.n_terms == 2 ? kClassTwo : kClassMany;
     cls[c].push_back(dq);
@@ -251,6 +260,7 @@ int UploadBatch(wsr_batch *b) {
   v.thr = b->d_thr.p;
   v.counters = b->d_counters.p;
   v.k_stride = (uint32_t)b->k_stride;
+  v.doc_base = b->idx->doc_base;
   v.seg_doc = b->d_seg_doc.p;
   v.seg_score = b->d_seg_score.p;
   v.seg_count = b->d_seg_count.p;
