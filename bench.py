@@ -55,7 +55,8 @@ def parse_args():
     ap.add_argument("--mu", type=float, default=5.34)
     ap.add_argument("--queries", type=int, default=100_000)
     ap.add_argument("--workload", default="two_term",
-                    choices=["two_term", "single_high", "single_low", "multi_term", "mix_aol"])
+                    choices=["two_term", "two_term_hh", "two_term_lh", "two_term_ll", "single_high",
+                             "single_low", "multi_term", "mix_aol"])
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--high-df", type=int, default=10000)

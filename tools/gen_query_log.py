@@ -38,6 +38,24 @@ def single_term(rng, groups, group, n):
     return [g[rng.randint(0, len(g) - 1)] for _ in range(n)]
 
 
+def two_term_fixed(rng, groups, n, g1name, g2name):
+    """Diagnostic variants of two_term with the groups pinned (hh / lh / ll)."""
+    queries, seen = [], set()
+    limit = n * 50
+    g1, g2 = groups[g1name], groups[g2name]
+    while len(queries) < n and limit > 0:
+        limit -= 1
+        t1 = g1[rng.randint(0, len(g1) - 1)]
+        t2 = g2[rng.randint(0, len(g2) - 1)]
+        if t2 == t1:
+            continue
+        q = " ".join(sorted([t1, t2]))
+        if q not in seen:
+            seen.add(q)
+            queries.append(q)
+    return queries
+
+
 def two_term(rng, groups, n):
     names = [g for g in ("low", "high") if groups[g]]
     queries, seen = [], set()
@@ -108,6 +126,12 @@ def generate(kind, groups, n, seed):
         return single_term(rng, groups, "high", n)
     if kind == "two_term":
         return two_term(rng, groups, n)
+    if kind == "two_term_hh":
+        return two_term_fixed(rng, groups, n, "high", "high")
+    if kind == "two_term_lh":
+        return two_term_fixed(rng, groups, n, "low", "high")
+    if kind == "two_term_ll":
+        return two_term_fixed(rng, groups, n, "low", "low")
     if kind == "multi_term":
         return multi_term(rng, groups, n)
     if kind == "mix_aol":
@@ -119,7 +143,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--terms", required=True, help="file with 'term df' per line")
     ap.add_argument("--kind", required=True,
-                    choices=["single_low", "single_high", "two_term", "multi_term", "mix_aol"])
+                    choices=["single_low", "single_high", "two_term", "two_term_hh", "two_term_lh",
+                             "two_term_ll", "multi_term", "mix_aol"])
     ap.add_argument("--n", type=int, required=True)
     ap.add_argument("--high-df", type=int, default=10000)
     ap.add_argument("--seed", type=int, default=1)

@@ -128,6 +128,8 @@ void PackTfRecords(const uint32_t (*tf)[4], int nl, const BlockShape &sh, std::v
 struct Chunk {               // output of one slice of terms
   size_t term_begin = 0, term_end = 0;
   std::vector<ListInfo> lists;
+  std::vector<uint32_t> filters;
+  std::vector<uint64_t> list_flt;
   std::vector<uint64_t> list_alg_bytes;
   std::vector<BlockInfo> blk_info;
   std::vector<uint32_t> blk_last;
@@ -242,6 +244,23 @@ struct Builder {
       alg += AlgorithmicBytes(sh);
       base = p;
     }
+    // doc-range-partitioned Bloom filter of this (shard-local) list
+    uint64_t flt = 0xFFFFFFFFull << 32;
+    if (b - a >= kFilterMinDf) {
+      const uint64_t range = (uint64_t)doc_hi - doc_lo;
+      uint32_t g = 0;
+      while (g < 31 && (range >> (g + 1)) >= (uint64_t)(b - a) / 4 + 1) g++;   // ~4 postings per word
+      const size_t words = (size_t)(range >> g) + 1;
+      const size_t at = c->filters.size();
+      c->filters.resize(at + words, 0u);
+      uint32_t *w = c->filters.data() + at;
+      for (size_t i = a; i < b; i++) {
+        const uint32_t doc = (*docs)[i];
+        w[(doc - doc_lo) >> g] |= (1u << FilterBit1(doc)) | (1u << FilterBit2(doc));
+      }
+      flt = ((uint64_t)g << 32) | (uint32_t)at;
+    }
+    c->list_flt.push_back(flt);
     c->lists.push_back(li);
     c->list_alg_bytes.push_back(alg);
     c->postings += (int64_t)(b - a);
@@ -410,12 +429,14 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
     worker();
     for (auto &t : pool) t.join();
   }
-  size_t tot_blocks = 0, tot_payload = 0;
+  size_t tot_blocks = 0, tot_payload = 0, tot_flt = 0;
   for (auto &c : chunks) {
     if (!c.err.empty()) { *err = c.err; return false; }
     tot_blocks += c.blk_info.size();
     tot_payload += c.payload.size();
+    tot_flt += c.filters.size();
   }
+  if (tot_flt >= 0xFFFFFFF0ull) { *err = "filters exceed 2^32 words"; return false; }
   if (tot_payload / 16 > 0xFFFFFFF0ull) { *err = "payload exceeds 64 GiB addressable by u32 offsets"; return false; }
   if (tot_blocks >= (1ull << 25)) { *err = "more than 2^25 blocks on one shard (hit records pack block<<7|slot)"; return false; }
 
@@ -425,13 +446,17 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
   ix.blk_info.resize(tot_blocks);
   ix.blk_last.resize(tot_blocks);
   ix.payload.assign(tot_payload + 1024, 0);  // tail pad: prefetchers read up to 512 B past a block
-  std::vector<size_t> blk_base(chunks.size()), pay_base(chunks.size());
-  size_t bb = 0, pb = 0;
+  ix.filters.assign(tot_flt + 1, 0u);
+  ix.list_flt.resize(n_terms);
+  std::vector<size_t> blk_base(chunks.size()), pay_base(chunks.size()), flt_base(chunks.size());
+  size_t bb = 0, pb = 0, fb = 0;
   for (size_t i = 0; i < chunks.size(); i++) {
     blk_base[i] = bb;
     pay_base[i] = pb;
+    flt_base[i] = fb;
     bb += chunks[i].blk_info.size();
     pb += chunks[i].payload.size();
+    fb += chunks[i].filters.size();
     ix.n_postings += chunks[i].postings;
     ix.n_postings_global += chunks[i].postings_global;
   }
@@ -447,7 +472,13 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
         li.first_block += b0;
         ix.lists[c.term_begin + j] = li;
         ix.list_alg_bytes[c.term_begin + j] = c.list_alg_bytes[j];
+        uint64_t f = c.list_flt[j];
+        if ((f >> 32) != 0xFFFFFFFFull) f = (f & 0xFFFFFFFF00000000ull) | (uint32_t)((f & 0xFFFFFFFFull) + flt_base[i]);
+        ix.list_flt[c.term_begin + j] = f;
       }
+      if (!c.filters.empty())
+        memcpy(ix.filters.data() + flt_base[i], c.filters.data(), c.filters.size() * 4);
+      std::vector<uint32_t>().swap(c.filters);
       for (size_t j = 0; j < c.blk_info.size(); j++) {
         BlockInfo bi = c.blk_info[j];
         bi.payload_off16 += p0;

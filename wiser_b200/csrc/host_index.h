@@ -24,7 +24,15 @@
 //                       the algorithmic bytes of the roofline; max_tfn = upper bound of
 //                       tf*(k1+1)/(tf+cache[norm]) over the block (block-max metadata).
 //   blk_last  u32[]     last doc id of each block (searched when skipping)
+//   blk_max   f32[]     copy of max_tfn as its own array: single-term queries scan it coalesced
+//                       to bound the k-th score before touching any payload
 //   lists     uint4[]   per term {first_block, n_blocks, df_shard, df_global}
+//   list_flt  uint2[]   per term {first filter word, shift g | 0xFFFFFFFF = no filter}
+//   filters   u32[]     per list a doc-range-partitioned Bloom filter, ~8 bits per posting:
+//                       doc d sets bits h1(d), h2(d) of word (d - doc_lo) >> g. An AND query
+//                       tests the driver's candidates against the other lists' filters first, so
+//                       the exact probe (block lookup + record search) runs only for the few
+//                       percent that may be present. No false negatives.
 //   norms     u8[]      DocLengthCharStore bytes indexed by GLOBAL doc id
 //   cache     f64[256]  Bm25Similarity::cache_ (scoring.h:85-90)
 #ifndef WSR_HOST_INDEX_H
@@ -83,6 +91,11 @@ inline BlockShape UnpackShape(uint32_t bits) {
 inline uint32_t RefStreamBytes(int n, int bits) {
   return (uint32_t)(((uint64_t)n * bits + 127) / 128 * 16);
 }
+// Bloom filter bit positions inside a filter word (identical on host and device).
+inline uint32_t FilterBit1(uint32_t doc) { return (doc * 0x9E3779B1u) >> 27; }
+inline uint32_t FilterBit2(uint32_t doc) { return (doc * 0x85EBCA6Bu) >> 27; }
+constexpr uint32_t kFilterMinDf = 256;   // shorter lists are probed directly
+
 inline uint32_t AlgorithmicBytes(const BlockShape &s) {
   return RefStreamBytes(s.n, s.ref_dbits) + RefStreamBytes(s.n, s.ref_tbits) + 16;
 }
@@ -118,6 +131,8 @@ struct HostIndex {
   std::vector<BlockInfo> blk_info;
   std::vector<uint32_t> blk_last;
   std::vector<uint8_t> payload;
+  std::vector<uint32_t> filters;
+  std::vector<uint64_t> list_flt;     // low 32: first word, high 32: shift (0xFFFFFFFF none)
   std::vector<uint64_t> list_alg_bytes;  // algorithmic bytes of all blocks of each list
   int64_t n_postings = 0, n_postings_global = 0;
   int shard = 0, n_shards = 1;

@@ -61,21 +61,25 @@ __device__ __forceinline__ uint32_t AlgBytes(uint32_t bits, bool with_tf) {
 // ---- K1: block decode ------------------------------------------------------------------------
 // Doc ids of the four postings of record `rec` = [f:w0][d1:b][d2:b][d3:b] (host_index.h).
 // Padded slots of a block's last record repeat its last doc.
-__device__ __forceinline__ void DecodeRecord(const DevIndexView &ix, const uint4 info, uint32_t rec,
-                                             uint32_t d[4]) {
-  const uint32_t bits = info.z;
-  const uint32_t w0 = ShW0(bits), b = ShB(bits), rc = ShRcode(bits);
+__device__ __forceinline__ uint4 LoadRecord(const DevIndexView &ix, const uint4 info, uint32_t rec) {
+  const uint32_t rc = ShRcode(info.z);
   const uint4 *src = ix.payload + info.y;
-  uint32_t r0, r1 = 0, r2 = 0, r3 = 0;
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
   if (rc == 0) {
-    r0 = __ldg(reinterpret_cast<const uint32_t *>(src) + rec);
+    r.x = __ldg(reinterpret_cast<const uint32_t *>(src) + rec);
   } else if (rc == 1) {
     const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src) + rec);
-    r0 = v.x; r1 = v.y;
+    r.x = v.x; r.y = v.y;
   } else {
-    const uint4 v = __ldg(src + rec);
-    r0 = v.x; r1 = v.y; r2 = v.z; r3 = v.w;
+    r = __ldg(src + rec);
   }
+  return r;
+}
+
+__device__ __forceinline__ void DecodeRaw(const uint4 info, const uint4 raw, uint32_t d[4]) {
+  const uint32_t bits = info.z;
+  const uint32_t w0 = ShW0(bits), b = ShB(bits), rc = ShRcode(bits);
+  const uint32_t r0 = raw.x, r1 = raw.y, r2 = raw.z, r3 = raw.w;
   const uint32_t m0 = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
   const uint32_t mb = b >= 32u ? 0xffffffffu : ((1u << b) - 1u);
   uint32_t f, d1, d2, d3;
@@ -107,6 +111,11 @@ __device__ __forceinline__ void DecodeRecord(const DevIndexView &ix, const uint4
   d[1] = d[0] + d1;
   d[2] = d[1] + d2;
   d[3] = d[2] + d3;
+}
+
+__device__ __forceinline__ void DecodeRecord(const DevIndexView &ix, const uint4 info, uint32_t rec,
+                                             uint32_t d[4]) {
+  DecodeRaw(info, LoadRecord(ix, info, rec), d);
 }
 
 // Whole block: lane l decodes record l (postings 4l..4l+3); lanes past the records get kNoDoc.
@@ -209,9 +218,14 @@ struct HitRec {
 };
 
 // Per-warp scratch of the intersecting kernels.
+struct CandRec {
+  uint32_t doc;
+  uint32_t pos_a;
+};
 struct __align__(16) ProbeScratch {
   uint32_t win[32];              // the probe list's blk_last window, for per-lane block lookup
-  HitRec hits[kHitCap];
+  CandRec cand[kHitCap];         // filter survivors awaiting the exact probe (doc ascending)
+  HitRec hits[kHitCap];          // intersection hits awaiting scoring
 };
 struct __align__(16) NoScratch { uint32_t unused; };
 
@@ -269,10 +283,14 @@ __device__ __forceinline__ void OfferToTopK(const BatchView &bv, uint32_t qi, bo
   }
 }
 
-// ---- single-term units: SingleTermQueryProcessor::Process, query_processing.h:632-641 --------
-// Every posting is a hit. Blocks whose block-max score cannot reach the running k-th score are
-// skipped without touching their payload; surviving postings are pre-filtered with an fp32
-// upper bound and only candidates are re-scored in exact fp64.
+// ---- single-term queries: SingleTermQueryProcessor::Process, query_processing.h:632-641 ------
+// Every posting is a hit, so the work is choosing which blocks can hold a top-k document.
+// Fast path (k <= 32, one warp per query): the list's block-max array is scanned coalesced to
+// find the k-th largest block maximum — k different blocks each hold a document scoring at
+// least that, so it bounds the k-th best score from below before any payload is read. Blocks
+// whose block-max score is below the bound are skipped; survivors are decoded, pre-filtered
+// with an fp32 upper bound, and only candidates are re-scored in exact fp64.
+// Collect path (k > 32): all postings are scored and appended, split into units.
 template <bool COLLECT>
 __device__ void ProcessOneTerm(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
                                uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
@@ -282,59 +300,87 @@ __device__ void ProcessOneTerm(const DevIndexView &ix, const BatchView &bv, cons
   const double idf = __ldg(&ix.idf[term]);
   const float idf_up = __double2float_ru(idf);
   const int k = (int)q.k;
-  const bool multi = q.n_units > 1;
   TopK top;
   TopKInit(top);
-  double thr_shared = 0.0, published = 0.0;
+  double published = 0.0;
+  double lb = 0.0;   // lower bound of the k-th best score of the whole list
+  const float *__restrict__ bmax = ix.blk_max + li.x;
 
-  uint4 info = __ldg(&ix.blk_info[li.x + b0]);
-  for (uint32_t j = b0; j < b1; j++) {
-    const uint4 cur = info;
-    if (j + 1 < b1) info = __ldg(&ix.blk_info[li.x + j + 1]);
-    const uint32_t n = ShN(cur.z);
-    double kth = -1.0;
-    if (!COLLECT) {
-      if (multi) thr_shared = fmax(thr_shared, __longlong_as_double((long long)__ldcg(&bv.thr[qi])));
-      const bool full = top.count == k;
-      kth = full ? TopKKth(top, k) : -1.0;
-      // upper bound of every exact score in the block (rounded up at each step)
-      const double ub = (double)(idf_up * __uint_as_float(cur.w) * 1.00001f);
-      if (ub < thr_shared || (full && ub <= kth)) continue;
-    }
-    uint32_t d[4], tf[4];
-    DecodeDocs(ix, cur, lane, d);
-    DecodeTfs(ix, cur, lane, tf);
-    st.decoded += n;
-    st.bytes += AlgBytes(cur.z, true) + n;   // + one norm byte per posting
-    st.matches += n;
-
-    bool pass[4];
-    double s64[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const bool valid = 4u * lane + i < n;
-      pass[i] = valid;
-      s64[i] = 0.0;
-      if (valid) {
-        const uint32_t nb = __ldg(ix.norms + d[i]);
-        if (!COLLECT) {
-          const float f = (float)tf[i];
-          const float s32 = idf_up * __fdividef(f * 2.2f, f + sh->cache32[nb]) * 1.00001f;
-          pass[i] = (double)s32 >= fmax(thr_shared, kth);
-        }
-        if (pass[i]) {
-          s64[i] = __dadd_rn(0.0, TermScore(idf, tf[i], sh->cache[nb]));
-          if (!COLLECT) pass[i] = !(s64[i] < thr_shared) && !(s64[i] < kth);
-        }
+  if (!COLLECT && b1 - b0 > (uint32_t)k) {
+    // k-th largest block maximum (TopK reused with the block index as tie-breaker)
+    TopK bt;
+    TopKInit(bt);
+    for (uint32_t base = b0; base < b1; base += 32) {
+      const uint32_t j = base + lane;
+      const float v = j < b1 ? __ldg(bmax + j) : -1.f;
+      const double kth = bt.count == k ? TopKKth(bt, k) : -1.0;
+      unsigned m = __ballot_sync(kFull, (double)v > kth);
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        TopKInsert(bt, k, (double)__shfl_sync(kFull, v, src), (int)(base + src), lane);
       }
     }
+    st.bytes += 4ull * (b1 - b0);
+    // the best document of a block scores idf * tfn with block_max >= tfn > block_max*(1 - 2^-23)
+    if (bt.count == k) lb = __dmul_rn(__dmul_rn(idf, TopKKth(bt, k)), 1.0 - 3e-7);
+  }
+
+  for (uint32_t base = b0; base < b1; base += 32) {
+    unsigned need;
     if (COLLECT) {
-#pragma unroll
-      for (int i = 0; i < 4; i++) CollectAppend(bv, q, qi, pass[i], (int)d[i], s64[i], lane);
+      need = base + 32 <= b1 ? kFull : ((1u << (b1 - base)) - 1u);
     } else {
+      const uint32_t j = base + lane;
+      const float v = j < b1 ? __ldg(bmax + j) : -1.f;
+      // upper bound of every exact score in the block (rounded up at each step)
+      need = __ballot_sync(kFull, j < b1 && (double)(idf_up * v * 1.00001f) >= lb);
+    }
+    while (need) {
+      const uint32_t j = base + (uint32_t)(__ffs(need) - 1);
+      need &= need - 1;
+      const uint4 cur = __ldg(&ix.blk_info[li.x + j]);
+      const uint32_t n = ShN(cur.z);
+      double kth = -1.0;
+      if (!COLLECT && top.count == k) {
+        kth = TopKKth(top, k);
+        // later blocks hold larger doc ids: a tie with the k-th entry cannot displace it
+        if ((double)(idf_up * __uint_as_float(cur.w) * 1.00001f) <= kth) continue;
+      }
+      uint32_t d[4], tf[4];
+      DecodeDocs(ix, cur, lane, d);
+      DecodeTfs(ix, cur, lane, tf);
+      st.decoded += n;
+      st.bytes += AlgBytes(cur.z, true) + n;   // + one norm byte per posting
+      st.matches += n;
+      bool pass[4];
+      double s64[4];
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-        OfferToTopK(bv, qi, multi, k, pass[i], s64[i], (int)d[i], top, published, lane);
+      for (int i = 0; i < 4; i++) {
+        const bool valid = 4u * lane + i < n;
+        pass[i] = valid;
+        s64[i] = 0.0;
+        if (valid) {
+          const uint32_t nb = __ldg(ix.norms + d[i]);
+          if (!COLLECT) {
+            const float f = (float)tf[i];
+            const float s32 = idf_up * __fdividef(f * 2.2f, f + sh->cache32[nb]) * 1.00001f;
+            pass[i] = (double)s32 >= fmax(lb, kth);
+          }
+          if (pass[i]) {
+            s64[i] = __dadd_rn(0.0, TermScore(idf, tf[i], sh->cache[nb]));
+            if (!COLLECT) pass[i] = !(s64[i] < lb) && !(s64[i] < kth);
+          }
+        }
+      }
+      if (COLLECT) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) CollectAppend(bv, q, qi, pass[i], (int)d[i], s64[i], lane);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          OfferToTopK(bv, qi, false, k, pass[i], s64[i], (int)d[i], top, published, lane);
+      }
     }
   }
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
@@ -441,19 +487,23 @@ __device__ __forceinline__ bool ProbeCandidates(const DevIndexView &ix, ProbeLis
     rec[i] = 0;
     if (alive[i]) info[i] = __ldg(&ix.blk_info[p.first + j[i]]);
   }
+  uint32_t nl[4], rcs[4], m0[4], rel[4];
+  const uint32_t *rp[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const uint32_t bits = info[i].z, w0 = ShW0(bits);
+    nl[i] = alive[i] ? (ShN(bits) + 3u) >> 2 : 0u;
+    rcs[i] = ShRcode(bits);
+    m0[i] = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
+    rp[i] = reinterpret_cast<const uint32_t *>(ix.payload + info[i].y);
+    rel[i] = d[i] - info[i].x;
+  }
 #pragma unroll
   for (uint32_t s = 16; s; s >>= 1) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const uint32_t bits = info[i].z;
       const uint32_t mid = rec[i] + s;
-      if (alive[i] && mid < ((ShN(bits) + 3u) >> 2)) {
-        const uint32_t w0 = ShW0(bits);
-        const uint32_t m0 = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
-        const uint32_t head = __ldg(reinterpret_cast<const uint32_t *>(ix.payload + info[i].y) +
-                                    (mid << ShRcode(bits)));
-        if (info[i].x + (head & m0) <= d[i]) rec[i] = mid;
-      }
+      if (mid < nl[i] && (__ldg(rp[i] + (mid << rcs[i])) & m0[i]) <= rel[i]) rec[i] = mid;
     }
   }
   // ---- decode that record and compare
@@ -491,6 +541,89 @@ __device__ __forceinline__ bool ProbeCandidates(const DevIndexView &ix, ProbeLis
   return true;
 }
 
+// Bloom pre-test of one candidate against a probe list's filter (no false negatives).
+struct ListFilter {
+  const uint32_t *words;   // nullptr: the list has no filter, everything passes
+  uint32_t shift;
+};
+__device__ __forceinline__ ListFilter FilterOf(const DevIndexView &ix, uint32_t term) {
+  const uint2 f = __ldg(&ix.list_flt[term]);
+  ListFilter lf;
+  lf.words = f.y == 0xffffffffu ? nullptr : ix.filters + f.x;
+  lf.shift = f.y & 31u;
+  return lf;
+}
+__device__ __forceinline__ bool FilterPass(const DevIndexView &ix, const ListFilter &lf, uint32_t doc) {
+  if (lf.words == nullptr) return true;
+  const uint32_t w = __ldg(lf.words + ((doc - ix.doc_lo) >> lf.shift));
+  const uint32_t need = (1u << ((doc * 0x9E3779B1u) >> 27)) | (1u << ((doc * 0x85EBCA6Bu) >> 27));
+  return (w & need) == need;
+}
+
+// Exact probe of ONE candidate per lane (filter survivors, doc ascending across lanes):
+// skip metadata -> block, 5-step search over the block's record heads -> record, one record
+// decode -> membership. Returns false when the list has nothing at or after the first candidate.
+__device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, uint32_t *win, bool has,
+                                         uint32_t x, bool *hit, uint32_t *pos, int lane,
+                                         UnitStats &st) {
+  *hit = false;
+  const uint32_t mn = __reduce_min_sync(kFull, has ? x : kNoDoc);
+  const uint32_t mx = __reduce_max_sync(kFull, has ? x : 0u);
+  const uint32_t j_lo = ProbeFind(p, mn, lane);
+  if (j_lo == kNoDoc) return false;
+  uint32_t j;
+  if (mx <= __shfl_sync(kFull, p.wl, 31)) {
+    __syncwarp();
+    win[lane] = p.wl;
+    __syncwarp();
+    uint32_t c = 0;
+#pragma unroll
+    for (uint32_t s = 16; s; s >>= 1)
+      if (win[c + s - 1] < x) c += s;
+    c += win[c] < x;
+    j = p.wbase + c;
+    if (c >= 32u) has = false;
+  } else {
+    uint32_t lo = j_lo, hi = p.nb;
+    if (has) {
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(p.last + mid) < x) lo = mid + 1; else hi = mid;
+      }
+    }
+    j = lo;
+  }
+  if (j >= p.nb) has = false;
+  uint4 info = make_uint4(0u, 0u, 0u, 0u);
+  if (has) {
+    info = __ldg(&ix.blk_info[p.first + j]);
+    const uint32_t bits = info.z;
+    const uint32_t nl = (ShN(bits) + 3u) >> 2, rcs = ShRcode(bits), w0 = ShW0(bits);
+    const uint32_t m0 = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
+    const uint32_t *rp = reinterpret_cast<const uint32_t *>(ix.payload + info.y);
+    const uint32_t rel = x - info.x;     // x > base of its block
+    uint32_t rec = 0;
+#pragma unroll
+    for (uint32_t s = 16; s; s >>= 1) {
+      const uint32_t mid = rec + s;
+      if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) rec = mid;
+    }
+    uint32_t e[4];
+    DecodeRecord(ix, info, rec, e);
+    const int slot = e[0] == x ? 0 : e[1] == x ? 1 : e[2] == x ? 2 : e[3] == x ? 3 : -1;
+    *hit = slot >= 0;
+    *pos = ((p.first + j) << 7) | (4u * rec + (uint32_t)max(slot, 0));
+  }
+  // accounting: each distinct probe block touched counts once (candidates are doc-ascending)
+  {
+    const uint32_t prev = __shfl_up_sync(kFull, has ? j : kNoDoc, 1);
+    const bool fresh = has && (lane == 0 || j != prev);
+    st.decoded += __reduce_add_sync(kFull, fresh ? ShN(info.z) : 0u);
+    st.bytes += __reduce_add_sync(kFull, fresh ? AlgBytes(info.z, false) : 0u);
+  }
+  return true;
+}
+
 // ---- two-term units (the headline path): TwoTermNonPhraseQueryProcessor::Process -------------
 // Driver blocks are walked in order; for the smallest unresolved candidate the probe block is
 // located, staged once, and every candidate that falls inside it is resolved in the same pass.
@@ -523,6 +656,30 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
   __syncwarp();
 }
 
+// Probes the first n (<= 32) queued survivors and appends the hits to the hit queue.
+__device__ __forceinline__ bool ProbeBatch(const DevIndexView &ix, ProbeList &pb, ProbeScratch *ws,
+                                           int base, int n, int &nq, int lane, UnitStats &st) {
+  const bool has = lane < n;
+  CandRec c;
+  c.doc = 0; c.pos_a = 0;
+  if (has) c = ws->cand[base + lane];
+  bool hit;
+  uint32_t pos = 0;
+  const bool more = ProbeOne(ix, pb, ws->win, has, c.doc, &hit, &pos, lane, st);
+  const unsigned m = __ballot_sync(kFull, hit);
+  if (m) {
+    if (hit) {
+      HitRec h;
+      h.doc = c.doc;
+      h.pos_a = c.pos_a;
+      h.pos_b = pos;
+      ws->hits[nq + __popc(m & ((1u << lane) - 1u))] = h;
+    }
+    nq += __popc(m);
+  }
+  return more;
+}
+
 template <bool COLLECT>
 __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
                            uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
@@ -531,6 +688,7 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
   const uint4 la = __ldg(&ix.lists[q.term[drv]]);
   const uint4 lb = __ldg(&ix.lists[q.term[oth]]);
   const double idf0 = __ldg(&ix.idf[q.term[0]]), idf1 = __ldg(&ix.idf[q.term[1]]);
+  const ListFilter flt = FilterOf(ix, q.term[oth]);
   const uint32_t first_a = la.x;
   const bool multi = q.n_units > 1;
   TopK top;
@@ -538,42 +696,71 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
   double published = 0.0;
   ProbeList pb;
   ProbeInit(pb, ix, lb, lane);
-  int nq = 0;
+  int nq = 0, nc = 0;
+  bool more = true;
 
-  uint4 info_a = __ldg(&ix.blk_info[first_a + b0]);
-  for (uint32_t ja = b0; ja < b1; ja++) {
-    const uint4 cur = info_a;
-    if (ja + 1 < b1) info_a = __ldg(&ix.blk_info[first_a + ja + 1]);
-    uint32_t d[4], pos[4];
-    DecodeDocs(ix, cur, lane, d);
-    const uint32_t na = ShN(cur.z);
+  // driver blocks: info two ahead, raw record one ahead
+  uint4 info_cur = __ldg(&ix.blk_info[first_a + b0]);
+  uint4 info_nxt = b0 + 1 < b1 ? __ldg(&ix.blk_info[first_a + b0 + 1]) : info_cur;
+  uint4 raw_cur = make_uint4(0u, 0u, 0u, 0u);
+  if ((uint32_t)lane < ((ShN(info_cur.z) + 3u) >> 2)) raw_cur = LoadRecord(ix, info_cur, (uint32_t)lane);
+  for (uint32_t ja = b0; ja < b1 && more; ja++) {
+    uint4 raw_nxt = make_uint4(0u, 0u, 0u, 0u), info_nxt2 = info_nxt;
+    if (ja + 1 < b1 && (uint32_t)lane < ((ShN(info_nxt.z) + 3u) >> 2))
+      raw_nxt = LoadRecord(ix, info_nxt, (uint32_t)lane);
+    if (ja + 2 < b1) info_nxt2 = __ldg(&ix.blk_info[first_a + ja + 2]);
+
+    const uint32_t na = ShN(info_cur.z);
+    uint32_t d[4];
+    DecodeRaw(info_cur, raw_cur, d);
     st.decoded += na;
-    st.bytes += AlgBytes(cur.z, false);
-    bool alive[4];
+    st.bytes += AlgBytes(info_cur.z, false);
+    // ---- Bloom pre-test, then compaction in (lane, slot) = doc order
+    bool pass[4];
+    unsigned bm[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) alive[i] = 4u * lane + i < na;   // padded slots repeat the last doc
-    const bool more = ProbeCandidates(ix, pb, ws->win, d, alive, pos, lane, st);
+    for (int i = 0; i < 4; i++) {
+      pass[i] = 4u * lane + i < na && FilterPass(ix, flt, d[i]);   // padded slots repeat the last doc
+      bm[i] = __ballot_sync(kFull, pass[i]);
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    int at = nc + __popc(bm[0] & lt) + __popc(bm[1] & lt) + __popc(bm[2] & lt) + __popc(bm[3] & lt);
     const uint32_t ga = (first_a + ja) << 7;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      const unsigned m = __ballot_sync(kFull, alive[i]);
-      if (m) {
-        if (alive[i]) {
-          HitRec h;
-          h.doc = d[i];
-          h.pos_a = ga | (4u * lane + i);
-          h.pos_b = pos[i];
-          ws->hits[nq + __popc(m & ((1u << lane) - 1u))] = h;
-        }
-        nq += __popc(m);
+      if (pass[i]) {
+        CandRec c;
+        c.doc = d[i];
+        c.pos_a = ga | (4u * lane + i);
+        ws->cand[at++] = c;
       }
     }
-    if (nq >= 32) {
-      FlushHits<COLLECT>(ix, bv, q, qi, sh, ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
-      nq = 0;
+    nc += __popc(bm[0]) + __popc(bm[1]) + __popc(bm[2]) + __popc(bm[3]);
+    __syncwarp();
+    // ---- exact probe, 32 survivors at a time
+    int base = 0;
+    for (; nc - base >= 32 && more; base += 32) {
+      more = ProbeBatch(ix, pb, ws, base, 32, nq, lane, st);
+      if (nq >= 32) {
+        FlushHits<COLLECT>(ix, bv, q, qi, sh, ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
+        nq = 0;
+      }
     }
-    if (!more) break;   // probe list exhausted: nothing further can match
+    if (base) {   // move the leftover (< 32) to the front
+      CandRec c;
+      c.doc = 0; c.pos_a = 0;
+      const bool mv = base + lane < nc;
+      if (mv) c = ws->cand[base + lane];
+      __syncwarp();
+      if (mv) ws->cand[lane] = c;
+      nc -= base;
+      __syncwarp();
+    }
+    info_cur = info_nxt;
+    raw_cur = raw_nxt;
+    info_nxt = info_nxt2;
   }
+  if (nc && more) ProbeBatch(ix, pb, ws, 0, nc, nq, lane, st);
   if (nq) FlushHits<COLLECT>(ix, bv, q, qi, sh, ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
 }
@@ -619,6 +806,14 @@ __device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const 
     for (int i = 0; i < 4; i++) al[i] = 4u * lane + i < na;
     uint32_t posv[M][4];
 
+#pragma unroll
+    for (int t = 0; t < M; t++) {
+      if (t >= m || t == drv) continue;
+      const ListFilter lf = FilterOf(ix, q.term[t]);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (al[i] && !FilterPass(ix, lf, d[i])) al[i] = false;
+    }
 #pragma unroll
     for (int t = 0; t < M; t++) {
       if (t >= m || t == drv) continue;
@@ -690,8 +885,9 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
     const uint32_t local = u - q.unit_begin;
     // driver list block range of this unit
     const uint4 li = __ldg(&ix.lists[q.term[q.driver]]);
-    const uint32_t b0 = local * q.unit_blocks;
-    const uint32_t b1 = min(b0 + q.unit_blocks, li.y);
+    // the single-term fast path takes the whole list in one unit
+    const uint32_t b0 = CLASS == kClassOne ? 0u : local * q.unit_blocks;
+    const uint32_t b1 = CLASS == kClassOne ? li.y : min(b0 + q.unit_blocks, li.y);
     if constexpr (CLASS == kClassOne) {
       ProcessOneTerm<false>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
     } else if constexpr (CLASS == kClassTwo) {

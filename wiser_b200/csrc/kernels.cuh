@@ -22,8 +22,12 @@ struct DevIndexView {
   const uint8_t *norms;
   const double *cache;        // 256 entries
   const double *idf;          // per term, calc_es_idf(N_global, df_global)
+  const float *blk_max;       // SoA copy of blk_info.w
+  const uint32_t *filters;    // per-list doc-range-partitioned Bloom filters
+  const uint2 *list_flt;      // per term {first filter word, shift g (0xFFFFFFFF: no filter)}
   uint32_t n_terms;
   uint32_t n_docs;
+  uint32_t doc_lo;            // first doc id held by this shard (filter origin)
 };
 
 // One planned query. unit_begin = index of its first work unit in its class queue.

@@ -93,6 +93,9 @@ struct wsr_index {
   DevBuf<uint8_t> d_norms;
   DevBuf<double> d_cache;
   DevBuf<double> d_idf;
+  DevBuf<float> d_blk_max;
+  DevBuf<uint32_t> d_filters;
+  DevBuf<uint2> d_list_flt;
   DevIndexView view;
   int64_t n_blocks = 0, payload_bytes = 0, hbm_bytes = 0;
   uint32_t doc_base = 0;          // global id of this partition's doc 0
@@ -189,6 +192,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
     dq.n_units = (drv.n_blocks + ub - 1) / ub;
     int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
             : q.n_terms == 1 ? kClassOne : q.n_terms == 2 ? kClassTwo : kClassMany;
+    if (c == kClassOne) dq.n_units = 1;   // block-max prepass + selective decode, one warp
     cls[c].push_back(dq);
   }
   uint32_t cand = 0, seg = 0;
@@ -400,20 +404,31 @@ wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_s
       !cu(ix->d_lists.Ensure(h.lists.size() + 1), "cudaMalloc lists") ||
       !cu(ix->d_norms.Ensure(h.norms.size() + 1), "cudaMalloc norms") ||
       !cu(ix->d_cache.Ensure(256), "cudaMalloc cache") ||
-      !cu(ix->d_idf.Ensure(ix->idf.size() + 1), "cudaMalloc idf"))
+      !cu(ix->d_idf.Ensure(ix->idf.size() + 1), "cudaMalloc idf") ||
+      !cu(ix->d_blk_max.Ensure(h.blk_info.size() + 1), "cudaMalloc blk_max") ||
+      !cu(ix->d_filters.Ensure(h.filters.size() + 1), "cudaMalloc filters") ||
+      !cu(ix->d_list_flt.Ensure(h.list_flt.size() + 1), "cudaMalloc list_flt"))
     return fail(e);
+  std::vector<float> blk_max(h.blk_info.size());
+  for (size_t b = 0; b < blk_max.size(); b++) blk_max[b] = h.blk_info[b].max_tfn;
+  std::vector<uint2> list_flt(h.list_flt.size());
+  for (size_t t = 0; t < list_flt.size(); t++)
+    list_flt[t] = make_uint2((uint32_t)h.list_flt[t], (uint32_t)(h.list_flt[t] >> 32));
   if (!cu(cudaMemcpy(ix->d_payload.p, h.payload.data(), n_gran * 16, cudaMemcpyHostToDevice), "H2D payload") ||
       !cu(cudaMemcpy(ix->d_blk_info.p, h.blk_info.data(), h.blk_info.size() * 16, cudaMemcpyHostToDevice), "H2D blk_info") ||
       !cu(cudaMemcpy(ix->d_blk_last.p, h.blk_last.data(), h.blk_last.size() * 4, cudaMemcpyHostToDevice), "H2D blk_last") ||
       !cu(cudaMemcpy(ix->d_lists.p, h.lists.data(), h.lists.size() * 16, cudaMemcpyHostToDevice), "H2D lists") ||
       !cu(cudaMemcpy(ix->d_norms.p, h.norms.data(), h.norms.size(), cudaMemcpyHostToDevice), "H2D norms") ||
       !cu(cudaMemcpy(ix->d_cache.p, h.cache, 256 * 8, cudaMemcpyHostToDevice), "H2D cache") ||
-      !cu(cudaMemcpy(ix->d_idf.p, ix->idf.data(), ix->idf.size() * 8, cudaMemcpyHostToDevice), "H2D idf"))
+      !cu(cudaMemcpy(ix->d_idf.p, ix->idf.data(), ix->idf.size() * 8, cudaMemcpyHostToDevice), "H2D idf") ||
+      !cu(cudaMemcpy(ix->d_blk_max.p, blk_max.data(), blk_max.size() * 4, cudaMemcpyHostToDevice), "H2D blk_max") ||
+      !cu(cudaMemcpy(ix->d_filters.p, h.filters.data(), h.filters.size() * 4, cudaMemcpyHostToDevice), "H2D filters") ||
+      !cu(cudaMemcpy(ix->d_list_flt.p, list_flt.data(), list_flt.size() * 8, cudaMemcpyHostToDevice), "H2D list_flt"))
     return fail(e);
   ix->n_blocks = (int64_t)h.blk_info.size();
   ix->payload_bytes = (int64_t)n_gran * 16;
-  ix->hbm_bytes = ix->payload_bytes + ix->n_blocks * 20 + (int64_t)h.lists.size() * 24 +
-                  (int64_t)h.norms.size() + 2048;
+  ix->hbm_bytes = ix->payload_bytes + ix->n_blocks * 24 + (int64_t)h.lists.size() * 32 +
+                  (int64_t)h.filters.size() * 4 + (int64_t)h.norms.size() + 2048;
   DevIndexView &v = ix->view;
   v.payload = ix->d_payload.p;
   v.blk_info = ix->d_blk_info.p;
@@ -422,12 +437,17 @@ wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_s
   v.norms = ix->d_norms.p;
   v.cache = ix->d_cache.p;
   v.idf = ix->d_idf.p;
+  v.blk_max = ix->d_blk_max.p;
+  v.filters = ix->d_filters.p;
+  v.list_flt = ix->d_list_flt.p;
   v.n_terms = (uint32_t)h.lists.size();
   v.n_docs = (uint32_t)h.n_docs;
+  v.doc_lo = (uint32_t)h.doc_lo;
   // the block arrays now live in HBM only
   std::vector<uint8_t>().swap(h.payload);
   std::vector<BlockInfo>().swap(h.blk_info);
   std::vector<uint32_t>().swap(h.blk_last);
+  std::vector<uint32_t>().swap(h.filters);
   return ix.release();
 }
 
