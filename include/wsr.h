@@ -90,6 +90,22 @@ wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_s
 void wsr_index_close(wsr_index *idx);
 int wsr_index_get_info(const wsr_index *idx, wsr_index_info *info);
 
+/* ---- document-partitioned deployment -----------------------------------------
+ * Every GPU opens ITS OWN partition directory (a standalone vacuum index whose doc ids start at
+ * 0) and is then told the collection-wide statistics, because the reference scores with the
+ * whole index's N, average length and document frequencies:
+ *   doc_base       global id of this partition's doc 0 (added to every emitted doc id)
+ *   n_docs_global  N used by idf (calc_es_idf, scoring.h:21-25)
+ *   avg_len_global average document length used by the BM25 length-norm cache (scoring.h:85-90)
+ *   df_global      per LOCAL term id, the term's document frequency over all partitions
+ * Recomputes idf, the 256-entry cache and every block's block-max bound on the device. */
+int wsr_index_set_global_stats(wsr_index *idx, int64_t doc_base, int64_t n_docs_global,
+                               double avg_len_global, const uint32_t *df_global);
+/* Shard-local statistics for that exchange: df_local[i] = postings of term i on this shard.
+ * For synthetic corpora whose terms are named t<rank>, ranks[i] = that rank (else the call
+ * fails with WSR_ERR_ARG); either pointer may be NULL. */
+int wsr_index_local_stats(const wsr_index *idx, uint32_t *df_local, uint32_t *ranks);
+
 /* ---- term dictionary: TermTrieIndex::Find (term_index.h:136-144) -------------------------
  * Returns 0 and fills term_id / df (GLOBAL document frequency = posting-list size,
  * VacuumEngine::PostinglistSizes) or 1 if the term is absent. */
@@ -133,6 +149,8 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
  * wsr_batch_create uploads and plans a batch once; wsr_batch_run launches the kernels on the
  * batch's stream (no host<->device copies); results stay in device memory until fetched. */
 wsr_batch *wsr_batch_create(wsr_index *idx, const wsr_query *queries, int n, int k_stride);
+/* Re-plans and re-uploads an existing batch object with a new set of queries (buffers reused). */
+int wsr_batch_reset(wsr_batch *b, const wsr_query *queries, int n, int k_stride);
 void wsr_batch_destroy(wsr_batch *b);
 int wsr_batch_run(wsr_batch *b);                       /* asynchronous on the batch stream */
 int wsr_batch_sync(wsr_batch *b);

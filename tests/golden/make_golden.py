@@ -163,6 +163,25 @@ def main():
     qs += ["t0 t0", "t1 nosuch", "t5 t3 t5", "t0 t1 t2 t3 t4 t5 t6 t7", '"t0"', " t2  t1 "]
     make_fixture("zipf2k", ld, qs)
 
+    # E. the same corpus as two document partitions (docs 0-999 / 1000-1999), each indexed on
+    #    its own by the reference: the per-partition directories of a document-partitioned
+    #    deployment. Index files only; queries and expected results are zipf2k's.
+    lines = open(ld).read().split("\n")
+    header, docs = lines[0], [l for l in lines[1:] if l]
+    for part, (lo, hi) in enumerate([(0, 1000), (1000, 2000)]):
+        pld = os.path.join(TMP, f"zipf2k_p{part}.linedoc")
+        with open(pld, "w") as f:
+            f.write(header + "\n" + "\n".join(docs[lo:hi]) + "\n")
+        work = os.path.join(TMP, f"zipf2k_p{part}")
+        run(REF_TOOL, "build", pld, work)
+        out = os.path.join(HERE, f"zipf2k_p{part}")
+        shutil.rmtree(out, ignore_errors=True)
+        os.makedirs(out)
+        for fn in ("my.tip", "my.vacuum", "my.doc_length", "terms.txt"):
+            shutil.copy(os.path.join(work, fn), os.path.join(out, fn))
+        write_stub_doc_store(out)
+        print(f"zipf2k_p{part}: docs {lo}-{hi - 1}")
+
 
 if __name__ == "__main__":
     main()

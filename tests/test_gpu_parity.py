@@ -136,3 +136,81 @@ def test_document_partitioned_shards_merge(golden_dir, n_shards):
         k = ref_n[i]
         assert np.array_equal(got["doc_id"][i, :k], ref_hits["doc_id"][i, :k]), lines[i]
         assert np.array_equal(got["score"][i, :k].view(np.uint64), ref_hits["score"][i, :k].view(np.uint64))
+
+
+def test_partition_directories_with_global_stats(golden_dir):
+    """SURVEY §8e deployment shape: every shard opens ITS OWN partition directory (indexed
+    separately by the reference, local doc ids), receives the collection statistics, and the
+    merged per-shard top-k equals the single-index result bit for bit."""
+    import torch
+    from wiser_b200 import Batch, GpuVacuumEngine, SearchQuery
+    from wiser_b200.capi import HIT_DTYPE, check, lib
+    d = os.path.join(golden_dir, "zipf2k")
+    lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
+    qs = [SearchQuery(parse_query_line(l)[0], n_results=10) for l in lines]
+    whole = GpuVacuumEngine(d).Load()
+    ref_hits, ref_n, _, _ = whole.search_batch(whole.make_queries(qs), 10)
+    ora = OracleIndex(d)
+    gdf = dict((l.split()[0], int(l.split()[1])) for l in open(os.path.join(d, "terms.txt")))
+    n = len(qs)
+    gathered = torch.zeros((2, n, 10, 16), dtype=torch.uint8, device="cuda")
+    gathered_n = torch.zeros((2, n), dtype=torch.int32, device="cuda")
+    keep = []
+    for s, base in enumerate([0, 1000]):
+        e = GpuVacuumEngine(os.path.join(golden_dir, f"zipf2k_p{s}")).Load()
+        terms = [e.term_at(i)[0] for i in range(e.TermCount())]
+        e.set_global_stats(base, 2000, ora.avg_doc_len, np.array([gdf[t] for t in terms], np.uint32))
+        b = Batch(e, e.make_queries(qs), 10)
+        b.run()
+        b.sync()
+        h, nh = b.fetch()
+        gathered[s] = torch.from_numpy(h.view(np.uint8).reshape(n, 10, 16)).cuda()
+        gathered_n[s] = torch.from_numpy(nh).cuda()
+        keep.append((e, b))
+    out = torch.zeros((n, 10, 16), dtype=torch.uint8, device="cuda")
+    out_n = torch.zeros(n, dtype=torch.int32, device="cuda")
+    check(lib().wsr_merge_topk_device(gathered.data_ptr(), gathered_n.data_ptr(), 2, n, 10,
+                                      out.data_ptr(), out_n.data_ptr(), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(n, 160).view(HIT_DTYPE).reshape(n, 10)
+    got_n = out_n.cpu().numpy()
+    assert np.array_equal(got_n, ref_n)
+    for i in range(n):
+        k = ref_n[i]
+        assert np.array_equal(got["doc_id"][i, :k], ref_hits["doc_id"][i, :k]), lines[i]
+        assert np.array_equal(got["score"][i, :k].view(np.uint64), ref_hits["score"][i, :k].view(np.uint64))
+
+
+def test_generated_corpus_vs_oracle(tmp_path):
+    """A 60k-doc corpus from the native generator (multi-thousand-posting lists, skewed AND,
+    3-5 term queries): GPU top-10 vs the CPU oracle on the same directory, bit-exact scores."""
+    import subprocess
+    import gen_query_log
+    from wiser_b200 import GpuVacuumEngine, SearchQuery
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = str(tmp_path / "c")
+    subprocess.check_call([os.path.join(root, "wiser_b200", "wsr_gen_corpus"), "--out", d, "--docs", "60000",
+                           "--vocab", "80000", "--seed", "11"], stdout=subprocess.DEVNULL)
+    groups = gen_query_log.load_groups(os.path.join(d, "terms.txt"), 3000)
+    lines = (gen_query_log.generate("two_term", groups, 400, 1) +
+             gen_query_log.generate("two_term_hh", groups, 150, 2) +
+             gen_query_log.generate("multi_term", groups, 150, 3) +
+             gen_query_log.generate("single_high", groups, 60, 4) +
+             gen_query_log.generate("single_low", groups, 60, 5))
+    eng = GpuVacuumEngine(d).Load()
+    ora = OracleIndex(d)
+    qs = [SearchQuery(parse_query_line(l)[0], n_results=10) for l in lines]
+    res = eng.SearchBatch(qs)
+    for q, r in zip(qs, res):
+        rd, rs, rdf = ora.search(q.terms, 10)
+        fd, fs, _ = ora.search(q.terms, 1 << 30)
+        assert r.doc_freqs == rdf
+        check_topk(rd, rs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], fd, fs,
+                   what=" ".join(q.terms))
+    # full intersections through the collect path for a sample
+    for q in qs[:120:3]:
+        q.n_results = 100000
+    res = eng.SearchBatch(qs[:120:3])
+    for q, r in zip(qs[:120:3], res):
+        fd, fs, _ = ora.search(q.terms, 1 << 30)
+        check_full(fd, fs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], what=" ".join(q.terms))

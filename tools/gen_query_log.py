@@ -88,7 +88,7 @@ def multi_term(rng, groups, n, lo=3, hi=5):
         while len(terms) < m and guard < 2000:
             terms.add(groups["low"][rng.randint(0, len(groups["low"]) - 1)])
             guard += 1
-        t = list(terms)
+        t = sorted(terms)   # set order depends on the per-process hash seed
         rng.shuffle(t)
         out.append(" ".join(t))
     return out

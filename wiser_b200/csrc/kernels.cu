@@ -990,7 +990,7 @@ DecodeAllKernel(const DevIndexView ix, uint32_t n_blocks, unsigned long long *ch
 // Block-max refresh after the global statistics changed (document-partitioned load): recomputes
 // every block's upper bound of tf*(k1+1)/(tf+cache[norm]) with the new cache.
 __global__ void __launch_bounds__(kThreadsPerCta)
-RefreshBlockMaxKernel(const DevIndexView ix, uint32_t n_blocks, uint4 *blk_info_rw) {
+RefreshBlockMaxKernel(const DevIndexView ix, uint32_t n_blocks, uint4 *blk_info_rw, float *blk_max_rw) {
   const int lane = threadIdx.x & 31;
   const uint32_t warps = gridDim.x * kWarpsPerCta;
   for (uint32_t b = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); b < n_blocks; b += warps) {
@@ -1010,7 +1010,10 @@ RefreshBlockMaxKernel(const DevIndexView ix, uint32_t n_blocks, uint4 *blk_info_
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-    if (lane == 0) blk_info_rw[b].w = __float_as_uint(mx);
+    if (lane == 0) {
+      blk_info_rw[b].w = __float_as_uint(mx);
+      blk_max_rw[b] = mx;
+    }
   }
 }
 
@@ -1125,11 +1128,11 @@ void LaunchDecodeAll(const DevIndexView &ix, uint32_t n_blocks, unsigned long lo
 }
 
 void LaunchRefreshBlockMax(const DevIndexView &ix, uint32_t n_blocks, uint4 *blk_info_rw,
-                           int sm_count, cudaStream_t s) {
+                           float *blk_max_rw, int sm_count, cudaStream_t s) {
   if (!n_blocks) return;
   const uint32_t grid = std::min<uint32_t>((n_blocks + kWarpsPerCta - 1) / kWarpsPerCta,
                                            (uint32_t)(sm_count * 8));
-  RefreshBlockMaxKernel<<<grid, kThreadsPerCta, 0, s>>>(ix, n_blocks, blk_info_rw);
+  RefreshBlockMaxKernel<<<grid, kThreadsPerCta, 0, s>>>(ix, n_blocks, blk_info_rw, blk_max_rw);
 }
 
 void LaunchMergeShards(const wsr_hit *gathered, const int32_t *gathered_n, int n_shards,

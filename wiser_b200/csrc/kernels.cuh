@@ -83,7 +83,7 @@ void LaunchDecodeList(const DevIndexView &ix, uint32_t first_block, uint32_t n_b
 void LaunchDecodeAll(const DevIndexView &ix, uint32_t n_blocks, unsigned long long *checksum,
                      int sm_count, cudaStream_t s);
 void LaunchRefreshBlockMax(const DevIndexView &ix, uint32_t n_blocks, uint4 *blk_info_rw,
-                           int sm_count, cudaStream_t s);
+                           float *blk_max_rw, int sm_count, cudaStream_t s);
 void LaunchMergeShards(const wsr_hit *gathered, const int32_t *gathered_n, int n_shards,
                        int n_queries, int k_stride, wsr_hit *out, int32_t *out_n,
                        cudaStream_t s);

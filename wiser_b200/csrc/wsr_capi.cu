@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -70,6 +71,21 @@ struct PinnedBuf {
   }
 };
 
+// Runs fn(t, T) on T threads (the calling thread is thread 0).
+template <typename F>
+void ParallelFor(int T, F fn) {
+  if (T <= 1) { fn(0, 1); return; }
+  std::vector<std::thread> th;
+  th.reserve(T - 1);
+  for (int t = 1; t < T; t++) th.emplace_back([=]() { fn(t, T); });
+  fn(0, T);
+  for (auto &x : th) x.join();
+}
+int HostThreads(size_t items, size_t per_thread) {
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  return (int)std::max<size_t>(1, std::min<size_t>({(size_t)hw, (size_t)16, items / per_thread}));
+}
+
 bool IsPinned(const void *p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -111,6 +127,8 @@ struct wsr_batch {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host plan
   std::vector<DevQuery> planned;
+  std::vector<DevQuery> tmp;         // per input query, before class placement
+  std::vector<uint8_t> tmp_cls;
   std::vector<uint32_t> multi;       // planned indices of multi-unit queries
   uint32_t class_begin[5] = {0, 0, 0, 0, 0};
   uint32_t class_units[4] = {0, 0, 0, 0};
@@ -142,83 +160,136 @@ struct wsr_batch {
 namespace {
 
 // Host-side half of the batch scheduler: validates queries, picks each query's driver list,
-// cuts it into warp work units and groups queries into kernel classes.
+// cuts it into warp work units and groups queries into kernel classes. Two parallel passes over
+// contiguous query ranges (classify + count, then place) keep the planned order deterministic:
+// within a class, queries stay in batch order.
 int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
   wsr_index *ix = b->idx;
   const uint32_t n_terms_index = (uint32_t)ix->host.lists.size();
   b->n = n;
   b->k_stride = k_stride;
-  b->planned.clear();
   b->multi.clear();
-  b->listed_postings = b->listed_bytes = 0;
-  std::vector<DevQuery> cls[4];
-  for (int i = 0; i < n; i++) {
-    const wsr_query &q = queries[i];
-    if (q.n_terms > WSR_MAX_TERMS)
-      return Fail(WSR_ERR_UNSUPPORTED, "query has more than WSR_MAX_TERMS terms");
-    if ((int)q.k > k_stride) return Fail(WSR_ERR_ARG, "query k exceeds k_stride");
-    if (q.k == 0 || q.n_terms == 0) continue;            // vacuum_engine.h:206-208
-    bool ok = true;
-    uint32_t best = 0, best_df = 0xffffffffu;
-    for (uint32_t t = 0; t < q.n_terms; t++) {
-      const uint32_t id = q.term_ids[t];
-      if (id == WSR_TERM_ABSENT) { ok = false; break; }   // vacuum_engine.h:213-215
-      if (id >= n_terms_index) return Fail(WSR_ERR_ARG, "term id out of range");
-      const ListInfo &li = ix->host.lists[id];
-      if (li.df_shard == 0) ok = false;                   // nothing of this list on this shard
-      if (li.df_shard < best_df) { best_df = li.df_shard; best = t; }
-    }
-    if (!ok) continue;
-    DevQuery dq;
-    memset(&dq, 0, sizeof(dq));
-    for (uint32_t t = 0; t < q.n_terms; t++) {
-      dq.term[t] = q.term_ids[t];
-      b->listed_postings += ix->host.lists[q.term_ids[t]].df_shard;
-      b->listed_bytes += ix->host.list_alg_bytes[q.term_ids[t]];
-    }
-    dq.n_terms = (uint16_t)q.n_terms;
-    dq.k = q.k;
-    dq.driver = best;
-    dq.out_slot = (uint32_t)i;
-    const ListInfo &drv = ix->host.lists[q.term_ids[best]];
-    // Unit size: a unit's work is its driver blocks plus the probe-list blocks they can reach,
-    // so skewed queries (long probe lists) get fewer driver blocks per unit.
-    uint64_t probe_blocks = 0;
-    for (uint32_t t = 0; t < q.n_terms; t++)
-      if (t != best) probe_blocks += ix->host.lists[q.term_ids[t]].n_blocks;
-    const uint64_t ratio = drv.n_blocks ? (probe_blocks + drv.n_blocks - 1) / drv.n_blocks : 0;
-    uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kUnitBlocks, 64 / (1 + ratio)));
-    dq.unit_blocks = (uint16_t)ub;
-    dq.n_units = (drv.n_blocks + ub - 1) / ub;
-    int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
-            : q.n_terms == 1 ? kClassOne : q.n_terms == 2 ? kClassTwo : kClassMany;
-    if (c == kClassOne) dq.n_units = 1;   // block-max prepass + selective decode, one warp
-    cls[c].push_back(dq);
-  }
-  uint32_t cand = 0, seg = 0;
-  for (int c = 0; c < 4; c++) {
-    b->class_begin[c] = (uint32_t)b->planned.size();
-    uint32_t units = 0;
-    for (DevQuery &dq : cls[c]) {
-      dq.unit_begin = units;
-      units += dq.n_units;
-      if (c == kClassCollect) {
-        dq.seg_begin = seg;
-        const uint64_t cap = ix->host.lists[dq.term[dq.driver]].df_shard;
-        if ((uint64_t)seg + cap > 0xfffffff0ull) return Fail(WSR_ERR_UNSUPPORTED, "collect-mode batch too large");
-        seg += (uint32_t)cap;
-      } else if (dq.n_units > 1) {
-        dq.cand_begin = cand;
-        cand += dq.n_units;
-        b->multi.push_back((uint32_t)b->planned.size());
+  const int T = HostThreads((size_t)n, 8192);
+  struct Part {
+    uint32_t count[4] = {0, 0, 0, 0}, units[4] = {0, 0, 0, 0};
+    uint32_t cand = 0, multi = 0;
+    uint64_t seg = 0, listed = 0, listed_bytes = 0;
+    int err = 0;
+  };
+  std::vector<Part> part(T);
+  b->tmp.resize((size_t)n);
+  b->tmp_cls.resize((size_t)n);
+  auto classify = [&](int t, int TT) {
+    Part &p = part[t];
+    const int lo = (int)((int64_t)n * t / TT), hi = (int)((int64_t)n * (t + 1) / TT);
+    for (int i = lo; i < hi; i++) {
+      const wsr_query &q = queries[i];
+      b->tmp_cls[i] = 255;
+      if (q.n_terms > WSR_MAX_TERMS) { p.err = WSR_ERR_UNSUPPORTED; return; }
+      if ((int)q.k > k_stride) { p.err = WSR_ERR_ARG; return; }
+      if (q.k == 0 || q.n_terms == 0) continue;            // vacuum_engine.h:206-208
+      bool ok = true;
+      uint32_t best = 0, best_df = 0xffffffffu;
+      for (uint32_t t2 = 0; t2 < q.n_terms; t2++) {
+        const uint32_t id = q.term_ids[t2];
+        if (id == WSR_TERM_ABSENT) { ok = false; break; }   // vacuum_engine.h:213-215
+        if (id >= n_terms_index) { p.err = WSR_ERR_ARG; return; }
+        const ListInfo &li = ix->host.lists[id];
+        if (li.df_shard == 0) ok = false;                   // nothing of this list on this shard
+        if (li.df_shard < best_df) { best_df = li.df_shard; best = t2; }
       }
-      b->planned.push_back(dq);
+      if (!ok) continue;
+      DevQuery dq;
+      memset(&dq, 0, sizeof(dq));
+      uint64_t probe_blocks = 0;
+      for (uint32_t t2 = 0; t2 < q.n_terms; t2++) {
+        const ListInfo &li = ix->host.lists[q.term_ids[t2]];
+        dq.term[t2] = q.term_ids[t2];
+        p.listed += li.df_shard;
+        p.listed_bytes += ix->host.list_alg_bytes[q.term_ids[t2]];
+        if (t2 != best) probe_blocks += li.n_blocks;
+      }
+      dq.n_terms = (uint16_t)q.n_terms;
+      dq.k = q.k;
+      dq.driver = best;
+      dq.out_slot = (uint32_t)i;
+      const ListInfo &drv = ix->host.lists[q.term_ids[best]];
+      // Unit size: a unit's work is its driver blocks plus the probe-list blocks they can
+      // reach, so skewed queries (long probe lists) get fewer driver blocks per unit.
+      const uint64_t ratio = drv.n_blocks ? (probe_blocks + drv.n_blocks - 1) / drv.n_blocks : 0;
+      const uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kUnitBlocks, 64 / (1 + ratio)));
+      dq.unit_blocks = (uint16_t)ub;
+      dq.n_units = (drv.n_blocks + ub - 1) / ub;
+      const int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
+                    : q.n_terms == 1 ? kClassOne : q.n_terms == 2 ? kClassTwo : kClassMany;
+      if (c == kClassOne) dq.n_units = 1;   // block-max prepass + selective decode, one warp
+      b->tmp[i] = dq;
+      b->tmp_cls[i] = (uint8_t)c;
+      p.count[c]++;
+      p.units[c] += dq.n_units;
+      if (c == kClassCollect) p.seg += drv.df_shard;
+      else if (dq.n_units > 1) { p.cand += dq.n_units; p.multi++; }
+    }
+  };
+  ParallelFor(T, classify);
+  for (const Part &p : part) {
+    if (p.err == WSR_ERR_UNSUPPORTED) return Fail(p.err, "query has more than WSR_MAX_TERMS terms");
+    if (p.err) return Fail(p.err, "query k exceeds k_stride, or term id out of range");
+  }
+  // exclusive prefixes: class-major, thread-minor
+  struct Base { uint32_t pos[4], unit[4], cand, multi, seg; };
+  std::vector<Base> base(T);
+  uint32_t pos = 0, cand = 0, multi = 0;
+  uint64_t seg = 0;
+  b->listed_postings = b->listed_bytes = 0;
+  for (int c = 0; c < 4; c++) {
+    b->class_begin[c] = pos;
+    uint32_t units = 0;
+    for (int t = 0; t < T; t++) {
+      base[t].pos[c] = pos;
+      base[t].unit[c] = units;
+      pos += part[t].count[c];
+      units += part[t].units[c];
     }
     b->class_units[c] = units;
   }
-  b->class_begin[4] = (uint32_t)b->planned.size();
+  b->class_begin[4] = pos;
+  for (int t = 0; t < T; t++) {
+    base[t].cand = cand;
+    base[t].multi = multi;
+    base[t].seg = (uint32_t)seg;
+    cand += part[t].cand;
+    multi += part[t].multi;
+    seg += part[t].seg;
+    b->listed_postings += part[t].listed;
+    b->listed_bytes += part[t].listed_bytes;
+  }
+  if (seg > 0xfffffff0ull) return Fail(WSR_ERR_UNSUPPORTED, "collect-mode batch too large");
+  b->planned.resize(pos);
+  b->multi.resize(multi);
+  auto place = [&](int t, int TT) {
+    Base bs = base[t];
+    const int lo = (int)((int64_t)n * t / TT), hi = (int)((int64_t)n * (t + 1) / TT);
+    for (int i = lo; i < hi; i++) {
+      const int c = b->tmp_cls[i];
+      if (c == 255) continue;
+      DevQuery dq = b->tmp[i];
+      dq.unit_begin = bs.unit[c];
+      bs.unit[c] += dq.n_units;
+      if (c == kClassCollect) {
+        dq.seg_begin = bs.seg;
+        bs.seg += ix->host.lists[dq.term[dq.driver]].df_shard;
+      } else if (dq.n_units > 1) {
+        dq.cand_begin = bs.cand;
+        bs.cand += dq.n_units;
+        b->multi[bs.multi++] = bs.pos[c];
+      }
+      b->planned[bs.pos[c]++] = dq;
+    }
+  };
+  ParallelFor(T, place);
   b->n_cand_units = cand;
-  b->n_seg_entries = seg;
+  b->n_seg_entries = (uint32_t)seg;
   b->n_collect = b->class_begin[4] - b->class_begin[kClassCollect];
   return WSR_OK;
 }
@@ -477,6 +548,62 @@ int wsr_index_get_info(const wsr_index *idx, wsr_index_info *info) {
   return WSR_OK;
 }
 
+int wsr_index_set_global_stats(wsr_index *idx, int64_t doc_base, int64_t n_docs_global,
+                               double avg_len_global, const uint32_t *df_global) {
+  if (!idx || !df_global || doc_base < 0 || n_docs_global <= 0 || !(avg_len_global > 0) ||
+      doc_base + (int64_t)idx->host.norms.size() > 0x7fffffffll)
+    return Fail(WSR_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(idx->device));
+  HostIndex &h = idx->host;
+  h.n_docs = (int32_t)n_docs_global;
+  h.avg_len = avg_len_global;
+  const double k1 = 1.2, b = 0.75;                         // Bm25Similarity::BuildCache, scoring.h:85-90
+  for (int i = 0; i < 256; i++) {
+    const uint32_t m = i & 7;
+    const int sh = (i >> 3) - 1;
+    const uint32_t len = sh < 0 ? m : (m | 8u) << sh;
+    h.cache[i] = k1 * (1 - b + b * len / h.avg_len);
+  }
+  h.n_postings_global = 0;
+  for (size_t t = 0; t < h.lists.size(); t++) {
+    if (df_global[t] < h.lists[t].df_shard) return Fail(WSR_ERR_ARG, "global df below the local df");
+    h.lists[t].df_global = df_global[t];
+    h.n_postings_global += df_global[t];
+    const int doc_count = h.n_docs, doc_freq = (int)df_global[t];
+    idx->idf[t] = log(1 + (doc_count - doc_freq + 0.5) / (doc_freq + 0.5));   // scoring.h:21-25
+  }
+  idx->doc_base = (uint32_t)doc_base;
+  CU(cudaMemcpy(idx->d_lists.p, h.lists.data(), h.lists.size() * 16, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(idx->d_cache.p, h.cache, 256 * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(idx->d_idf.p, idx->idf.data(), idx->idf.size() * 8, cudaMemcpyHostToDevice));
+  idx->view.n_docs = (uint32_t)h.n_docs;
+  LaunchRefreshBlockMax(idx->view, (uint32_t)idx->n_blocks, idx->d_blk_info.p, idx->d_blk_max.p,
+                        idx->sm_count, 0);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  return WSR_OK;
+}
+
+int wsr_index_local_stats(const wsr_index *idx, uint32_t *df_local, uint32_t *ranks) {
+  if (!idx) return Fail(WSR_ERR_ARG, "null argument");
+  const HostIndex &h = idx->host;
+  for (size_t t = 0; t < h.lists.size(); t++) {
+    if (df_local) df_local[t] = h.lists[t].df_shard;
+    if (ranks) {
+      const char *s = h.term_arena.data() + h.term_off[t];
+      const size_t len = h.term_off[t + 1] - h.term_off[t];
+      if (len < 2 || len > 10 || s[0] != 't') return Fail(WSR_ERR_ARG, "term is not named t<rank>");
+      uint32_t r = 0;
+      for (size_t i = 1; i < len; i++) {
+        if (s[i] < '0' || s[i] > '9') return Fail(WSR_ERR_ARG, "term is not named t<rank>");
+        r = r * 10 + (uint32_t)(s[i] - '0');
+      }
+      ranks[t] = r;
+    }
+  }
+  return WSR_OK;
+}
+
 int wsr_term_lookup(const wsr_index *idx, const char *term, size_t len, uint32_t *term_id,
                     uint32_t *df) {
   if (!idx || !term) return Fail(WSR_ERR_ARG, "null argument");
@@ -560,6 +687,14 @@ wsr_batch *wsr_batch_create(wsr_index *idx, const wsr_query *queries, int n, int
   return b;
 }
 
+int wsr_batch_reset(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
+  if (!b || (!queries && n > 0) || n < 0 || k_stride < 1) return Fail(WSR_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(b->idx->device));
+  int rc = PlanBatch(b, queries, n, k_stride);
+  if (rc == WSR_OK) rc = UploadBatch(b);
+  return rc;
+}
+
 void wsr_batch_destroy(wsr_batch *b) { FreeBatch(b); }
 
 int wsr_batch_run(wsr_batch *b) {
@@ -636,14 +771,16 @@ int wsr_batch_profile(wsr_batch *b, float ms[6]) {
   return WSR_OK;
 }
 
-int wsr_parse_query_log(const wsr_index *idx, const char *text, size_t len, int k,
-                        wsr_query *out, int cap, int *n_out) {
-  if (!idx || (!text && len) || !out || !n_out || k < 0) return Fail(WSR_ERR_ARG, "bad argument");
+namespace {
+// Parses the lines of text[begin, end) (begin is a line start) into out[0..]; returns the
+// number of queries, or a negative status.
+int ParseLines(const wsr_index *idx, const char *text, size_t begin, size_t end, int k,
+               wsr_query *out, int cap) {
   int n = 0;
-  size_t p = 0;
-  while (p < len) {
+  size_t p = begin;
+  while (p < end) {
     size_t e = p;
-    while (e < len && text[e] != '\n') e++;
+    while (e < end && text[e] != '\n') e++;
     // utils::trim + phrase quotes (query_pool.h:251-311)
     size_t a = p, b = e;
     while (a < b && isspace((unsigned char)text[a])) a++;
@@ -654,7 +791,7 @@ int wsr_parse_query_log(const wsr_index *idx, const char *text, size_t len, int 
       a++;
       if (b > a) b--;
     }
-    if (n >= cap) return Fail(WSR_ERR_ARG, "query buffer too small");
+    if (n >= cap) return WSR_ERR_ARG;
     wsr_query &q = out[n];
     memset(&q, 0, sizeof(q));
     q.k = (uint32_t)k;
@@ -665,7 +802,7 @@ int wsr_parse_query_log(const wsr_index *idx, const char *text, size_t len, int 
       size_t u = t;
       while (u < b && text[u] != ' ') u++;
       if (u > t) {
-        if (q.n_terms >= WSR_MAX_TERMS) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
+        if (q.n_terms >= WSR_MAX_TERMS) return WSR_ERR_UNSUPPORTED;
         q.term_ids[q.n_terms++] = idx->host.dict.Find(text + t, u - t);
       }
       t = u;
@@ -673,7 +810,45 @@ int wsr_parse_query_log(const wsr_index *idx, const char *text, size_t len, int 
     n++;
     p = e + 1;
   }
-  *n_out = n;
+  return n;
+}
+}  // namespace
+
+int wsr_parse_query_log(const wsr_index *idx, const char *text, size_t len, int k,
+                        wsr_query *out, int cap, int *n_out) {
+  if (!idx || (!text && len) || !out || !n_out || k < 0) return Fail(WSR_ERR_ARG, "bad argument");
+  const int T = HostThreads(len, 1 << 18);
+  // chunk boundaries on line starts, then per-chunk line counts give the output offsets
+  std::vector<size_t> cut(T + 1, len);
+  cut[0] = 0;
+  for (int t = 1; t < T; t++) {
+    size_t p = len * t / T;
+    while (p < len && text[p] != '\n') p++;
+    cut[t] = p < len ? p + 1 : len;
+  }
+  std::vector<int> lines(T, 0), got(T, 0);
+  ParallelFor(T, [&](int t, int) {
+    int c = 0;
+    const char *p = text + cut[t], *e = text + cut[t + 1];
+    while (p < e) {
+      const char *nl = (const char *)memchr(p, '\n', e - p);
+      c++;
+      if (!nl) break;
+      p = nl + 1;
+    }
+    lines[t] = c;
+  });
+  std::vector<int> off(T + 1, 0);
+  for (int t = 0; t < T; t++) off[t + 1] = off[t] + lines[t];
+  if (off[T] > cap) return Fail(WSR_ERR_ARG, "query buffer too small");
+  ParallelFor(T, [&](int t, int) {
+    got[t] = ParseLines(idx, text, cut[t], cut[t + 1], k, out + off[t], lines[t]);
+  });
+  for (int t = 0; t < T; t++) {
+    if (got[t] == WSR_ERR_UNSUPPORTED) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
+    if (got[t] != lines[t]) return Fail(WSR_ERR_ARG, "query log parse error");
+  }
+  *n_out = off[T];
   return WSR_OK;
 }
 

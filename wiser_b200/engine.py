@@ -203,6 +203,22 @@ class GpuVacuumEngine:
             out.append(r)
         return out
 
+    def local_stats(self, want_ranks=False):
+        """(df_local[n_terms], ranks[n_terms] | None) for the document-partition stats exchange."""
+        n = self.TermCount()
+        df = np.zeros(max(n, 1), np.uint32)
+        ranks = np.zeros(max(n, 1), np.uint32) if want_ranks else None
+        check(lib().wsr_index_local_stats(self._h, df.ctypes.data,
+                                          ranks.ctypes.data if want_ranks else None))
+        return df[:n], (ranks[:n] if want_ranks else None)
+
+    def set_global_stats(self, doc_base: int, n_docs_global: int, avg_len_global: float,
+                         df_global: np.ndarray):
+        df_global = np.ascontiguousarray(df_global, np.uint32)
+        assert len(df_global) == self.TermCount()
+        check(lib().wsr_index_set_global_stats(self._h, int(doc_base), int(n_docs_global),
+                                               float(avg_len_global), df_global.ctypes.data))
+
     def decode_list(self, term: str):
         tid, _ = self.term_lookup(term)
         if tid == WSR_TERM_ABSENT:
@@ -255,6 +271,10 @@ class Batch:
         self._b = lib().wsr_batch_create(engine._h, qarr.ctypes.data, self.n, k_stride)
         if not self._b:
             raise capi.WsrError("wsr_batch_create: " + lib().wsr_last_error().decode())
+
+    def reset(self, qarr: np.ndarray, k_stride: int):
+        self.n, self.k_stride = len(qarr), k_stride
+        check(lib().wsr_batch_reset(self._b, qarr.ctypes.data, self.n, k_stride))
 
     def run(self):
         check(lib().wsr_batch_run(self._b))
