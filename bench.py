@@ -438,9 +438,23 @@ def ours(a, rank, world, local_rank):
             "matches_per_step": int(st.matches), "work_units_per_step": int(st.work_units),
         }
         print(json.dumps(line), flush=True)
+    # orderly teardown: torch buffers that lived on the batch streams go first, then the batches
+    # (their streams), then the index; the process leaves through os._exit so that interpreter
+    # shutdown cannot run CUDA destructors in an arbitrary order across the two CUDA runtimes
+    # (torch's and libwsr's statically linked one).
+    if shard is not None:
+        shard._bufs.clear()
+    torch.cuda.synchronize()
+    if world > 1:
+        batch2.close()
+    batch.close()
+    eng.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

@@ -85,7 +85,7 @@ class GpuVacuumEngine : public SearchEngineServiceNew {
  public:
   explicit GpuVacuumEngine(const std::string engine_dir_path, int bloom_enable_factor = 1,
                            GpuEngineOptions opt = GpuEngineOptions());
-  ~GpuVacuumEngine() override;
+  ~GpuVacuumEngine();   // the reference base has no virtual destructor
 
   // ---- SearchEngineServiceNew
   void Load() override;
