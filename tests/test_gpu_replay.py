@@ -1,0 +1,31 @@
+"""GPU tests of the C++ host side: the replay driver (wsr_replay) and, through it, the
+GpuVacuumEngine adapter — batch mode and the multi-threaded Search() mode whose concurrent
+callers are coalesced into GPU batches — against the committed reference results."""
+import os
+import subprocess
+
+import pytest
+
+from oracle_py import read_ref_results
+from parity import check_topk
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPLAY = os.path.join(ROOT, "wiser_b200", "wsr_replay")
+
+
+@pytest.mark.parametrize("mode,extra", [("batchlog", ["-batch_size=1000"]), ("locallog", ["-n_threads=16"])])
+def test_replay_driver_matches_reference(golden_dir, tmp_path, mode, extra):
+    d = os.path.join(golden_dir, "zipf2k")
+    out = str(tmp_path / "dump.txt")
+    log = subprocess.check_output([REPLAY, f"-engine=gpu:vacuum_dump:{d}", f"-query_path={d}/queries.txt",
+                                   "-n_results=10", f"-exp_mode={mode}", f"-dump={out}"] + extra).decode()
+    assert "WSR_REPLAY_JSON" in log
+    got = read_ref_results(out)
+    ref = read_ref_results(os.path.join(d, "ref_top10.txt.gz"))
+    full = read_ref_results(os.path.join(d, "ref_full.txt.gz"))
+    lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
+    assert len(got) == len(ref) == len(lines)
+    for line, (gd, gs, gdf), (rd, rs, rdf), (fd, fs, _) in zip(lines, got, ref, full):
+        assert gdf == rdf, line
+        check_topk(rd, rs, gd, gs, fd, fs, what=line)

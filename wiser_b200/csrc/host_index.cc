@@ -249,14 +249,14 @@ struct Builder {
     if (b - a >= kFilterMinDf) {
       const uint64_t range = (uint64_t)doc_hi - doc_lo;
       uint32_t g = 0;
-      while (g < 31 && (range >> (g + 1)) >= (uint64_t)(b - a) / 4 + 1) g++;   // ~4 postings per word
+      while (g < 31 && (range >> (g + 1)) >= (uint64_t)(b - a) / 2 + 1) g++;   // ~2 postings per word
       const size_t words = (size_t)(range >> g) + 1;
       const size_t at = c->filters.size();
       c->filters.resize(at + words, 0u);
       uint32_t *w = c->filters.data() + at;
       for (size_t i = a; i < b; i++) {
         const uint32_t doc = (*docs)[i];
-        w[(doc - doc_lo) >> g] |= (1u << FilterBit1(doc)) | (1u << FilterBit2(doc));
+        w[(doc - doc_lo) >> g] |= FilterBits(doc);
       }
       flt = ((uint64_t)g << 32) | (uint32_t)at;
     }

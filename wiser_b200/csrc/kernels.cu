@@ -553,11 +553,19 @@ __device__ __forceinline__ ListFilter FilterOf(const DevIndexView &ix, uint32_t 
   lf.shift = f.y & 31u;
   return lf;
 }
-__device__ __forceinline__ bool FilterPass(const DevIndexView &ix, const ListFilter &lf, uint32_t doc) {
-  if (lf.words == nullptr) return true;
-  const uint32_t w = __ldg(lf.words + ((doc - ix.doc_lo) >> lf.shift));
-  const uint32_t need = (1u << ((doc * 0x9E3779B1u) >> 27)) | (1u << ((doc * 0x85EBCA6Bu) >> 27));
+__device__ __forceinline__ bool FilterTest(uint32_t w, uint32_t doc) {
+  const uint32_t h = doc * 0x9E3779B1u;   // host_index.h FilterBits
+  const uint32_t need = (1u << (h >> 27)) | (1u << ((h >> 22) & 31u)) | (1u << ((h >> 17) & 31u));
   return (w & need) == need;
+}
+// Filter word of a candidate (all ones = "may be present" when the list has no filter).
+__device__ __forceinline__ uint32_t FilterWord(const DevIndexView &ix, const ListFilter &lf, uint32_t doc,
+                                               bool valid) {
+  if (lf.words == nullptr || !valid) return 0xffffffffu;
+  return __ldg(lf.words + ((doc - ix.doc_lo) >> lf.shift));
+}
+__device__ __forceinline__ bool FilterPass(const DevIndexView &ix, const ListFilter &lf, uint32_t doc) {
+  return FilterTest(FilterWord(ix, lf, doc, true), doc);
 }
 
 // Exact probe of ONE candidate per lane (filter survivors, doc ascending across lanes):
@@ -602,11 +610,24 @@ __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, u
     const uint32_t m0 = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
     const uint32_t *rp = reinterpret_cast<const uint32_t *>(ix.payload + info.y);
     const uint32_t rel = x - info.x;     // x > base of its block
-    uint32_t rec = 0;
+    // last record whose head (first doc - base) <= rel. Two levels of INDEPENDENT loads (records
+    // 4,8,..,28, then the three inside the chosen group) instead of a 5-deep dependent chain:
+    // the probe is latency-bound, and the extra loads hit sectors the block search reads anyway.
+    uint32_t grp = 0;
 #pragma unroll
-    for (uint32_t s = 16; s; s >>= 1) {
-      const uint32_t mid = rec + s;
-      if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) rec = mid;
+    for (uint32_t t = 1; t < 8; t++) {
+      const uint32_t mid = 4u * t;
+      if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) grp = t;   // heads ascend: last true wins
+    }
+    uint32_t rec = 4u * grp;
+    {
+      uint32_t add = 0;
+#pragma unroll
+      for (uint32_t t = 1; t < 4; t++) {
+        const uint32_t mid = 4u * grp + t;
+        if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) add = t;
+      }
+      rec += add;
     }
     uint32_t e[4];
     DecodeRecord(ix, info, rec, e);
@@ -699,28 +720,43 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
   int nq = 0, nc = 0;
   bool more = true;
 
-  // driver blocks: info two ahead, raw record one ahead
+  // Software pipeline over driver blocks: blk_info two ahead, the lane's raw record one ahead,
+  // and the Bloom filter words of block ja+1 are requested BEFORE the survivors of block ja are
+  // probed, so neither the record nor the filter load sits on the critical path.
   uint4 info_cur = __ldg(&ix.blk_info[first_a + b0]);
   uint4 info_nxt = b0 + 1 < b1 ? __ldg(&ix.blk_info[first_a + b0 + 1]) : info_cur;
-  uint4 raw_cur = make_uint4(0u, 0u, 0u, 0u);
-  if ((uint32_t)lane < ((ShN(info_cur.z) + 3u) >> 2)) raw_cur = LoadRecord(ix, info_cur, (uint32_t)lane);
+  uint32_t d[4], fw[4];
+  {
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if ((uint32_t)lane < ((ShN(info_cur.z) + 3u) >> 2)) raw = LoadRecord(ix, info_cur, (uint32_t)lane);
+    DecodeRaw(info_cur, raw, d);
+#pragma unroll
+    for (int i = 0; i < 4; i++) fw[i] = FilterWord(ix, flt, d[i], 4u * lane + i < ShN(info_cur.z));
+  }
+  uint4 raw_nxt = make_uint4(0u, 0u, 0u, 0u);
+  if (b0 + 1 < b1 && (uint32_t)lane < ((ShN(info_nxt.z) + 3u) >> 2))
+    raw_nxt = LoadRecord(ix, info_nxt, (uint32_t)lane);
   for (uint32_t ja = b0; ja < b1 && more; ja++) {
-    uint4 raw_nxt = make_uint4(0u, 0u, 0u, 0u), info_nxt2 = info_nxt;
-    if (ja + 1 < b1 && (uint32_t)lane < ((ShN(info_nxt.z) + 3u) >> 2))
-      raw_nxt = LoadRecord(ix, info_nxt, (uint32_t)lane);
-    if (ja + 2 < b1) info_nxt2 = __ldg(&ix.blk_info[first_a + ja + 2]);
-
     const uint32_t na = ShN(info_cur.z);
-    uint32_t d[4];
-    DecodeRaw(info_cur, raw_cur, d);
     st.decoded += na;
     st.bytes += AlgBytes(info_cur.z, false);
-    // ---- Bloom pre-test, then compaction in (lane, slot) = doc order
+    // ---- stage for block ja+1: decode its record, request its filter words, fetch ja+2's record
+    uint32_t dn[4] = {kNoDoc, kNoDoc, kNoDoc, kNoDoc}, fwn[4] = {0u, 0u, 0u, 0u};
+    uint4 info_nxt2 = info_nxt;
+    if (ja + 1 < b1) {
+      DecodeRaw(info_nxt, raw_nxt, dn);
+#pragma unroll
+      for (int i = 0; i < 4; i++) fwn[i] = FilterWord(ix, flt, dn[i], 4u * lane + i < ShN(info_nxt.z));
+      if (ja + 2 < b1) {
+        info_nxt2 = __ldg(&ix.blk_info[first_a + ja + 2]);
+      }
+    }
+    // ---- Bloom pre-test of block ja, then compaction in (lane, slot) = doc order
     bool pass[4];
     unsigned bm[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      pass[i] = 4u * lane + i < na && FilterPass(ix, flt, d[i]);   // padded slots repeat the last doc
+      pass[i] = 4u * lane + i < na && FilterTest(fw[i], d[i]);   // padded slots repeat the last doc
       bm[i] = __ballot_sync(kFull, pass[i]);
     }
     const unsigned lt = (1u << lane) - 1u;
@@ -737,6 +773,10 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
     }
     nc += __popc(bm[0]) + __popc(bm[1]) + __popc(bm[2]) + __popc(bm[3]);
     __syncwarp();
+    // the record of block ja+2 (its info has had a whole iteration to arrive)
+    raw_nxt = make_uint4(0u, 0u, 0u, 0u);
+    if (ja + 2 < b1 && (uint32_t)lane < ((ShN(info_nxt2.z) + 3u) >> 2))
+      raw_nxt = LoadRecord(ix, info_nxt2, (uint32_t)lane);
     // ---- exact probe, 32 survivors at a time
     int base = 0;
     for (; nc - base >= 32 && more; base += 32) {
@@ -757,8 +797,9 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
       __syncwarp();
     }
     info_cur = info_nxt;
-    raw_cur = raw_nxt;
     info_nxt = info_nxt2;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { d[i] = dn[i]; fw[i] = fwn[i]; }
   }
   if (nc && more) ProbeBatch(ix, pb, ws, 0, nc, nq, lane, st);
   if (nq) FlushHits<COLLECT>(ix, bv, q, qi, sh, ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
@@ -858,7 +899,7 @@ template <> struct ScratchOf<kClassOne> { typedef NoScratch type; };
 
 // Persistent search kernel of one query class: warps drain the class's unit queue.
 template <int CLASS>
-__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? 3 : 1)
+__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? 4 : 1)
 SearchKernel(const DevIndexView ix, const BatchView bv) {
   __shared__ CtaShared sh;
   __shared__ typename ScratchOf<CLASS>::type scratch[kWarpsPerCta];

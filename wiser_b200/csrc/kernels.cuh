@@ -11,7 +11,7 @@ namespace wsr {
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kMaxFastK = 32;      // top-k held one entry per lane
-constexpr int kUnitBlocks = 16;    // max driver-list blocks per warp work unit
+constexpr int kUnitBlocks = 64;    // max driver-list blocks per warp work unit
 
 // Read-only view of the HBM-resident index (layout: host_index.h).
 struct DevIndexView {

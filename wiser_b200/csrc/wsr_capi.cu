@@ -217,7 +217,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
       // Unit size: a unit's work is its driver blocks plus the probe-list blocks they can
       // reach, so skewed queries (long probe lists) get fewer driver blocks per unit.
       const uint64_t ratio = drv.n_blocks ? (probe_blocks + drv.n_blocks - 1) / drv.n_blocks : 0;
-      const uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kUnitBlocks, 64 / (1 + ratio)));
+      const uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kUnitBlocks, 256 / (1 + ratio)));
       dq.unit_blocks = (uint16_t)ub;
       dq.n_units = (drv.n_blocks + ub - 1) / ub;
       const int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
