@@ -139,6 +139,7 @@ struct Chunk {               // output of one slice of terms
 };
 
 struct Builder {
+  uint32_t filter_ppw = 2;   // postings per 32-bit filter word (WSR_FILTER_PPW overrides, 1..8)
   const FileView &vac;
   const std::vector<uint64_t> &list_offs;
   const HostIndex &ix;      // norms / cache already filled
@@ -249,7 +250,7 @@ struct Builder {
     if (b - a >= kFilterMinDf) {
       const uint64_t range = (uint64_t)doc_hi - doc_lo;
       uint32_t g = 0;
-      while (g < 31 && (range >> (g + 1)) >= (uint64_t)(b - a) / 2 + 1) g++;   // ~2 postings per word
+      while (g < 31 && (range >> (g + 1)) >= (uint64_t)(b - a) / filter_ppw + 1) g++;   // postings per word
       const size_t words = (size_t)(range >> g) + 1;
       const size_t at = c->filters.size();
       c->filters.resize(at + words, 0u);
@@ -412,7 +413,11 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
       begin = end;
     }
   }
-  Builder builder{vac, list_offs, ix, tfn_tab.data(), (uint32_t)ix.doc_lo, (uint32_t)ix.doc_hi};
+  Builder builder{2, vac, list_offs, ix, tfn_tab.data(), (uint32_t)ix.doc_lo, (uint32_t)ix.doc_hi};
+  if (const char *e = getenv("WSR_FILTER_PPW")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 8) builder.filter_ppw = (uint32_t)v;
+  }
   if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
   threads = (int)std::min<size_t>(threads, std::max<size_t>(1, chunks.size()));
   std::atomic<size_t> next{0};

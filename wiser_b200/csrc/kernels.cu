@@ -1005,23 +1005,55 @@ DecodeListKernel(const DevIndexView ix, uint32_t first_block, uint32_t n_blocks,
   }
 }
 
+// Raw tf record of the lane (16 / 32 / 128 bits), and its unpacking.
+__device__ __forceinline__ uint4 LoadTfRecord(const DevIndexView &ix, const uint4 info, uint32_t rec) {
+  const uint32_t bits = info.z, tc = ShTcode(bits);
+  const uint4 *src = ix.payload + info.y + DocGranules(bits);
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  if (tc == 0) r.x = __ldg(reinterpret_cast<const unsigned short *>(src) + rec);
+  else if (tc == 1) r.x = __ldg(reinterpret_cast<const uint32_t *>(src) + rec);
+  else r = __ldg(src + rec);
+  return r;
+}
+__device__ __forceinline__ void UnpackTfs(const uint4 info, const uint4 raw, uint32_t tf[4]) {
+  const uint32_t tc = ShTcode(info.z), v = raw.x;
+  if (tc == 0) { tf[0] = v & 15u; tf[1] = (v >> 4) & 15u; tf[2] = (v >> 8) & 15u; tf[3] = v >> 12; }
+  else if (tc == 1) { tf[0] = v & 255u; tf[1] = (v >> 8) & 255u; tf[2] = (v >> 16) & 255u; tf[3] = v >> 24; }
+  else { tf[0] = raw.x; tf[1] = raw.y; tf[2] = raw.z; tf[3] = raw.w; }
+}
+
+// Whole-index decode (K1 roofline kernel): a warp takes 4 consecutive blocks per step and issues
+// all of their metadata loads, then all of their record loads, before decoding any — the kernel is
+// a pure stream and only memory-level parallelism keeps HBM busy.
 __global__ void __launch_bounds__(kThreadsPerCta)
 DecodeAllKernel(const DevIndexView ix, uint32_t n_blocks, unsigned long long *checksum) {
+  constexpr int U = 4;
   const int lane = threadIdx.x & 31;
   const uint32_t warps = gridDim.x * kWarpsPerCta;
+  const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   unsigned long long sum = 0;
-  uint32_t b = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  uint4 info = b < n_blocks ? __ldg(&ix.blk_info[b]) : make_uint4(0u, 0u, 0u, 0u);
-  for (; b < n_blocks; b += warps) {
-    const uint4 cur = info;
-    if (b + warps < n_blocks) info = __ldg(&ix.blk_info[b + warps]);
-    const uint32_t n = ShN(cur.z);
-    uint32_t d[4], tf[4];
-    DecodeDocs(ix, cur, lane, d);
-    DecodeTfs(ix, cur, lane, tf);
+  for (uint32_t b = w * U; b < n_blocks; b += warps * U) {
+    uint4 info[U], rd[U], rt[U];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-      if (4u * lane + i < n) sum += (unsigned long long)d[i] + tf[i];
+    for (int u = 0; u < U; u++)
+      info[u] = b + u < n_blocks ? __ldg(&ix.blk_info[b + u]) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const bool on = b + u < n_blocks && (uint32_t)lane < ((ShN(info[u].z) + 3u) >> 2);
+      rd[u] = on ? LoadRecord(ix, info[u], (uint32_t)lane) : make_uint4(0u, 0u, 0u, 0u);
+      rt[u] = on ? LoadTfRecord(ix, info[u], (uint32_t)lane) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (b + u >= n_blocks) continue;
+      const uint32_t n = ShN(info[u].z);
+      uint32_t d[4], tf[4];
+      DecodeRaw(info[u], rd[u], d);
+      UnpackTfs(info[u], rt[u], tf);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (4u * lane + i < n) sum += (unsigned long long)d[i] + tf[i];
+    }
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
