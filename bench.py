@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--high-df", type=int, default=10000)
-    ap.add_argument("--cpu-sample", type=int, default=20000, help="queries in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=100000, help="queries in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-sample", type=int, default=200)
     ap.add_argument("--dir", default=os.environ.get("WSR_BENCH_DIR", "/tmp/wsr_bench"))
@@ -439,7 +439,7 @@ def ours(a, rank, world, local_rank):
     cpu = None
     if rank == 0 and not a.no_cpu_baseline and world == 1:
         try:
-            kind, threads, r = cpu_baseline(a, corpus_dir, qlog, 1)
+            kind, threads, r = cpu_baseline(a, corpus_dir, qlog, 3)
             cpu = {"value": r["listed_postings_per_s"], "unit": UNIT, "cores": threads, "kind": kind,
                    "queries_per_s": r["qps"], "seconds": r["seconds"],
                    "sample": f"first {r['queries']} queries of the same log, {threads} threads on one shared "
