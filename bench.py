@@ -251,6 +251,9 @@ def ours(a, rank, world, local_rank):
     from wiser_b200 import Batch, GpuVacuumEngine
     from wiser_b200.capi import HIT_DTYPE, PinnedArray
 
+    # NCCL prints its version banner on fd 1; keep stdout for the ONE JSON line
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -462,7 +465,7 @@ def ours(a, rank, world, local_rank):
                       "blocks": int(info.n_blocks), "corpus_build_s": cinfo.get("wall_s")},
             "matches_per_step": int(st.matches), "work_units_per_step": int(st.work_units),
         }
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     # orderly teardown: torch buffers that lived on the batch streams go first, then the batches
     # (their streams), then the index; the process leaves through os._exit so that interpreter
     # shutdown cannot run CUDA destructors in an arbitrary order across the two CUDA runtimes
