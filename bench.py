@@ -374,17 +374,15 @@ def ours(a, rank, world, local_rank):
     e2e_steps = max(1, min(a.steps, 5))
     t_parse = t_search = 0.0
     if world == 1:
-        hits_p = PinnedArray((n, a.k), HIT_DTYPE)
-        nh_p = PinnedArray((n,), np.int32)
+        hits_p = PinnedArray((n + 2, a.k), HIT_DTYPE)
+        nh_p = PinnedArray((n + 2,), np.int32)
 
         def e2e_step():
             nonlocal t_parse, t_search
             t0 = time.perf_counter()
-            q2 = eng.parse_query_log(text, a.k)
-            t1 = time.perf_counter()
-            eng.search_batch(q2, a.k, hits_p.array, nh_p.array)
-            t_parse += t1 - t0
-            t_search += time.perf_counter() - t1
+            h, c = eng.search_log(text, a.k, hits_p.array, nh_p.array)
+            assert len(c) == n
+            t_search += time.perf_counter() - t0
     else:
         batch2 = Batch(eng, qarr, a.k)
         hits_t = torch.empty(n * a.k * 16, dtype=torch.uint8).pin_memory()
@@ -418,8 +416,8 @@ def ours(a, rank, world, local_rank):
            "d2h_bytes_per_step": int(n * a.k * 16 + n * 4), "ms_per_step": e2e_s * 1000.0,
            "queries_per_s": n / e2e_s,
            "parse_lookup_ms": 1000.0 * t_parse / e2e_steps, "search_ms": 1000.0 * t_search / e2e_steps,
-           "path": ("query-log text -> wsr_parse_query_log (term lookup) -> wsr_search_batch (pinned host "
-                    "buffers)" if world == 1 else
+           "path": ("wsr_search_log: query-log text -> term lookup + planning (host threads) overlapped with "
+                    "H2D, kernels and D2H of the previous chunk; pinned host result buffers" if world == 1 else
                     "query-log text -> wsr_parse_query_log -> wsr_batch_reset (plan + H2D) -> kernels -> "
                     "NCCL all-gather + merge kernel -> D2H of the merged top-k")}
 

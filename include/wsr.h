@@ -145,6 +145,14 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
                      wsr_hit *hits, int32_t *n_hits, uint32_t *doc_freqs,
                      int32_t *n_doc_freqs);
 
+/* Replays a whole query log given as TEXT (the replay driver's inner loop): the log is cut into
+ * chunks; while the GPU works on chunk i the host parses / looks up / plans chunk i+1 and the
+ * results of chunk i-1 travel back, all inside this one blocking call. hits: cap_q * k entries
+ * (query i at hits[i*k]); n_hits: cap_q entries; *n_queries receives the number of log lines.
+ * Pinned buffers (wsr_host_alloc) are written by DMA directly. */
+int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
+                   int32_t *n_hits, int cap_q, int *n_queries);
+
 /* ---- device-resident batches (replay driver, multi-GPU merge, benchmarking) --------------
  * wsr_batch_create uploads and plans a batch once; wsr_batch_run launches the kernels on the
  * batch's stream (no host<->device copies); results stay in device memory until fetched. */

@@ -214,3 +214,19 @@ def test_generated_corpus_vs_oracle(tmp_path):
     for q, r in zip(qs[:120:3], res):
         fd, fs, _ = ora.search(q.terms, 1 << 30)
         check_full(fd, fs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], what=" ".join(q.terms))
+
+
+def test_search_log_pipeline_equals_batch(golden_dir):
+    """wsr_search_log (chunked, host/GPU overlapped) returns exactly what one wsr_search_batch does."""
+    from wiser_b200 import GpuVacuumEngine
+    d = os.path.join(golden_dir, "zipf2k")
+    eng = GpuVacuumEngine(d).Load()
+    text = open(os.path.join(d, "queries.txt"), "rb").read()
+    text = b"\n".join(l for l in text.split(b"\n") if not l.startswith(b'"')) * 40   # > 64 KiB => several chunks
+    q = eng.parse_query_log(text, 10)
+    h1, n1, _, _ = eng.search_batch(q, 10)
+    h2, n2 = eng.search_log(text, 10)
+    assert len(n2) == len(n1) and np.array_equal(n1, n2)
+    mask = np.arange(10)[None, :] < n1[:, None]
+    assert np.array_equal(h1["doc_id"][mask], h2["doc_id"][mask])
+    assert np.array_equal(h1["score"][mask].view(np.uint64), h2["score"][mask].view(np.uint64))

@@ -39,7 +39,7 @@ EXPORTS = [
     "wsr_decode_all", "wsr_search", "wsr_search_batch", "wsr_batch_create", "wsr_batch_destroy",
     "wsr_batch_run", "wsr_batch_sync", "wsr_batch_fetch", "wsr_batch_device_results",
     "wsr_batch_time", "wsr_batch_get_stats", "wsr_merge_topk_device", "wsr_batch_profile",
-    "wsr_parse_query_log", "wsr_index_set_global_stats", "wsr_index_local_stats", "wsr_batch_reset",
+    "wsr_parse_query_log", "wsr_index_set_global_stats", "wsr_index_local_stats", "wsr_batch_reset", "wsr_search_log",
 ]
 
 _lib = None
@@ -84,6 +84,7 @@ def lib():
     L.wsr_index_set_global_stats.argtypes = [vp, C.c_int64, C.c_int64, C.c_double, vp]
     L.wsr_index_local_stats.argtypes = [vp, vp, vp]
     L.wsr_batch_reset.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.wsr_search_log.argtypes = [vp, cp, sz, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.wsr_merge_topk_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     _lib = L
     return L

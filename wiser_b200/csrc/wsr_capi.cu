@@ -897,6 +897,88 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
   return rc;
 }
 
+int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
+                   int32_t *n_hits, int cap_q, int *n_queries) {
+  if (!idx || (!text && len) || k < 1 || !hits || !n_hits || !n_queries || cap_q < 0)
+    return Fail(WSR_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(idx->device));
+  // chunk boundaries on line starts: ~4 chunks, at least ~64 KiB of text each
+  const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(8, len >> 16));
+  std::vector<size_t> cut(n_chunks + 1, len);
+  cut[0] = 0;
+  for (int c = 1; c < n_chunks; c++) {
+    size_t p = len * c / n_chunks;
+    while (p < len && text[p] != '\n') p++;
+    cut[c] = p < len ? p + 1 : len;
+  }
+  const bool pinned = IsPinned(hits) && IsPinned(n_hits);
+  wsr_batch *bt[2] = {AcquirePooled(idx), AcquirePooled(idx)};
+  if (!bt[0] || !bt[1]) return Fail(WSR_ERR_CUDA, "cannot create batch");
+  struct Pend { int q0 = 0, n = 0; bool live = false; } pend[2];
+  std::vector<wsr_query> qs;
+  int done_q = 0, rc = WSR_OK;
+  auto drain = [&](int s) -> int {      // waits for slot s and, if staged, copies its results out
+    if (!pend[s].live) return WSR_OK;
+    CU(cudaStreamSynchronize(bt[s]->stream));
+    if (!pinned) {
+      memcpy(hits + (size_t)pend[s].q0 * k, bt[s]->h_hits.p, (size_t)pend[s].n * k * sizeof(wsr_hit));
+      memcpy(n_hits + pend[s].q0, bt[s]->h_n_hits.p, (size_t)pend[s].n * 4);
+    }
+    pend[s].live = false;
+    return WSR_OK;
+  };
+  for (int c = 0; c < n_chunks && rc == WSR_OK; c++) {
+    const int s = c & 1;
+    const char *ct = text + cut[c];
+    const size_t cl = cut[c + 1] - cut[c];
+    size_t lines = 0;
+    for (const char *p = ct, *e = ct + cl; p < e;) {
+      const char *nl = (const char *)memchr(p, '\n', e - p);
+      lines++;
+      if (!nl) break;
+      p = nl + 1;
+    }
+    if (done_q + (int)lines > cap_q) { rc = Fail(WSR_ERR_ARG, "result buffers too small"); break; }
+    qs.resize(lines + 1);
+    int n = 0;
+    rc = wsr_parse_query_log(idx, ct, cl, k, qs.data(), (int)qs.size(), &n);   // overlaps the GPU
+    if (rc) break;
+    for (int i = 0; i < n; i++)
+      if ((qs[i].flags & 1u) && qs[i].n_terms > 1) { rc = Fail(WSR_ERR_UNSUPPORTED, "phrase queries are not built yet"); break; }
+    if (rc) break;
+    rc = drain(s);                         // this slot's previous chunk must be finished
+    if (rc) break;
+    wsr_batch *b = bt[s];
+    rc = PlanBatch(b, qs.data(), n, k);
+    if (rc == WSR_OK) rc = UploadBatch(b);
+    if (rc == WSR_OK) rc = EnqueueRun(b);
+    if (rc) break;
+    const size_t nh = (size_t)n * k;
+    if (pinned) {
+      if (nh) CU(cudaMemcpyAsync(hits + (size_t)done_q * k, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+      if (n) CU(cudaMemcpyAsync(n_hits + done_q, b->d_n_hits.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+    } else {
+      CU(b->h_hits.Ensure(nh + 1));
+      CU(b->h_n_hits.Ensure((size_t)n + 1));
+      if (nh) CU(cudaMemcpyAsync(b->h_hits.p, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+      if (n) CU(cudaMemcpyAsync(b->h_n_hits.p, b->d_n_hits.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+    }
+    pend[s].q0 = done_q;
+    pend[s].n = n;
+    pend[s].live = true;
+    done_q += n;
+  }
+  for (int s = 0; s < 2; s++) {
+    const int r2 = drain(s);
+    if (rc == WSR_OK) rc = r2;
+    if (pend[s].live) cudaStreamSynchronize(bt[s]->stream);
+  }
+  ReleasePooled(idx, bt[0]);
+  ReleasePooled(idx, bt[1]);
+  *n_queries = done_q;
+  return rc;
+}
+
 int wsr_search(wsr_index *idx, const char *const *terms, const size_t *term_lens, int n_terms,
                int k, wsr_hit *hits, int *n_hits, uint32_t *doc_freqs, int *n_doc_freqs) {
   if (!idx || n_terms < 0 || k < 0 || !n_hits) return Fail(WSR_ERR_ARG, "bad argument");

@@ -184,6 +184,19 @@ class GpuVacuumEngine:
                                      ndfs.ctypes.data if want_doc_freqs else None))
         return hits, n_hits, dfs, ndfs
 
+    def search_log(self, text: bytes, k: int, hits=None, n_hits=None):
+        """wsr_search_log: whole query-log text -> (hits[n,k], n_hits[n]); parse, GPU and copies
+        pipelined inside the library."""
+        cap = text.count(b"\n") + 2
+        if hits is None:
+            hits = np.zeros((cap, k), HIT_DTYPE)
+        if n_hits is None:
+            n_hits = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        check(lib().wsr_search_log(self._h, text, len(text), k, hits.ctypes.data, n_hits.ctypes.data,
+                                   min(cap, len(n_hits)), C.byref(n)))
+        return hits[:n.value], n_hits[:n.value]
+
     def SearchBatch(self, queries: Sequence[SearchQuery]) -> List[SearchResult]:
         if not queries:
             return []
