@@ -8,7 +8,9 @@
 #include <cctype>
 #include <cmath>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -71,19 +73,72 @@ struct PinnedBuf {
   }
 };
 
-// Runs fn(t, T) on T threads (the calling thread is thread 0).
+// Persistent host worker pool: ParallelFor(T, fn) runs fn(t, T) for t in [0, T) with the caller
+// as thread 0. Planning and log parsing call it several times per batch, so threads are kept.
+class WorkerPool {
+ public:
+  static WorkerPool &Get() {
+    static WorkerPool *p = new WorkerPool();   // intentionally leaked: no teardown-order issues
+    return *p;
+  }
+  int Size() const { return (int)workers_.size() + 1; }
+  void Run(int T, const std::function<void(int, int)> &fn) {
+    T = std::max(1, std::min(T, Size()));
+    if (T == 1) { fn(0, 1); return; }
+    std::lock_guard<std::mutex> serial(run_mu_);      // one parallel region at a time
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      fn_ = &fn;
+      T_ = T;
+      pending_ = T - 1;
+      epoch_++;
+    }
+    cv_.notify_all();
+    fn(0, T);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [&]() { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+ private:
+  WorkerPool() {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int n = (int)std::min(16u, hw) - 1;
+    for (int i = 0; i < n; i++) workers_.emplace_back([this, i]() { Loop(i + 1); });
+    for (auto &w : workers_) w.detach();
+  }
+  void Loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int, int)> *fn;
+      int T;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&]() { return epoch_ != seen; });
+        seen = epoch_;
+        fn = fn_;
+        T = T_;
+      }
+      if (id < T && fn) {
+        (*fn)(id, T);
+        std::lock_guard<std::mutex> g(mu_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_, run_mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int, int)> *fn_ = nullptr;
+  int T_ = 1, pending_ = 0;
+  uint64_t epoch_ = 0;
+};
+
 template <typename F>
 void ParallelFor(int T, F fn) {
-  if (T <= 1) { fn(0, 1); return; }
-  std::vector<std::thread> th;
-  th.reserve(T - 1);
-  for (int t = 1; t < T; t++) th.emplace_back([=]() { fn(t, T); });
-  fn(0, T);
-  for (auto &x : th) x.join();
+  WorkerPool::Get().Run(T, std::function<void(int, int)>(fn));
 }
 int HostThreads(size_t items, size_t per_thread) {
-  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  return (int)std::max<size_t>(1, std::min<size_t>({(size_t)hw, (size_t)16, items / per_thread}));
+  return (int)std::max<size_t>(1, std::min<size_t>((size_t)WorkerPool::Get().Size(), items / per_thread));
 }
 
 bool IsPinned(const void *p) {
@@ -169,7 +224,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
   b->n = n;
   b->k_stride = k_stride;
   b->multi.clear();
-  const int T = HostThreads((size_t)n, 8192);
+  const int T = HostThreads((size_t)n, 1024);
   struct Part {
     uint32_t count[4] = {0, 0, 0, 0}, units[4] = {0, 0, 0, 0};
     uint32_t cand = 0, multi = 0;
@@ -817,7 +872,7 @@ int ParseLines(const wsr_index *idx, const char *text, size_t begin, size_t end,
 int wsr_parse_query_log(const wsr_index *idx, const char *text, size_t len, int k,
                         wsr_query *out, int cap, int *n_out) {
   if (!idx || (!text && len) || !out || !n_out || k < 0) return Fail(WSR_ERR_ARG, "bad argument");
-  const int T = HostThreads(len, 1 << 18);
+  const int T = HostThreads(len, 1 << 14);
   // chunk boundaries on line starts, then per-chunk line counts give the output offsets
   std::vector<size_t> cut(T + 1, len);
   cut[0] = 0;
@@ -902,8 +957,8 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
   if (!idx || (!text && len) || k < 1 || !hits || !n_hits || !n_queries || cap_q < 0)
     return Fail(WSR_ERR_ARG, "bad argument");
   CU(cudaSetDevice(idx->device));
-  // chunk boundaries on line starts: ~4 chunks, at least ~64 KiB of text each
-  const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(8, len >> 16));
+  // chunk boundaries on line starts: up to 4 chunks of at least 128 KiB of text each
+  const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(4, len >> 17));
   std::vector<size_t> cut(n_chunks + 1, len);
   cut[0] = 0;
   for (int c = 1; c < n_chunks; c++) {
