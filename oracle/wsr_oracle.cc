@@ -11,6 +11,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -89,6 +90,8 @@ struct SkipRow {
   uint32_t prev_doc;
   uint64_t docid_off;
   uint64_t tf_off;
+  uint64_t pos_off;   // blob holding the first position of posting 128*r ...
+  uint32_t pos_idx;   // ... and its index inside that blob
 };
 
 // A decoded blob of <=128 values: either a pack (0xD6,bits,16*bits B) or the VInts tail
@@ -140,16 +143,16 @@ class ListCursor {
     b += 1;
     b += VarintDecode(b, &n_rows);
     rows_.resize(n_rows);
-    uint64_t pd = 0, po = 0, pt = 0, x;
+    uint64_t pd = 0, po = 0, pt = 0, pp = 0, x, pidx;
     for (uint64_t r = 0; r < n_rows; r++) {
       b += VarintDecode(b, &x); pd += x;
       b += VarintDecode(b, &x); po += x;
       b += VarintDecode(b, &x); pt += x;
-      b += VarintDecode(b, &x);  // pos blob off (delta)  — unused on this path
-      b += VarintDecode(b, &x);  // pos in-blob index
-      b += VarintDecode(b, &x);  // offset blob off (delta)
-      b += VarintDecode(b, &x);  // offset in-blob index
-      rows_[r] = {(uint32_t)pd, po, pt};
+      b += VarintDecode(b, &x); pp += x;   // position blob offset (delta vs previous row)
+      b += VarintDecode(b, &pidx);         // position in-blob index
+      b += VarintDecode(b, &x);            // offset blob off (delta) — snippets only
+      b += VarintDecode(b, &x);            // offset in-blob index
+      rows_[r] = {(uint32_t)pd, po, pt, pp, (uint32_t)pidx};
     }
     // DocIdIterator::Reset -> SkipTo(0), flash_iterators.h:131-139
     cur_ = 0;
@@ -187,13 +190,47 @@ class ListCursor {
 
   // VacuumPostingListIterator::TermFreq, flash_iterators.h:989-992: random access by posting
   // index with a one-blob cache.
-  uint32_t TermFreq() {
-    int64_t blob = cur_ / kPack;
+  uint32_t TermFreq() { return TfAt(cur_); }
+  uint32_t TfAt(int64_t idx) {
+    int64_t blob = idx / kPack;
     if (blob != tf_blob_) {
       tf_.Load(file_ + rows_[blob].tf_off);
       tf_blob_ = blob;
     }
-    return tf_.v[cur_ % kPack];
+    return tf_.v[idx % kPack];
+  }
+
+  // Positions of the CURRENT posting: AssignPositionBegin + InBagPositionIterator::Pop until
+  // IsEnd (flash_iterators.h:1002-1005, 558-661). The position column is one "cozy box": the
+  // bags' values (deltas inside each bag, first from 0) concatenated and cut into 128-value
+  // packs plus a VInts tail, blobs back to back (CozyBoxIterator, :280-425). Skip row r points at
+  // the first value of posting 128*r; reaching posting p from there means advancing by the tfs
+  // of postings 128*r .. p-1 (PositionPostingBagIterator::NumCozyEntriesBetween, :619-628).
+  void Positions(std::vector<uint32_t> *out) {
+    out->clear();
+    const int64_t r = cur_ / kPack;
+    uint64_t blob_off = rows_[r].pos_off;
+    uint64_t in_blob = rows_[r].pos_idx;
+    for (int64_t q = r * kPack; q < cur_; q++) in_blob += TfAt(q);
+    const uint32_t tf = TfAt(cur_);
+    // CozyBoxIterator::AdvanceBy, flash_iterators.h:317-336: whole packs are stepped over by
+    // their serialized size (2 + 16*bits); the VInts blob is the last one of the column
+    while (file_[blob_off] == kPackMagic && in_blob >= (uint64_t)kPack) {
+      in_blob -= kPack;
+      blob_off += 2 + 16ull * file_[blob_off + 1];
+    }
+    Blob blob;
+    blob.Load(file_ + blob_off);
+    uint32_t prev = 0;
+    for (uint32_t i = 0; i < tf; i++) {
+      if (!blob.vints && in_blob == (uint64_t)kPack) {      // CozyBoxIterator::Advance, :309-315
+        blob_off += 2 + 16ull * file_[blob_off + 1];
+        blob.Load(file_ + blob_off);
+        in_blob = 0;
+      }
+      prev += blob.v[in_blob++];
+      out->push_back(prev);
+    }
   }
 
  private:
@@ -346,6 +383,71 @@ struct Processor {
     return rev;
   }
 
+  // HandleTheFoundDoc for phrase queries, query_processing.h:886-895: rank the doc only if
+  // PhraseQueryProcessor2 finds >= 1 match. No Bloom filters here: IsPossibleToPresent answers
+  // "possible" when the index has none (flash_iterators.h:1039-1058).
+  bool is_phrase = false;
+  std::vector<std::vector<uint32_t>> pos;
+  bool PhraseMatches() {
+    const size_t n = its.size();
+    pos.resize(n);
+    for (size_t i = 0; i < n; i++) its[i].Positions(&pos[i]);
+    if (n == 2) {
+      // PhraseQueryProcessor2::ProcessTwoTerm, query_processing.h:282-331
+      size_t i0 = 0, i1 = 0;
+      long pos0 = -100, pos1 = -200;
+      bool tried_pop_end = false;
+      int matches = 0;
+      while (!tried_pop_end) {
+        if (pos0 < pos1) {
+          if (i0 < pos[0].size()) pos0 = pos[0][i0++]; else tried_pop_end = true;
+        } else if (pos0 > pos1) {
+          if (i1 < pos[1].size()) pos1 = (long)pos[1][i1++] - 1; else tried_pop_end = true;
+        } else {
+          matches++;
+          if (i0 < pos[0].size()) pos0 = pos[0][i0++]; else tried_pop_end = true;
+          if (i1 < pos[1].size()) pos1 = (long)pos[1][i1++] - 1; else tried_pop_end = true;
+        }
+      }
+      return matches > 0;
+    }
+    // PhraseQueryProcessor2::ProcessGeneral, query_processing.h:333-362 with
+    // InitializeLastPopped / FindMaxAdjustedLastPopped / MovePoppedBeyond / IsPoppedMatch
+    std::vector<size_t> nxt(n, 0);
+    std::vector<long> last(n);
+    for (size_t i = 0; i < n; i++) {
+      if (pos[i].empty()) return false;
+      last[i] = pos[i][nxt[i]++];
+    }
+    auto move_beyond = [&](long target) {
+      for (size_t i = 0; i < n; i++) {
+        while (nxt[i] < pos[i].size() && last[i] - (long)i < target) last[i] = pos[i][nxt[i]++];
+        if (nxt[i] >= pos[i].size() && last[i] - (long)i < target) return false;
+      }
+      return true;
+    };
+    int matches = 0;
+    for (;;) {
+      long mx = last[0];
+      for (size_t i = 1; i < n; i++) mx = std::max(mx, last[i] - (long)i);
+      if (!move_beyond(mx)) break;
+      bool match = true;
+      for (size_t i = 0; i < n; i++) match = match && (last[i] - (long)i == mx);
+      if (match) {
+        matches++;
+        if (!move_beyond(mx + 1)) break;
+      }
+    }
+    return matches > 0;
+  }
+  void Found(int32_t doc) {
+    if (is_phrase && its.size() > 1) {
+      if (PhraseMatches()) Rank(doc);
+    } else {
+      Rank(doc);
+    }
+  }
+
   // SingleTermQueryProcessor::Process, query_processing.h:632-641
   void One() {
     auto &it = its[0];
@@ -364,7 +466,7 @@ struct Processor {
       } else if (d0 < d1) {
         a.SkipForward(d1);
       } else {
-        Rank(d0);
+        Found(d0);      // non-phrase: RankDoc (:669); phrase: QueryProcessor::ProcessTwoTerm (:742-763)
         a.Advance();
         b.Advance();
       }
@@ -385,7 +487,7 @@ struct Processor {
         if (its[i].IsEnd()) return;
         if ((int32_t)its[i].DocId() != max_doc) break;
         if (i == n - 1) {
-          Rank(max_doc);
+          Found(max_doc);
           for (int j = 0; j < n; j++) its[j].Advance();
         }
       }
@@ -395,7 +497,7 @@ struct Processor {
 
 // VacuumEngine::Search, vacuum_engine.h:201-258 (non-phrase; snippets never requested).
 int Search(const Index &ix, const char *const *terms, const size_t *lens, int n_terms, int k,
-           std::vector<HeapEntry> *out, std::vector<int32_t> *dfs) {
+           std::vector<HeapEntry> *out, std::vector<int32_t> *dfs, bool is_phrase = false) {
   out->clear();
   dfs->clear();
   if (k == 0) return 0;                                  // :206-208
@@ -410,6 +512,7 @@ int Search(const Index &ix, const char *const *terms, const size_t *lens, int n_
   if (its.empty() || (int)its.size() < n_terms) return 0;  // :213-215
   for (auto &it : its) dfs->push_back((int32_t)it.Size()); // :217-219
   Processor p(ix, its, k);
+  p.is_phrase = is_phrase;
   // qq_search::ProcessQueryDelta, query_processing.h:956-979
   if (its.size() == 1) p.One();
   else if (its.size() == 2) p.Two();
@@ -472,13 +575,22 @@ int64_t wsr_oracle_decode_list(const wsr_oracle_index *h, const char *term, size
   }
   return c.Size();
 }
+int wsr_oracle_search_ex(const wsr_oracle_index *h, const char *const *terms, const size_t *lens,
+                         int n_terms, int k, int is_phrase, int32_t *out_docs, double *out_scores,
+                         size_t cap, int *n_hits, int32_t *doc_freqs, int *n_df);
 int wsr_oracle_search(const wsr_oracle_index *h, const char *const *terms, const size_t *lens,
                       int n_terms, int k, int32_t *out_docs, double *out_scores, size_t cap,
                       int *n_hits, int32_t *doc_freqs, int *n_df) {
+  return wsr_oracle_search_ex(h, terms, lens, n_terms, k, 0, out_docs, out_scores, cap, n_hits,
+                              doc_freqs, n_df);
+}
+int wsr_oracle_search_ex(const wsr_oracle_index *h, const char *const *terms, const size_t *lens,
+                         int n_terms, int k, int is_phrase, int32_t *out_docs, double *out_scores,
+                         size_t cap, int *n_hits, int32_t *doc_freqs, int *n_df) {
   if (n_terms < 0 || k < 0) return -1;
   std::vector<HeapEntry> r;
   std::vector<int32_t> dfs;
-  int rc = Search(h->ix, terms, lens, n_terms, k, &r, &dfs);
+  int rc = Search(h->ix, terms, lens, n_terms, k, &r, &dfs, is_phrase != 0);
   if (rc) return rc;
   size_t n = r.size() < cap ? r.size() : cap;
   for (size_t i = 0; i < n; i++) {

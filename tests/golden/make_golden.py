@@ -161,6 +161,22 @@ def main():
     qs += gen_query_log.generate("multi_term", groups, 300, 4)
     qs += gen_query_log.generate("mix_aol", groups, 300, 5)
     qs += ["t0 t0", "t1 nosuch", "t5 t3 t5", "t0 t1 t2 t3 t4 t5 t6 t7", '"t0"', " t2  t1 "]
+    # phrase queries (config 4): word n-grams that really occur, random n-grams that mostly do
+    # not, repeated terms, a missing term
+    import random
+    prng = random.Random(21)
+    bodies = [l.split("\t")[1].split(" ") for l in open(ld).read().split("\n")[1:] if l]
+    for n, cnt in ((2, 260), (3, 100), (4, 30), (5, 10)):
+        for _ in range(cnt):
+            b = bodies[prng.randrange(len(bodies))]
+            if len(b) > n:
+                i = prng.randrange(len(b) - n)
+                qs.append('"' + " ".join(b[i:i + n]) + '"')
+    allt = sorted(groups["low"] + groups["high"])
+    for n, cnt in ((2, 60), (3, 20)):
+        for _ in range(cnt):
+            qs.append('"' + " ".join(prng.choice(groups["high"]) for _ in range(n)) + '"')
+    qs += ['"t0 t0"', '"t1 t0 t1"', '"t0 nosuch"', '"t3 t2"', '"t2 t3"', '"' + allt[5] + " " + allt[9] + '"']
     make_fixture("zipf2k", ld, qs)
 
     # E. the same corpus as two document partitions (docs 0-999 / 1000-1999), each indexed on

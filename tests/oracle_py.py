@@ -45,6 +45,9 @@ def lib():
         L.wsr_oracle_search.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
                                         C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                         C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
+        L.wsr_oracle_search_ex.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+                                           C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                           C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
         L.wsr_oracle_time_batch.argtypes = [C.c_void_p, C.POINTER(C.c_char_p),
                                             C.POINTER(C.c_size_t), C.c_void_p, C.c_int64, C.c_int,
                                             C.c_int, C.POINTER(C.c_uint64)]
@@ -107,7 +110,7 @@ class OracleIndex:
         lib().wsr_oracle_decode_list(self._h, t, len(t), docs.ctypes.data, tfs.ctypes.data, df)
         return docs, tfs
 
-    def search(self, terms, k=10):
+    def search(self, terms, k=10, is_phrase=False):
         """-> (docs[int32], scores[float64], doc_freqs[list]) exactly as VacuumEngine::Search."""
         enc = [t.encode() for t in terms]
         n = len(enc)
@@ -120,9 +123,9 @@ class OracleIndex:
         scores = np.empty(max(cap, 1), np.float64)
         dfs = np.empty(max(n, 1), np.int32)
         nh, ndf = C.c_int(0), C.c_int(0)
-        rc = lib().wsr_oracle_search(self._h, arr, lens, n, k, docs.ctypes.data,
-                                     scores.ctypes.data, cap, C.byref(nh), dfs.ctypes.data,
-                                     C.byref(ndf))
+        rc = lib().wsr_oracle_search_ex(self._h, arr, lens, n, k, int(is_phrase), docs.ctypes.data,
+                                        scores.ctypes.data, cap, C.byref(nh), dfs.ctypes.data,
+                                        C.byref(ndf))
         if rc != 0:
             raise RuntimeError(f"oracle search rc={rc}")
         return docs[:nh.value].copy(), scores[:nh.value].copy(), dfs[:ndf.value].tolist()

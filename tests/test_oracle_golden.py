@@ -12,7 +12,7 @@ FIXTURES = ["hello3", "abc3", "wiki4", "zipf2k"]
 
 
 def _queries(d):
-    return [parse_query_line(l)[0] for l in open(os.path.join(d, "queries.txt"))]
+    return [parse_query_line(l) for l in open(os.path.join(d, "queries.txt"))]
 
 
 @pytest.mark.parametrize("name", FIXTURES)
@@ -24,8 +24,8 @@ def test_search_matches_reference(golden_dir, name, k, fn):
     ref = read_ref_results(os.path.join(d, fn))
     qs = _queries(d)
     assert len(ref) == len(qs)
-    for q, (docs, scores, dfs) in zip(qs, ref):
-        od, os_, odfs = ix.search(q, k)
+    for (q, is_phrase), (docs, scores, dfs) in zip(qs, ref):
+        od, os_, odfs = ix.search(q, k, is_phrase=is_phrase)
         assert np.array_equal(od, docs), q
         assert np.array_equal(os_.view(np.uint64), scores.view(np.uint64)), q
         assert odfs == dfs, q
