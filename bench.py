@@ -275,7 +275,7 @@ def ours(a, rank, world, local_rank):
         text = open(qlog, "rb").read()
 
     t0 = time.time()
-    eng = GpuVacuumEngine(corpus_dir, device=local_rank).Load()
+    eng = GpuVacuumEngine(corpus_dir, device=local_rank, positions=False).Load()
     load_s = time.time() - t0
     info = eng.info()
     shard = None

@@ -26,6 +26,8 @@ extern "C" {
 
 #define WSR_MAX_TERMS 8      /* QueryProcessor's phrase capacity, query_processing.h:695 */
 #define WSR_TERM_ABSENT 0xFFFFFFFFu
+#define WSR_QUERY_PHRASE 1u
+#define WSR_OPEN_POSITIONS 1u   /* also load the position column (4 B per token in HBM) */
 
 typedef enum {
   WSR_OK = 0,
@@ -54,7 +56,9 @@ typedef struct {
   uint32_t term_ids[WSR_MAX_TERMS];
   uint32_t n_terms;
   uint32_t k;      /* n_results */
-  uint32_t flags;  /* reserved (phrase bit later) */
+  uint32_t flags;  /* WSR_QUERY_PHRASE: SearchQuery::is_phrase — with >= 2 terms a document is
+                    * ranked only if the terms occur at consecutive positions, in query order
+                    * (query_processing.h:886-895); needs WSR_OPEN_POSITIONS */
 } wsr_query;
 
 /* Index statistics. */
@@ -87,6 +91,10 @@ void wsr_host_free(void *p);
  * sharding. */
 wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_shards,
                           int loader_threads, char *err, size_t errlen);
+/* Same with flags: WSR_OPEN_POSITIONS loads the reference's position column (skip-list
+ * addressed "cozy box" packs, flash_iterators.h:558-661) so that phrase queries can be served. */
+wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int n_shards,
+                             int loader_threads, unsigned flags, char *err, size_t errlen);
 void wsr_index_close(wsr_index *idx);
 int wsr_index_get_info(const wsr_index *idx, wsr_index_info *info);
 
@@ -132,10 +140,11 @@ int wsr_decode_list(wsr_index *idx, uint32_t term_id, uint32_t *docs, uint32_t *
 int wsr_decode_all(wsr_index *idx, uint64_t *checksum, float *kernel_ms);
 
 /* ---- Search(): VacuumEngine::Search (vacuum_engine.h:201-258) ----------------------------
- * String-term single query, blocking. hits must hold k entries, doc_freqs n_terms entries.
+ * String-term single query, blocking; flags = WSR_QUERY_PHRASE for SearchQuery::is_phrase. hits must hold k entries, doc_freqs n_terms entries.
  * *n_doc_freqs is 0 when the reference returns early with an empty result, else n_terms. */
 int wsr_search(wsr_index *idx, const char *const *terms, const size_t *term_lens, int n_terms,
-               int k, wsr_hit *hits, int *n_hits, uint32_t *doc_freqs, int *n_doc_freqs);
+               int k, unsigned flags, wsr_hit *hits, int *n_hits, uint32_t *doc_freqs,
+               int *n_doc_freqs);
 
 /* Batched Search over HOST buffers: the query batch is copied to the device, processed by
  * the batch scheduler in one pass, and the results copied back (all inside the call).

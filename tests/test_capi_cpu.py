@@ -43,6 +43,7 @@ def test_interface_mirrors_reference_names():
     import wiser_b200 as w
     q = w.SearchQuery(["a", "b"])
     assert (q.n_results, q.return_snippets, q.n_snippet_passages, q.is_phrase) == (5, False, 3, False)
+    assert w.SearchQuery(["a", "b"], True).is_phrase
     for name in ("Load", "Search", "TermCount", "PostinglistSizes", "AddDocument", "LoadLocalDocuments",
                  "Serialize", "Deserialize"):
         assert hasattr(w.GpuVacuumEngine, name)

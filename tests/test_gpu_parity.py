@@ -49,7 +49,7 @@ def test_topk_vs_reference(engines, name, k, fn):
     eng, _, d = engines[name]
     ref = read_ref_results(os.path.join(d, fn))
     full = read_ref_results(os.path.join(d, "ref_full.txt.gz"))
-    qs = [SearchQuery(parse_query_line(l)[0], n_results=k) for l in open(os.path.join(d, "queries.txt"))]
+    qs = [SearchQuery(*parse_query_line(l), n_results=k) for l in open(os.path.join(d, "queries.txt"))]
     res = eng.SearchBatch(qs)
     assert len(res) == len(ref)
     for q, r, (rd, rs, rdf), (fd, fs, _) in zip(qs, res, ref, full):
@@ -65,7 +65,7 @@ def test_full_intersection_vs_reference(engines, name):
     eng, _, d = engines[name]
     full = read_ref_results(os.path.join(d, "ref_full.txt.gz"))
     lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
-    qs = [SearchQuery(parse_query_line(l)[0], n_results=1000000) for l in lines]
+    qs = [SearchQuery(*parse_query_line(l), n_results=1000000) for l in lines]
     # collect-mode segments are sized by the shortest list; keep batches modest
     for lo in range(0, len(qs), 512):
         chunk = qs[lo:lo + 512]
@@ -107,7 +107,7 @@ def test_document_partitioned_shards_merge(golden_dir, n_shards):
     from wiser_b200.capi import HIT_DTYPE, check, lib
     d = os.path.join(golden_dir, "zipf2k")
     lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
-    qs = [SearchQuery(parse_query_line(l)[0], n_results=10) for l in lines]
+    qs = [SearchQuery(*parse_query_line(l), n_results=10) for l in lines]
     whole = GpuVacuumEngine(d).Load()
     qarr = whole.make_queries(qs)
     ref_hits, ref_n, _, _ = whole.search_batch(qarr, 10)
@@ -147,7 +147,7 @@ def test_partition_directories_with_global_stats(golden_dir):
     from wiser_b200.capi import HIT_DTYPE, check, lib
     d = os.path.join(golden_dir, "zipf2k")
     lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
-    qs = [SearchQuery(parse_query_line(l)[0], n_results=10) for l in lines]
+    qs = [SearchQuery(*parse_query_line(l), n_results=10) for l in lines]
     whole = GpuVacuumEngine(d).Load()
     ref_hits, ref_n, _, _ = whole.search_batch(whole.make_queries(qs), 10)
     ora = OracleIndex(d)
@@ -199,7 +199,7 @@ def test_generated_corpus_vs_oracle(tmp_path):
              gen_query_log.generate("single_low", groups, 60, 5))
     eng = GpuVacuumEngine(d).Load()
     ora = OracleIndex(d)
-    qs = [SearchQuery(parse_query_line(l)[0], n_results=10) for l in lines]
+    qs = [SearchQuery(*parse_query_line(l), n_results=10) for l in lines]
     res = eng.SearchBatch(qs)
     for q, r in zip(qs, res):
         rd, rs, rdf = ora.search(q.terms, 10)

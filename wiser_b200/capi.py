@@ -11,6 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libwsr.so")
 
 WSR_MAX_TERMS = 8
 WSR_TERM_ABSENT = 0xFFFFFFFF
+WSR_QUERY_PHRASE = 1
+WSR_OPEN_POSITIONS = 1
 
 QUERY_DTYPE = np.dtype([("term_ids", np.uint32, (WSR_MAX_TERMS,)), ("n_terms", np.uint32),
                         ("k", np.uint32), ("flags", np.uint32)])
@@ -34,7 +36,7 @@ class BatchStats(C.Structure):
 
 
 EXPORTS = [
-    "wsr_last_error", "wsr_device_count", "wsr_host_alloc", "wsr_host_free", "wsr_index_open",
+    "wsr_last_error", "wsr_device_count", "wsr_host_alloc", "wsr_host_free", "wsr_index_open", "wsr_index_open_ex",
     "wsr_index_close", "wsr_index_get_info", "wsr_term_lookup", "wsr_term_at", "wsr_decode_list",
     "wsr_decode_all", "wsr_search", "wsr_search_batch", "wsr_batch_create", "wsr_batch_destroy",
     "wsr_batch_run", "wsr_batch_sync", "wsr_batch_fetch", "wsr_batch_device_results",
@@ -61,13 +63,15 @@ def lib():
     L.wsr_host_free.argtypes = [vp]
     L.wsr_index_open.restype = vp
     L.wsr_index_open.argtypes = [cp, C.c_int, C.c_int, C.c_int, C.c_int, cp, sz]
+    L.wsr_index_open_ex.restype = vp
+    L.wsr_index_open_ex.argtypes = [cp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, cp, sz]
     L.wsr_index_close.argtypes = [vp]
     L.wsr_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.wsr_term_lookup.argtypes = [vp, cp, sz, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.wsr_term_at.argtypes = [vp, C.c_uint32, cp, sz, C.POINTER(C.c_uint32)]
     L.wsr_decode_list.argtypes = [vp, C.c_uint32, vp, vp, sz, C.POINTER(sz)]
     L.wsr_decode_all.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
-    L.wsr_search.argtypes = [vp, C.POINTER(cp), C.POINTER(sz), C.c_int, C.c_int, vp,
+    L.wsr_search.argtypes = [vp, C.POINTER(cp), C.POINTER(sz), C.c_int, C.c_int, C.c_uint, vp,
                              C.POINTER(C.c_int), vp, C.POINTER(C.c_int)]
     L.wsr_search_batch.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
     L.wsr_batch_create.restype = vp

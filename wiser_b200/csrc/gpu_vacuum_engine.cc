@@ -43,8 +43,8 @@ GpuVacuumEngine::~GpuVacuumEngine() {
 void GpuVacuumEngine::Load() {
   if (idx_) Fatal("Engine is already loaded.");                     // vacuum_engine.h:145
   char err[512] = {0};
-  idx_ = wsr_index_open(dir_.c_str(), opt_.device, opt_.shard, opt_.n_shards, opt_.loader_threads,
-                        err, sizeof(err));
+  idx_ = wsr_index_open_ex(dir_.c_str(), opt_.device, opt_.shard, opt_.n_shards, opt_.loader_threads,
+                           opt_.load_positions ? WSR_OPEN_POSITIONS : 0u, err, sizeof(err));
   if (!idx_) Fatal(std::string("wsr_index_open: ") + err);
   batcher_ = std::thread([this]() { BatcherLoop(); });
 }
@@ -69,9 +69,9 @@ bool GpuVacuumEngine::ToWsrQuery(const SearchQuery &q, wsr_query *out) const {
   memset(out, 0, sizeof(*out));
   if (q.n_results <= 0 || q.terms.empty()) return false;           // vacuum_engine.h:206-208
   if (q.terms.size() > WSR_MAX_TERMS) Fatal("more than WSR_MAX_TERMS query terms");
-  if (q.is_phrase && q.terms.size() > 1) Fatal("phrase queries are not implemented on the GPU path yet");
   out->n_terms = (uint32_t)q.terms.size();
   out->k = (uint32_t)q.n_results;
+  out->flags = q.is_phrase ? WSR_QUERY_PHRASE : 0u;
   for (size_t t = 0; t < q.terms.size(); t++) {
     uint32_t id, df;
     if (wsr_term_lookup(idx_, q.terms[t].data(), q.terms[t].size(), &id, &df) != 0)

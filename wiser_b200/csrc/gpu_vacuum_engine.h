@@ -77,6 +77,7 @@ struct GpuEngineOptions {
   int device = 0;
   int shard = 0, n_shards = 1;       // document partition held by this engine
   int loader_threads = 0;            // 0 = all cores
+  bool load_positions = true;        // position column in HBM: needed by phrase queries
   int coalesce_max_batch = 4096;     // Search() callers coalesced per launch
   int coalesce_window_us = 100;      // how long the batcher waits for more callers
 };

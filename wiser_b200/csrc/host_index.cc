@@ -134,12 +134,15 @@ struct Chunk {               // output of one slice of terms
   std::vector<BlockInfo> blk_info;
   std::vector<uint32_t> blk_last;
   std::vector<uint8_t> payload;
+  std::vector<uint32_t> positions;   // optional position column, absolute in-document positions
+  std::vector<uint32_t> blk_pos;     // per block: index of its first position
   int64_t postings = 0, postings_global = 0;
   std::string err;
 };
 
 struct Builder {
   uint32_t filter_ppw = 2;   // postings per 32-bit filter word (WSR_FILTER_PPW overrides, 1..8)
+  bool want_positions = false;
   const FileView &vac;
   const std::vector<uint64_t> &list_offs;
   const HostIndex &ix;      // norms / cache already filled
@@ -154,7 +157,8 @@ struct Builder {
     return f;
   }
 
-  bool BuildList(uint64_t off, Chunk *c, std::vector<uint32_t> *docs, std::vector<uint32_t> *tfs) {
+  bool BuildList(uint64_t off, Chunk *c, std::vector<uint32_t> *docs, std::vector<uint32_t> *tfs,
+                 std::vector<uint32_t> &pos_scratch) {
     // Posting-list header: VacuumPostingListIterator::ResetWithZoneInfo, flash_iterators.h:903-956
     if (off + 10 > vac.size || vac.data[off] != 0xF4) { c->err = "bad posting-list magic"; return false; }
     ByteCursor cur{vac.data + off + 1, vac.data + vac.size};
@@ -167,12 +171,15 @@ struct Builder {
     if (n_rows != (df + kBlock - 1) / kBlock) { c->err = "skip rows != ceil(df/128)"; return false; }
     docs->resize(df);
     tfs->resize(df);
-    uint64_t prev_doc = 0, docid_off = 0, tf_off = 0;
+    uint64_t prev_doc = 0, docid_off = 0, tf_off = 0, pos_col_off = 0;
     for (uint64_t r = 0; r < n_rows; r++) {
       prev_doc += cur.Varint();
       docid_off += cur.Varint();
       tf_off += cur.Varint();
-      cur.Varint(); cur.Varint(); cur.Varint(); cur.Varint();  // position / offset columns
+      const uint64_t pos_off = cur.Varint();      // position blob offset (delta vs previous row)
+      cur.Varint();                               // position in-blob index
+      cur.Varint(); cur.Varint();                 // offset column (snippets only)
+      if (r == 0) pos_col_off = pos_off;          // the column starts at posting 0's blob
       if (!cur.ok) { c->err = "truncated skip list"; return false; }
       const int n = (int)std::min<uint64_t>(kBlock, df - r * kBlock);
       uint32_t *d = docs->data() + r * kBlock;
@@ -185,6 +192,28 @@ struct Builder {
       // previous_doc_id (DeltaEncodedPackedIntsIterator::Reset, packed_value.h:328-333)
       uint32_t run = (uint32_t)prev_doc;
       for (int i = 0; i < n; i++) { run += d[i]; d[i] = run; }
+    }
+    // Position column (phrase queries): all bags' values back to back, delta-coded inside each
+    // bag, cut into 128-value packs + a VInts tail (GeneralTermEntry::GetCozyBoxWriter,
+    // flash_engine_dumper.h:78-104; read side CozyBoxIterator, flash_iterators.h:280-425).
+    std::vector<uint32_t> &pos_vals = pos_scratch;
+    pos_vals.clear();
+    if (want_positions) {
+      uint64_t total = 0;
+      for (uint64_t i = 0; i < df; i++) total += (*tfs)[i];
+      pos_vals.resize(total);
+      uint64_t off = pos_col_off, done = 0;
+      while (done < total) {
+        const int n = (int)std::min<uint64_t>(kBlock, total - done);
+        if (!ReadBlob(vac.data, vac.size, off, n, pos_vals.data() + done)) { c->err = "bad position blob"; return false; }
+        if (vac.data[off] == 0xD6) off += 2 + 16ull * vac.data[off + 1];
+        done += n;
+      }
+      uint64_t at = 0;
+      for (uint64_t i = 0; i < df; i++) {          // deltas -> absolute positions inside each bag
+        uint32_t run = 0;
+        for (uint32_t j = 0; j < (*tfs)[i]; j++) { run += pos_vals[at]; pos_vals[at++] = run; }
+      }
     }
     // shard filter: contiguous doc-id range
     size_t a = 0, b = df;
@@ -199,6 +228,9 @@ struct Builder {
     li.n_blocks = (uint32_t)((b - a + kBlock - 1) / kBlock);
     uint64_t alg = 0;
     uint32_t base = doc_lo;  // shard 0: 0, as in the reference
+    uint64_t pos_at = 0;     // index into pos_vals of posting s's first position
+    if (want_positions)
+      for (size_t i = 0; i < a; i++) pos_at += (*tfs)[i];
     for (size_t s = a; s < b; s += kBlock) {
       const int n = (int)std::min<size_t>(kBlock, b - s);
       const int nl = (n + 3) / 4;
@@ -242,6 +274,14 @@ struct Builder {
       PackTfRecords(tfr, nl, sh, &c->payload);
       c->blk_info.push_back(bi);
       c->blk_last.push_back(p);
+      if (want_positions) {
+        if (c->positions.size() > 0xFFFFFFF0ull) { c->err = "more than 2^32 positions"; return false; }
+        c->blk_pos.push_back((uint32_t)c->positions.size());
+        uint64_t cnt = 0;
+        for (int i = 0; i < n; i++) cnt += (*tfs)[s + i];
+        c->positions.insert(c->positions.end(), pos_vals.begin() + pos_at, pos_vals.begin() + pos_at + cnt);
+        pos_at += cnt;
+      }
       alg += AlgorithmicBytes(sh);
       base = p;
     }
@@ -270,9 +310,9 @@ struct Builder {
   }
 
   void BuildChunk(Chunk *c) {
-    std::vector<uint32_t> docs, tfs;
+    std::vector<uint32_t> docs, tfs, pos_scratch;
     for (size_t t = c->term_begin; t < c->term_end; t++)
-      if (!BuildList(list_offs[t], c, &docs, &tfs)) return;
+      if (!BuildList(list_offs[t], c, &docs, &tfs, pos_scratch)) return;
   }
 };
 
@@ -314,7 +354,7 @@ uint32_t TermDict::Find(const char *s, size_t len) const {
 }
 
 bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
-                   HostIndex *out, std::string *err) {
+                   HostIndex *out, std::string *err, int flags) {
   HostIndex &ix = *out;
   if (n_shards < 1 || shard < 0 || shard >= n_shards) { *err = "bad shard/n_shards"; return false; }
   ix.shard = shard;
@@ -413,7 +453,9 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
       begin = end;
     }
   }
-  Builder builder{2, vac, list_offs, ix, tfn_tab.data(), (uint32_t)ix.doc_lo, (uint32_t)ix.doc_hi};
+  Builder builder{2, false, vac, list_offs, ix, tfn_tab.data(), (uint32_t)ix.doc_lo, (uint32_t)ix.doc_hi};
+  builder.want_positions = (flags & kLoadPositions) != 0;
+  ix.has_positions = builder.want_positions;
   if (const char *e = getenv("WSR_FILTER_PPW")) {
     const int v = atoi(e);
     if (v >= 1 && v <= 8) builder.filter_ppw = (uint32_t)v;
@@ -434,13 +476,15 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
     worker();
     for (auto &t : pool) t.join();
   }
-  size_t tot_blocks = 0, tot_payload = 0, tot_flt = 0;
+  size_t tot_blocks = 0, tot_payload = 0, tot_flt = 0, tot_pos = 0;
   for (auto &c : chunks) {
     if (!c.err.empty()) { *err = c.err; return false; }
     tot_blocks += c.blk_info.size();
     tot_payload += c.payload.size();
     tot_flt += c.filters.size();
+    tot_pos += c.positions.size();
   }
+  if (tot_pos >= 0xFFFFFFF0ull) { *err = "positions exceed 2^32 entries on one shard"; return false; }
   if (tot_flt >= 0xFFFFFFF0ull) { *err = "filters exceed 2^32 words"; return false; }
   if (tot_payload / 16 > 0xFFFFFFF0ull) { *err = "payload exceeds 64 GiB addressable by u32 offsets"; return false; }
   if (tot_blocks >= (1ull << 25)) { *err = "more than 2^25 blocks on one shard (hit records pack block<<7|slot)"; return false; }
@@ -453,12 +497,19 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
   ix.payload.assign(tot_payload + 1024, 0);  // tail pad: prefetchers read up to 512 B past a block
   ix.filters.assign(tot_flt + 1, 0u);
   ix.list_flt.resize(n_terms);
-  std::vector<size_t> blk_base(chunks.size()), pay_base(chunks.size()), flt_base(chunks.size());
-  size_t bb = 0, pb = 0, fb = 0;
+  if (ix.has_positions) {
+    ix.positions.assign(tot_pos + 1, 0u);
+    ix.blk_pos.assign(tot_blocks + 1, 0u);
+  }
+  std::vector<size_t> blk_base(chunks.size()), pay_base(chunks.size()), flt_base(chunks.size()),
+      pos_base(chunks.size());
+  size_t bb = 0, pb = 0, fb = 0, qb = 0;
   for (size_t i = 0; i < chunks.size(); i++) {
     blk_base[i] = bb;
     pay_base[i] = pb;
     flt_base[i] = fb;
+    pos_base[i] = qb;
+    qb += chunks[i].positions.size();
     bb += chunks[i].blk_info.size();
     pb += chunks[i].payload.size();
     fb += chunks[i].filters.size();
@@ -484,6 +535,12 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
       if (!c.filters.empty())
         memcpy(ix.filters.data() + flt_base[i], c.filters.data(), c.filters.size() * 4);
       std::vector<uint32_t>().swap(c.filters);
+      if (ix.has_positions) {
+        for (size_t j = 0; j < c.blk_pos.size(); j++) ix.blk_pos[b0 + j] = c.blk_pos[j] + (uint32_t)pos_base[i];
+        if (!c.positions.empty())
+          memcpy(ix.positions.data() + pos_base[i], c.positions.data(), c.positions.size() * 4);
+        std::vector<uint32_t>().swap(c.positions);
+      }
       for (size_t j = 0; j < c.blk_info.size(); j++) {
         BlockInfo bi = c.blk_info[j];
         bi.payload_off16 += p0;

@@ -34,6 +34,12 @@
 //                       tests the driver's candidates against the other lists' filters first, so
 //                       the exact probe (block lookup + record search) runs only for the few
 //                       percent that may be present. No false negatives.
+//   positions u32[]     (optional, phrase queries) token positions of every posting, absolute
+//                       inside the document, postings back to back in list order — the
+//                       reference's position column (delta-coded "cozy box" packs addressed
+//                       through the skip list, flash_iterators.h:558-661) with the deltas summed
+//   blk_pos   u32[]     index into positions[] of each block's first posting; a posting's run
+//                       starts at blk_pos + sum of the tfs before it in the block
 //   norms     u8[]      DocLengthCharStore bytes indexed by GLOBAL doc id
 //   cache     f64[256]  Bm25Similarity::cache_ (scoring.h:85-90)
 #ifndef WSR_HOST_INDEX_H
@@ -136,6 +142,9 @@ struct HostIndex {
   std::vector<uint8_t> payload;
   std::vector<uint32_t> filters;
   std::vector<uint64_t> list_flt;     // low 32: first word, high 32: shift (0xFFFFFFFF none)
+  bool has_positions = false;
+  std::vector<uint32_t> positions;
+  std::vector<uint32_t> blk_pos;
   std::vector<uint64_t> list_alg_bytes;  // algorithmic bytes of all blocks of each list
   int64_t n_postings = 0, n_postings_global = 0;
   int shard = 0, n_shards = 1;
@@ -144,8 +153,9 @@ struct HostIndex {
 
 // Parses the vacuum directory and builds the layout for one shard. Multi-threaded over terms.
 // Returns false and sets *err on malformed input.
+enum LoadFlags { kLoadPositions = 1 };
 bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
-                   HostIndex *out, std::string *err);
+                   HostIndex *out, std::string *err, int flags = 0);
 
 }  // namespace wsr
 #endif

@@ -645,6 +645,58 @@ __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, u
   return true;
 }
 
+// ---- phrase verification (QueryProcessor::HandleTheFoundDoc + PhraseQueryProcessor2,
+// query_processing.h:282-362, 886-895): a document that holds every term is ranked only if the
+// terms occur at consecutive positions, in query order. Only existence matters (the score
+// ignores the phrase frequency). Runs per intersection hit, one hit per lane.
+struct PosRun {
+  const uint32_t *p;   // the posting's positions, ascending
+  uint32_t n;          // = tf
+};
+// tf of posting `pos` and the start of its run in positions[]: the block's first position index
+// plus the tfs of the postings before it in the block.
+__device__ __forceinline__ PosRun PositionsOf(const DevIndexView &ix, uint32_t pos) {
+  const uint32_t blk = pos >> 7, slot = pos & 127u;
+  const uint4 info = __ldg(&ix.blk_info[blk]);
+  const uint32_t bits = info.z, tc = ShTcode(bits);
+  const uint4 *src = ix.payload + info.y + DocGranules(bits);
+  uint32_t before = 0, tf = 0;
+  for (uint32_t r = 0; r <= (slot >> 2); r++) {
+    uint32_t t[4];
+    if (tc == 0) {
+      const uint32_t v = __ldg(reinterpret_cast<const unsigned short *>(src) + r);
+      t[0] = v & 15u; t[1] = (v >> 4) & 15u; t[2] = (v >> 8) & 15u; t[3] = v >> 12;
+    } else if (tc == 1) {
+      const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src) + r);
+      t[0] = v & 255u; t[1] = (v >> 8) & 255u; t[2] = (v >> 16) & 255u; t[3] = v >> 24;
+    } else {
+      const uint4 v = __ldg(src + r);
+      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+    }
+    if (r < (slot >> 2)) {
+      before += t[0] + t[1] + t[2] + t[3];
+    } else {
+      const uint32_t s = slot & 3u;
+      before += (s > 0 ? t[0] : 0u) + (s > 1 ? t[1] : 0u) + (s > 2 ? t[2] : 0u);
+      tf = s == 0 ? t[0] : s == 1 ? t[1] : s == 2 ? t[2] : t[3];
+    }
+  }
+  PosRun run;
+  run.p = ix.positions + __ldg(&ix.blk_pos[blk]) + before;
+  run.n = tf;
+  return run;
+}
+// exists p in a with p + 1 in b
+__device__ __forceinline__ bool PhraseTwo(const PosRun a, const PosRun b) {
+  uint32_t i = 0, j = 0;
+  while (i < a.n && j < b.n) {
+    const uint32_t x = __ldg(a.p + i) + 1u, y = __ldg(b.p + j);
+    if (x == y) return true;
+    if (x < y) i++; else j++;
+  }
+  return false;
+}
+
 // ---- two-term units (the headline path): TwoTermNonPhraseQueryProcessor::Process -------------
 // Driver blocks are walked in order; for the smallest unresolved candidate the probe block is
 // located, staged once, and every candidate that falls inside it is resolved in the same pass.
@@ -657,18 +709,25 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
                           UnitStats &st) {
   __syncwarp();
   for (int base = 0; base < nq; base += 32) {
-    const bool has = base + lane < nq;
+    bool has = base + lane < nq;
+    bool keep = true;
     double s = 0.0;
     int doc = 0;
     if (has) {
       const HitRec h = ws->hits[base + lane];
       doc = (int)h.doc;
+      if (q.flags & 1u) {   // phrase: query term 0 must be directly followed by term 1
+        const PosRun ra = PositionsOf(ix, h.pos_a), rb = PositionsOf(ix, h.pos_b);
+        keep = drv == 0 ? PhraseTwo(ra, rb) : PhraseTwo(rb, ra);
+        st.bytes += 4ull * (ra.n + rb.n);
+      }
       const uint32_t tfa = TfAt(ix, h.pos_a), tfb = TfAt(ix, h.pos_b);
       const double cn = sh->cache[__ldg(ix.norms + h.doc)];
       // query order: term 0 first (scoring.h:124-145)
       s = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? tfa : tfb, cn));
       s = __dadd_rn(s, TermScore(idf1, drv == 0 ? tfb : tfa, cn));
     }
+    has = has && keep;
     if (COLLECT) CollectAppend(bv, q, qi, has, doc, s, lane);
     else OfferToTopK(bv, qi, multi, (int)q.k, has, s, doc, top, published, lane);
   }
@@ -866,6 +925,38 @@ __device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const 
     double s64[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
+      if (al[i] && (q.flags & 1u)) {
+        // positions of every term's posting in this doc; p in term 0, p + t in term t for all t
+        PosRun run[M];
+#pragma unroll
+        for (int t = 0; t < M; t++) {
+          run[t].p = nullptr;
+          run[t].n = 0;
+          if (t < m) {
+            const uint32_t pos = t == drv ? (((first_a + ja) << 7) | (4u * lane + i)) : posv[t][i];
+            run[t] = PositionsOf(ix, pos);
+            st.bytes += 4ull * run[t].n;
+          }
+        }
+        uint32_t ptr[M];
+#pragma unroll
+        for (int t = 0; t < M; t++) ptr[t] = 0;
+        bool found = false;
+        for (uint32_t a0 = 0; a0 < run[0].n && !found; a0++) {
+          const uint32_t p0 = __ldg(run[0].p + a0);
+          bool ok = true;
+#pragma unroll
+          for (int t = 1; t < M; t++) {
+            if (t < m && ok) {
+              const uint32_t want = p0 + (uint32_t)t;
+              while (ptr[t] < run[t].n && __ldg(run[t].p + ptr[t]) < want) ptr[t]++;
+              ok = ptr[t] < run[t].n && __ldg(run[t].p + ptr[t]) == want;
+            }
+          }
+          found = ok;
+        }
+        al[i] = found;
+      }
       hit[i] = al[i];
       s64[i] = 0.0;
       if (al[i]) {

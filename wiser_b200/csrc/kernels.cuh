@@ -25,6 +25,8 @@ struct DevIndexView {
   const float *blk_max;       // SoA copy of blk_info.w
   const uint32_t *filters;    // per-list doc-range-partitioned Bloom filters
   const uint2 *list_flt;      // per term {first filter word, shift g (0xFFFFFFFF: no filter)}
+  const uint32_t *positions;  // optional: in-document token positions, postings back to back
+  const uint32_t *blk_pos;    // optional: index into positions[] of each block's first posting
   uint32_t n_terms;
   uint32_t n_docs;
   uint32_t doc_lo;            // first doc id held by this shard (filter origin)
@@ -33,7 +35,8 @@ struct DevIndexView {
 // One planned query. unit_begin = index of its first work unit in its class queue.
 struct DevQuery {
   uint32_t term[WSR_MAX_TERMS];  // query order
-  uint16_t n_terms;
+  uint8_t n_terms;
+  uint8_t flags;                 // bit 0: phrase query (terms must occur at consecutive positions)
   uint16_t unit_blocks;          // driver-list blocks per work unit of this query
   uint32_t k;
   uint32_t unit_begin;

@@ -112,11 +112,6 @@ int main(int argc, char **argv) {
       fprintf(stderr, "parse: %s\n", wsr_last_error());
       return 1;
     }
-    for (int i = 0; i < n; i++)
-      if ((qs[i].flags & 1u) && qs[i].n_terms > 1) {
-        fprintf(stderr, "phrase queries are not implemented on the GPU path yet (line %d)\n", i + 1);
-        return 1;
-      }
     const int B = batch_size > 0 ? batch_size : n;
     wsr_hit *hits = (wsr_hit *)wsr_host_alloc((size_t)B * n_results * sizeof(wsr_hit));
     int32_t *n_hits = (int32_t *)wsr_host_alloc((size_t)B * 4);

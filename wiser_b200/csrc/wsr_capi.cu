@@ -167,6 +167,7 @@ struct wsr_index {
   DevBuf<float> d_blk_max;
   DevBuf<uint32_t> d_filters;
   DevBuf<uint2> d_list_flt;
+  DevBuf<uint32_t> d_positions, d_blk_pos;
   DevIndexView view;
   int64_t n_blocks = 0, payload_bytes = 0, hbm_bytes = 0;
   uint32_t doc_base = 0;          // global id of this partition's doc 0
@@ -264,7 +265,9 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
         p.listed_bytes += ix->host.list_alg_bytes[q.term_ids[t2]];
         if (t2 != best) probe_blocks += li.n_blocks;
       }
-      dq.n_terms = (uint16_t)q.n_terms;
+      dq.n_terms = (uint8_t)q.n_terms;
+      dq.flags = (q.flags & 1u) && q.n_terms > 1 ? 1 : 0;   // a one-term "phrase" is a plain query
+      if (dq.flags && !ix->host.has_positions) { p.err = WSR_ERR_IO; return; }
       dq.k = q.k;
       dq.driver = best;
       dq.out_slot = (uint32_t)i;
@@ -289,6 +292,8 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
   ParallelFor(T, classify);
   for (const Part &p : part) {
     if (p.err == WSR_ERR_UNSUPPORTED) return Fail(p.err, "query has more than WSR_MAX_TERMS terms");
+    if (p.err == WSR_ERR_IO)
+      return Fail(WSR_ERR_UNSUPPORTED, "phrase query on an index opened without WSR_OPEN_POSITIONS");
     if (p.err) return Fail(p.err, "query k exceeds k_stride, or term id out of range");
   }
   // exclusive prefixes: class-major, thread-minor
@@ -489,6 +494,11 @@ void wsr_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_shards,
                           int loader_threads, char *err, size_t errlen) {
+  return wsr_index_open_ex(vacuum_dir, device, shard, n_shards, loader_threads, 0, err, errlen);
+}
+
+wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int n_shards,
+                             int loader_threads, unsigned flags, char *err, size_t errlen) {
   auto fail = [&](const std::string &m) -> wsr_index * {
     g_err = m;
     if (err && errlen) snprintf(err, errlen, "%s", m.c_str());
@@ -503,7 +513,8 @@ wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_s
   if (device < 0 || device >= ndev) return fail("bad device ordinal");
   std::unique_ptr<wsr_index> ix(new wsr_index);
   std::string e;
-  if (!LoadVacuumDir(vacuum_dir, shard, n_shards, loader_threads, &ix->host, &e))
+  if (!LoadVacuumDir(vacuum_dir, shard, n_shards, loader_threads, &ix->host, &e,
+                     (flags & WSR_OPEN_POSITIONS) ? kLoadPositions : 0))
     return fail(std::string(vacuum_dir) + ": " + e);
   HostIndex &h = ix->host;
   // idf per term: calc_es_idf(doc_count, doc_freq), scoring.h:21-25 — GLOBAL N and df
@@ -569,6 +580,20 @@ wsr_index *wsr_index_open(const char *vacuum_dir, int device, int shard, int n_s
   v.n_terms = (uint32_t)h.lists.size();
   v.n_docs = (uint32_t)h.n_docs;
   v.doc_lo = (uint32_t)h.doc_lo;
+  v.positions = nullptr;
+  v.blk_pos = nullptr;
+  if (h.has_positions) {
+    if (!cu(ix->d_positions.Ensure(h.positions.size() + 1), "cudaMalloc positions") ||
+        !cu(ix->d_blk_pos.Ensure(h.blk_pos.size() + 1), "cudaMalloc blk_pos") ||
+        !cu(cudaMemcpy(ix->d_positions.p, h.positions.data(), h.positions.size() * 4, cudaMemcpyHostToDevice), "H2D positions") ||
+        !cu(cudaMemcpy(ix->d_blk_pos.p, h.blk_pos.data(), h.blk_pos.size() * 4, cudaMemcpyHostToDevice), "H2D blk_pos"))
+      return fail(e);
+    v.positions = ix->d_positions.p;
+    v.blk_pos = ix->d_blk_pos.p;
+    ix->hbm_bytes += (int64_t)h.positions.size() * 4 + (int64_t)h.blk_pos.size() * 4;
+    std::vector<uint32_t>().swap(h.positions);
+    std::vector<uint32_t>().swap(h.blk_pos);
+  }
   // the block arrays now live in HBM only
   std::vector<uint8_t>().swap(h.payload);
   std::vector<BlockInfo>().swap(h.blk_info);
@@ -998,9 +1023,6 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
     int n = 0;
     rc = wsr_parse_query_log(idx, ct, cl, k, qs.data(), (int)qs.size(), &n);   // overlaps the GPU
     if (rc) break;
-    for (int i = 0; i < n; i++)
-      if ((qs[i].flags & 1u) && qs[i].n_terms > 1) { rc = Fail(WSR_ERR_UNSUPPORTED, "phrase queries are not built yet"); break; }
-    if (rc) break;
     rc = drain(s);                         // this slot's previous chunk must be finished
     if (rc) break;
     wsr_batch *b = bt[s];
@@ -1035,7 +1057,8 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
 }
 
 int wsr_search(wsr_index *idx, const char *const *terms, const size_t *term_lens, int n_terms,
-               int k, wsr_hit *hits, int *n_hits, uint32_t *doc_freqs, int *n_doc_freqs) {
+               int k, unsigned flags, wsr_hit *hits, int *n_hits, uint32_t *doc_freqs,
+               int *n_doc_freqs) {
   if (!idx || n_terms < 0 || k < 0 || !n_hits) return Fail(WSR_ERR_ARG, "bad argument");
   if (n_terms > WSR_MAX_TERMS) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
   *n_hits = 0;
@@ -1045,6 +1068,7 @@ int wsr_search(wsr_index *idx, const char *const *terms, const size_t *term_lens
   memset(&q, 0, sizeof(q));
   q.n_terms = (uint32_t)n_terms;
   q.k = (uint32_t)k;
+  q.flags = flags;
   for (int t = 0; t < n_terms; t++) {
     uint32_t id, df;
     if (wsr_term_lookup(idx, terms[t], term_lens[t], &id, &df) != 0) return WSR_OK;  // missing term

@@ -20,10 +20,10 @@ from .capi import HIT_DTYPE, QUERY_DTYPE, WSR_MAX_TERMS, WSR_TERM_ABSENT, check,
 @dataclass
 class SearchQuery:            # types.h:205-218 (same field names and defaults)
     terms: List[str] = field(default_factory=list)
+    is_phrase: bool = False
     n_results: int = 5
     return_snippets: bool = False
     n_snippet_passages: int = 3
-    is_phrase: bool = False
 
 
 @dataclass
@@ -72,11 +72,13 @@ class GpuVacuumEngine:
     vacuum_engine.h:120-300). URL scheme: gpu:vacuum_dump:<dir>."""
 
     def __init__(self, engine_dir_path: str, bloom_enable_factor: int = 1, device: int = 0,
-                 shard: int = 0, n_shards: int = 1, loader_threads: int = 0):
+                 shard: int = 0, n_shards: int = 1, loader_threads: int = 0, positions: bool = True):
+        """positions: also load the position column (needed by phrase queries; 4 B/token)."""
         self.engine_dir_path = engine_dir_path
         self.bloom_enable_factor = bloom_enable_factor
         self.device, self.shard, self.n_shards = device, shard, n_shards
         self.loader_threads = loader_threads
+        self.positions = positions
         self._h = None
 
     # ---- SearchEngineServiceNew ----------------------------------------------------------
@@ -84,8 +86,9 @@ class GpuVacuumEngine:
         if self._h:
             raise RuntimeError("Engine is already loaded.")       # vacuum_engine.h:145
         err = C.create_string_buffer(512)
-        self._h = lib().wsr_index_open(self.engine_dir_path.encode(), self.device, self.shard,
-                                       self.n_shards, self.loader_threads, err, 512)
+        self._h = lib().wsr_index_open_ex(self.engine_dir_path.encode(), self.device, self.shard,
+                                          self.n_shards, self.loader_threads,
+                                          capi.WSR_OPEN_POSITIONS if self.positions else 0, err, 512)
         if not self._h:
             raise capi.WsrError("wsr_index_open: " + err.value.decode())
         return self
@@ -102,8 +105,6 @@ class GpuVacuumEngine:
         return out
 
     def Search(self, query: SearchQuery) -> SearchResult:
-        if query.is_phrase and len(query.terms) > 1:
-            raise NotImplementedError("phrase queries (SURVEY §8 config 4) are not built yet")
         enc = [t.encode() for t in query.terms]
         n = len(enc)
         k = int(query.n_results)
@@ -112,8 +113,9 @@ class GpuVacuumEngine:
         hits = np.zeros(max(k, 1), HIT_DTYPE)
         dfs = np.zeros(WSR_MAX_TERMS, np.uint32)
         nh, ndf = C.c_int(0), C.c_int(0)
-        check(lib().wsr_search(self._h, arr, lens, n, k, hits.ctypes.data, C.byref(nh),
-                               dfs.ctypes.data, C.byref(ndf)))
+        check(lib().wsr_search(self._h, arr, lens, n, k,
+                               capi.WSR_QUERY_PHRASE if query.is_phrase else 0, hits.ctypes.data,
+                               C.byref(nh), dfs.ctypes.data, C.byref(ndf)))
         res = SearchResult()
         for i in range(nh.value):
             res.entries.append(SearchResultEntry(int(hits["doc_id"][i]), float(hits["score"][i])))
@@ -157,6 +159,7 @@ class GpuVacuumEngine:
                 ids[j] = tid
             arr["n_terms"][i] = len(q.terms)
             arr["k"][i] = q.n_results
+            arr["flags"][i] = capi.WSR_QUERY_PHRASE if q.is_phrase else 0
         return arr
 
     def parse_query_log(self, text: bytes, k: int) -> np.ndarray:
@@ -200,9 +203,6 @@ class GpuVacuumEngine:
     def SearchBatch(self, queries: Sequence[SearchQuery]) -> List[SearchResult]:
         if not queries:
             return []
-        for q in queries:
-            if q.is_phrase and len(q.terms) > 1:
-                raise NotImplementedError("phrase queries are not built yet")
         qarr = self.make_queries(queries)
         k_stride = max(1, max(q.n_results for q in queries))
         hits, n_hits, dfs, ndfs = self.search_batch(qarr, k_stride, want_doc_freqs=True)
