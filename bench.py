@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=100_000)
     ap.add_argument("--workload", default="two_term",
                     choices=["two_term", "two_term_hh", "two_term_lh", "two_term_ll", "single_high",
-                             "single_low", "multi_term", "mix_aol"])
+                             "single_low", "multi_term", "mix_aol", "phrase2", "phrase3"])
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--high-df", type=int, default=10000)
@@ -70,7 +70,8 @@ def parse_args():
 # ---------------------------------------------------------------------------------------------
 def ensure_corpus(a, part=0, n_parts=1):
     """One partition of the corpus = a standalone vacuum index of a.docs documents."""
-    name = f"c_d{a.docs}_v{a.vocab}_mu{a.mu}_s{a.seed}_p{part}of{n_parts}"
+    with_pos = a.workload.startswith("phrase")
+    name = f"c_d{a.docs}_v{a.vocab}_mu{a.mu}_s{a.seed}_p{part}of{n_parts}" + ("_pos" if with_pos else "")
     d = os.path.join(a.dir, name)
     done = os.path.join(d, "DONE.json")
     if not os.path.exists(done):
@@ -79,7 +80,8 @@ def ensure_corpus(a, part=0, n_parts=1):
             raise RuntimeError(f"{GEN} missing: run __graft_entry__.build()")
         t0 = time.time()
         out = subprocess.check_output([GEN, "--out", d, "--docs", str(a.docs), "--vocab", str(a.vocab),
-                                       "--mu", str(a.mu), "--seed", str(a.seed * 1000 + part)])
+                                       "--mu", str(a.mu), "--seed", str(a.seed * 1000 + part),
+                                       "--positions", "1" if with_pos else "0"])
         info = json.loads(out.decode().strip().split("\n")[-1])
         info["wall_s"] = time.time() - t0
         with open(done, "w") as f:
@@ -275,7 +277,7 @@ def ours(a, rank, world, local_rank):
         text = open(qlog, "rb").read()
 
     t0 = time.time()
-    eng = GpuVacuumEngine(corpus_dir, device=local_rank, positions=False).Load()
+    eng = GpuVacuumEngine(corpus_dir, device=local_rank, positions=a.workload.startswith("phrase")).Load()
     load_s = time.time() - t0
     info = eng.info()
     shard = None
@@ -431,9 +433,9 @@ def ours(a, rank, world, local_rank):
         lines = text.decode().split("\n")
         idxs = list(range(0, n, max(1, n // a.parity_sample)))[:a.parity_sample]
         for i in idxs:
-            terms = parse_query_line(lines[i])[0]
-            rd, rs, _ = ora.search(terms, a.k)
-            fd, fs, _ = ora.search(terms, 1 << 30)
+            terms, is_phrase = parse_query_line(lines[i])
+            rd, rs, _ = ora.search(terms, a.k, is_phrase=is_phrase)
+            fd, fs, _ = ora.search(terms, 1 << 30, is_phrase=is_phrase)
             check_topk(rd, rs, hits["doc_id"][i, :nh[i]], hits["score"][i, :nh[i]], fd, fs, what=lines[i])
         parity = {"queries_checked": len(idxs), "against": "CPU oracle (bit-exact scores, tie-aware docs)"}
 

@@ -190,13 +190,15 @@ def test_generated_corpus_vs_oracle(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     d = str(tmp_path / "c")
     subprocess.check_call([os.path.join(root, "wiser_b200", "wsr_gen_corpus"), "--out", d, "--docs", "60000",
-                           "--vocab", "80000", "--seed", "11"], stdout=subprocess.DEVNULL)
+                           "--vocab", "80000", "--seed", "11", "--positions", "1"], stdout=subprocess.DEVNULL)
     groups = gen_query_log.load_groups(os.path.join(d, "terms.txt"), 3000)
     lines = (gen_query_log.generate("two_term", groups, 400, 1) +
              gen_query_log.generate("two_term_hh", groups, 150, 2) +
              gen_query_log.generate("multi_term", groups, 150, 3) +
              gen_query_log.generate("single_high", groups, 60, 4) +
-             gen_query_log.generate("single_low", groups, 60, 5))
+             gen_query_log.generate("single_low", groups, 60, 5) +
+             gen_query_log.generate("phrase2", groups, 200, 6) +
+             gen_query_log.generate("phrase3", groups, 80, 7))
     eng = GpuVacuumEngine(d).Load()
     ora = OracleIndex(d)
     qs = [SearchQuery(*parse_query_line(l), n_results=10) for l in lines]
@@ -207,12 +209,18 @@ def test_generated_corpus_vs_oracle(tmp_path):
         assert r.doc_freqs == rdf
         check_topk(rd, rs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], fd, fs,
                    what=" ".join(q.terms))
-    # full intersections through the collect path for a sample
-    for q in qs[:120:3]:
+    # full intersections through the collect path for a sample (AND and phrase queries)
+    sample = qs[:120:3] + qs[-280::7]
+    for q in sample:
         q.n_results = 100000
+    res = eng.SearchBatch(sample)
+    for q, r in zip(sample, res):
+        fd, fs, _ = ora.search(q.terms, 1 << 30, is_phrase=q.is_phrase)
+        check_full(fd, fs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], what=" ".join(q.terms))
+    return
     res = eng.SearchBatch(qs[:120:3])
     for q, r in zip(qs[:120:3], res):
-        fd, fs, _ = ora.search(q.terms, 1 << 30)
+        fd, fs, _ = ora.search(q.terms, 1 << 30, is_phrase=q.is_phrase)
         check_full(fd, fs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], what=" ".join(q.terms))
 
 

@@ -56,6 +56,16 @@ def two_term_fixed(rng, groups, n, g1name, g2name):
     return queries
 
 
+def phrase_queries(rng, groups, n, m=2):
+    """Quoted m-term phrase queries (gen_synthetic_log.py:254-265 wraps sampled phrases in double
+    quotes). Terms are drawn from the high-df group so that phrases do occur in a synthetic corpus."""
+    g = groups["high"] or groups["low"]
+    out = []
+    for _ in range(n):
+        out.append('"' + " ".join(g[rng.randint(0, len(g) - 1)] for _ in range(m)) + '"')
+    return out
+
+
 def two_term(rng, groups, n):
     names = [g for g in ("low", "high") if groups[g]]
     queries, seen = [], set()
@@ -132,6 +142,10 @@ def generate(kind, groups, n, seed):
         return two_term_fixed(rng, groups, n, "low", "high")
     if kind == "two_term_ll":
         return two_term_fixed(rng, groups, n, "low", "low")
+    if kind == "phrase2":
+        return phrase_queries(rng, groups, n, 2)
+    if kind == "phrase3":
+        return phrase_queries(rng, groups, n, 3)
     if kind == "multi_term":
         return multi_term(rng, groups, n)
     if kind == "mix_aol":
@@ -144,7 +158,7 @@ def main():
     ap.add_argument("--terms", required=True, help="file with 'term df' per line")
     ap.add_argument("--kind", required=True,
                     choices=["single_low", "single_high", "two_term", "two_term_hh", "two_term_lh",
-                             "two_term_ll", "multi_term", "mix_aol"])
+                             "two_term_ll", "phrase2", "phrase3", "multi_term", "mix_aol"])
     ap.add_argument("--n", type=int, required=True)
     ap.add_argument("--high-df", type=int, default=10000)
     ap.add_argument("--seed", type=int, default=1)

@@ -14,9 +14,10 @@
 //   cumulative lengths), i.e. the Poissonised multinomial bag-of-words model. tf = tokens of
 //   the term in the doc; the stored doc length is the ACTUAL token count of the doc, and
 //   avg length is accumulated as the reference does (doc_length_store.h:102-112).
-// Only the doc-id and tf columns are written; the position/offset columns are empty (skip rows
-// carry zeros), so the directory serves non-phrase queries without snippets — exactly the
-// path under test. Deterministic for a given (seed, parameters), independent of thread count.
+// The doc-id and tf columns are always written; --positions 1 adds the position column (a
+// token's position is its slot inside the document), which phrase queries need. The offset
+// column is never written (skip rows carry zeros), so the directory serves queries without
+// snippets — exactly the path under test. Deterministic for a given (seed, parameters), independent of thread count.
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -74,6 +75,7 @@ struct Params {
   double zipf = 1.0, mu = 4.3, sigma = 0.6;
   uint32_t min_len = 5, max_len = 2000;
   int threads = 0;
+  bool positions = false;   // also write the position column (phrase queries)
 };
 
 inline int VarLen(uint64_t v) { int n = 1; while (v >= 128) { v >>= 7; n++; } return n; }
@@ -129,8 +131,9 @@ struct ListRec {        // what is needed to patch the first skip row once offse
   uint32_t term;
   uint32_t df;
   uint64_t rel_start;   // list start inside the chunk buffer
-  uint32_t patch_at;    // offset (from list start) of the two 7-byte absolute fields
+  uint32_t patch_at;    // offset (from list start) of the 7-byte absolute fields
   uint32_t docid0, tf0; // offsets (from list start) of the first doc-id / tf blob
+  uint32_t pos0;        // offset of the first position blob (0: no position column)
   uint32_t tf_end;      // offset (from list start) of the end of the tf column
 };
 
@@ -186,43 +189,68 @@ struct Gen {
     for (auto &a : actual_len) a.store(0, std::memory_order_relaxed);
   }
 
-  // Postings (doc ascending, tf) of one term.
+  // Postings (doc ascending, tf) of one term; with P.positions also the in-document positions
+  // of every posting, ascending and distinct, postings back to back.
   void TermPostings(uint64_t r, std::vector<uint32_t> *docs, std::vector<uint32_t> *tfs,
-                    std::vector<uint32_t> *scratch) {
+                    std::vector<uint64_t> *scratch, std::vector<uint32_t> *pos) {
     docs->clear();
     tfs->clear();
+    pos->clear();
     const double p = pow((double)(r + 1), -P.zipf) / H;
     const double expect = p * (double)T;
     Rng rng(Mix(P.seed, 0x7E4A00000000ull + r));
     const uint64_t N = P.docs;
     if (expect >= 0.5 * (double)N) {
       for (uint64_t d = 0; d < N; d++) {
-        const uint64_t tf = rng.Poisson(p * len_nominal[d]);
-        if (tf) { docs->push_back((uint32_t)d); tfs->push_back((uint32_t)tf); }
+        uint64_t tf = rng.Poisson(p * len_nominal[d]);
+        if (!tf) continue;
+        if (P.positions) {
+          // tf distinct positions inside the document (rejection; tf is far below the length)
+          const uint32_t L = len_nominal[d];
+          tf = std::min<uint64_t>(tf, L);
+          const size_t at = pos->size();
+          while (pos->size() - at < tf) {
+            const uint32_t x = (uint32_t)(((unsigned __int128)rng.Next() * L) >> 64);
+            bool dup = false;
+            for (size_t q = at; q < pos->size(); q++) dup = dup || (*pos)[q] == x;
+            if (!dup) pos->push_back(x);
+          }
+          std::sort(pos->begin() + at, pos->end());
+        }
+        docs->push_back((uint32_t)d);
+        tfs->push_back((uint32_t)tf);
       }
       return;
     }
     const uint64_t n = rng.Poisson(expect);
     if (!n) return;
     scratch->resize(n);
-    for (uint64_t i = 0; i < n; i++) {
-      // uniform slot in [0, T): 64x64 -> high 64 multiply
-      const uint64_t slot = (uint64_t)(((unsigned __int128)rng.Next() * T) >> 64);
-      (*scratch)[i] = DocOfSlot(slot);
-    }
+    for (uint64_t i = 0; i < n; i++)   // uniform slot in [0, T): 64x64 -> high 64 multiply
+      (*scratch)[i] = (uint64_t)(((unsigned __int128)rng.Next() * T) >> 64);
     std::sort(scratch->begin(), scratch->end());
-    for (uint64_t i = 0; i < n;) {
-      uint64_t j = i + 1;
-      while (j < n && (*scratch)[j] == (*scratch)[i]) j++;
-      docs->push_back((*scratch)[i]);
-      tfs->push_back((uint32_t)(j - i));
-      i = j;
+    uint64_t prev_slot = ~0ull;
+    uint32_t d = 0;
+    bool first = true;
+    for (uint64_t i = 0; i < n; i++) {
+      const uint64_t slot = (*scratch)[i];
+      if (P.positions && slot == prev_slot) continue;   // one token per slot: positions stay distinct
+      prev_slot = slot;
+      const uint32_t doc = first ? DocOfSlot(slot) : [&]() { uint32_t x = d; while (cum[x + 1] <= slot) x++; return x; }();
+      if (first || doc != d) {
+        docs->push_back(doc);
+        tfs->push_back(1);
+        d = doc;
+        first = false;
+      } else {
+        tfs->back()++;
+      }
+      if (P.positions) pos->push_back((uint32_t)(slot - cum[doc]));
     }
   }
 
   void EncodeList(uint64_t r, const std::vector<uint32_t> &docs, const std::vector<uint32_t> &tfs,
-                  Chunk *c, std::vector<uint32_t> *delta, std::vector<uint32_t> *rows_d,
-                  std::vector<uint32_t> *rows_t) {
+                  const std::vector<uint32_t> &pos, Chunk *c, std::vector<uint32_t> *delta,
+                  std::vector<uint32_t> *rows_d, std::vector<uint32_t> *rows_t) {
     const size_t df = docs.size();
     const size_t n_rows = (df + 127) / 128;
     std::vector<uint8_t> &b = c->buf;
@@ -246,6 +274,21 @@ struct Gen {
     EncodeColumn(delta->data(), df, &cols, 0, rows_d);
     const size_t tf_col = cols.size();
     EncodeColumn(tfs.data(), df, &cols, 0, rows_t);
+    const size_t pos_col = cols.size();
+    // position column: per bag deltas (first from 0), all bags concatenated, same cozy-box
+    // container; skip row r addresses the first position of posting 128*r as (blob, index)
+    std::vector<uint32_t> blobs_p, prow_off, prow_idx;
+    if (P.positions) {
+      std::vector<uint32_t> pd(pos.size());
+      size_t at = 0;
+      for (size_t i = 0; i < df; i++) {
+        if (i % 128 == 0) { prow_off.push_back((uint32_t)(at / 128)); prow_idx.push_back((uint32_t)(at % 128)); }
+        uint32_t prev_p = 0;
+        for (uint32_t j = 0; j < tfs[i]; j++, at++) { pd[at] = pos[at] - prev_p; prev_p = pos[at]; }
+      }
+      EncodeColumn(pd.data(), pd.size(), &cols, 0, &blobs_p);
+      for (auto &o : prow_off) o = blobs_p[o];     // blob index -> offset inside cols
+    }
     // skip list: 0xA3, n_rows, rows of 7 varints (flash_containers.h:250-299). Row 0's two
     // absolute blob offsets use fixed 7-byte varints patched after layout; later rows are
     // deltas vs the previous row and do not depend on the absolute position.
@@ -255,12 +298,13 @@ struct Gen {
     size_t data_at = 0;   // offset of the columns from list start, known once the skip list is sized
     {
       size_t sz = b.size() - start;
-      sz += 1 + 7 + 7 + 4;                   // row 0
+      sz += 1 + 7 + 7 + (P.positions ? 7 : 1) + 3;   // row 0
       for (size_t rr = 1; rr < n_rows; rr++) {
         sz += VarLen(docs[rr * 128 - 1] - (rr >= 2 ? docs[(rr - 1) * 128 - 1] : 0));
         sz += VarLen((*rows_d)[rr] - (*rows_d)[rr - 1]);
         sz += VarLen((*rows_t)[rr] - (*rows_t)[rr - 1]);
-        sz += 4;
+        if (P.positions) sz += VarLen(prow_off[rr] - prow_off[rr - 1]) + VarLen(prow_idx[rr]) + 2;
+        else sz += 4;
       }
       data_at = sz;
     }
@@ -268,30 +312,39 @@ struct Gen {
     b.push_back(0);                          // row 0: previous_doc_id = 0
     rec.patch_at = (uint32_t)(b.size() - start);
     b.insert(b.end(), 14, 0);                // docid blob abs offset, tf blob abs offset (patched)
-    b.insert(b.end(), 4, 0);                 // pos blob off, pos idx, offset blob off, offset idx
+    b.insert(b.end(), P.positions ? 7 : 1, 0);   // pos blob abs offset (patched) or 0 = no positions
+    b.insert(b.end(), 3, 0);                 // pos idx (0), offset blob off, offset idx
     for (size_t rr = 1; rr < n_rows; rr++) {
       PutVarint(&b, docs[rr * 128 - 1] - (rr >= 2 ? docs[(rr - 1) * 128 - 1] : 0));
       PutVarint(&b, (*rows_d)[rr] - (*rows_d)[rr - 1]);
       PutVarint(&b, (*rows_t)[rr] - (*rows_t)[rr - 1]);
-      b.insert(b.end(), 4, 0);
+      if (P.positions) {
+        PutVarint(&b, prow_off[rr] - prow_off[rr - 1]);
+        PutVarint(&b, prow_idx[rr]);
+        b.insert(b.end(), 2, 0);
+      } else {
+        b.insert(b.end(), 4, 0);
+      }
     }
     if (b.size() - start != data_at) { fprintf(stderr, "internal: skip list size\n"); abort(); }
     rec.docid0 = (uint32_t)data_at;
     rec.tf0 = (uint32_t)(data_at + tf_col);
-    rec.tf_end = (uint32_t)(data_at + cols.size());
+    rec.pos0 = P.positions ? (uint32_t)(data_at + pos_col) : 0u;
+    rec.tf_end = (uint32_t)(data_at + pos_col);
     b.insert(b.end(), cols.begin(), cols.end());
     c->lists.push_back(rec);
     c->postings += df;
   }
 
   void RunChunk(Chunk *c) {
-    std::vector<uint32_t> docs, tfs, scratch, delta, rd, rt;
+    std::vector<uint32_t> docs, tfs, pos, delta, rd, rt;
+    std::vector<uint64_t> scratch;
     for (uint64_t r = c->term_begin; r < c->term_end; r++) {
-      TermPostings(r, &docs, &tfs, &scratch);
+      TermPostings(r, &docs, &tfs, &scratch, &pos);
       if (docs.empty()) continue;
       for (size_t i = 0; i < docs.size(); i++)
         actual_len[docs[i]].fetch_add(tfs[i], std::memory_order_relaxed);
-      EncodeList(r, docs, tfs, c, &delta, &rd, &rt);
+      EncodeList(r, docs, tfs, pos, c, &delta, &rd, &rt);
     }
   }
 };
@@ -327,11 +380,12 @@ int main(int argc, char **argv) {
     else if (k == "--min-len") P.min_len = (uint32_t)atoi(v.c_str());
     else if (k == "--max-len") P.max_len = (uint32_t)atoi(v.c_str());
     else if (k == "--threads") P.threads = atoi(v.c_str());
+    else if (k == "--positions") P.positions = atoi(v.c_str()) != 0;
     else { fprintf(stderr, "unknown option %s\n", k.c_str()); return 2; }
   }
   if (P.out.empty() || P.docs == 0 || P.vocab == 0 || P.docs >= (1ull << 31)) {
     fprintf(stderr, "usage: wsr_gen_corpus --out DIR --docs N --vocab V [--zipf s] [--mu m] "
-                    "[--sigma s] [--min-len a] [--max-len b] [--seed x] [--threads t]\n");
+                    "[--sigma s] [--min-len a] [--max-len b] [--seed x] [--threads t] [--positions 0|1]\n");
     return 2;
   }
   if (P.max_len >= (1u << 19)) { fprintf(stderr, "max-len must stay below 2^19 (SURVEY §5.1)\n"); return 2; }
@@ -392,6 +446,7 @@ int main(int argc, char **argv) {
       uint8_t *p = c.buf.data() + l.rel_start + l.patch_at;
       PutVarint7(p, abs + l.docid0);
       PutVarint7(p + 7, abs + l.tf0);
+      if (l.pos0) PutVarint7(p + 14, abs + l.pos0);
       char name[32];
       const int len = snprintf(name, sizeof(name), "t%u", l.term);
       const uint32_t ulen = (uint32_t)len;

@@ -136,6 +136,7 @@ struct Chunk {               // output of one slice of terms
   std::vector<uint8_t> payload;
   std::vector<uint32_t> positions;   // optional position column, absolute in-document positions
   std::vector<uint32_t> blk_pos;     // per block: index of its first position
+  bool no_positions = false;         // some list of the chunk has no position column
   int64_t postings = 0, postings_global = 0;
   std::string err;
 };
@@ -198,7 +199,10 @@ struct Builder {
     // flash_engine_dumper.h:78-104; read side CozyBoxIterator, flash_iterators.h:280-425).
     std::vector<uint32_t> &pos_vals = pos_scratch;
     pos_vals.clear();
-    if (want_positions) {
+    // a column offset of 0 means the index was written without positions (wsr_gen_corpus
+    // without --positions): phrase queries are then refused at planning time
+    if (want_positions && pos_col_off == 0) c->no_positions = true;
+    if (want_positions && pos_col_off != 0) {
       uint64_t total = 0;
       for (uint64_t i = 0; i < df; i++) total += (*tfs)[i];
       pos_vals.resize(total);
@@ -229,7 +233,8 @@ struct Builder {
     uint64_t alg = 0;
     uint32_t base = doc_lo;  // shard 0: 0, as in the reference
     uint64_t pos_at = 0;     // index into pos_vals of posting s's first position
-    if (want_positions)
+    const bool keep_pos = want_positions && pos_col_off != 0;
+    if (keep_pos)
       for (size_t i = 0; i < a; i++) pos_at += (*tfs)[i];
     for (size_t s = a; s < b; s += kBlock) {
       const int n = (int)std::min<size_t>(kBlock, b - s);
@@ -274,7 +279,8 @@ struct Builder {
       PackTfRecords(tfr, nl, sh, &c->payload);
       c->blk_info.push_back(bi);
       c->blk_last.push_back(p);
-      if (want_positions) {
+      if (want_positions && !keep_pos) c->blk_pos.push_back(0u);
+      if (keep_pos) {
         if (c->positions.size() > 0xFFFFFFF0ull) { c->err = "more than 2^32 positions"; return false; }
         c->blk_pos.push_back((uint32_t)c->positions.size());
         uint64_t cnt = 0;
@@ -483,6 +489,7 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
     tot_payload += c.payload.size();
     tot_flt += c.filters.size();
     tot_pos += c.positions.size();
+    if (c.no_positions) ix.has_positions = false;
   }
   if (tot_pos >= 0xFFFFFFF0ull) { *err = "positions exceed 2^32 entries on one shard"; return false; }
   if (tot_flt >= 0xFFFFFFF0ull) { *err = "filters exceed 2^32 words"; return false; }
