@@ -235,7 +235,7 @@ struct Gen {
       const uint64_t slot = (*scratch)[i];
       if (P.positions && slot == prev_slot) continue;   // one token per slot: positions stay distinct
       prev_slot = slot;
-      const uint32_t doc = first ? DocOfSlot(slot) : [&]() { uint32_t x = d; while (cum[x + 1] <= slot) x++; return x; }();
+      const uint32_t doc = (!first && slot < cum[d + 1]) ? d : DocOfSlot(slot);
       if (first || doc != d) {
         docs->push_back(doc);
         tfs->push_back(1);
