@@ -324,8 +324,13 @@ def ours(a, rank, world, local_rank):
         dev_ms = float(t.item())
     ms_per_step = dev_ms / a.steps
 
+    # per-kernel durations: CUDA events around every launch group of the SAME (uncounted) kernels,
+    # averaged over a few passes; algorithmic bytes: one extra pass through the counting
+    # instantiations of the same kernels (identical work, bookkeeping on)
+    profs = [batch.profile() for _ in range(5)]
+    prof = [sum(p[i] for p in profs) / len(profs) for i in range(6)]
+    batch.count_work()
     st = batch.stats()
-    prof = batch.profile()
     listed = int(st.listed_postings)
     if world > 1:
         t = torch.tensor([listed, int(st.touched_bytes), int(st.decoded_postings)], device="cuda", dtype=torch.int64)

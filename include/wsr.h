@@ -184,7 +184,13 @@ int wsr_batch_time(wsr_batch *b, int iters, float *ms_per_iter);
  * ms[5] = whole pass. */
 int wsr_batch_profile(wsr_batch *b, float ms[6]);
 
-/* Counters of the LAST run of this batch (read back from the device). */
+/* One pass of the batch through the kernel instantiations that COUNT their work (decoded
+ * postings, touched algorithmic bytes, matches); same results as wsr_batch_run. The bookkeeping
+ * costs ~7 % of the two-term kernel, so ordinary runs are compiled without it. */
+int wsr_batch_count_work(wsr_batch *b);
+
+/* Counters of the LAST run of this batch (read back from the device). decoded_postings,
+ * touched_bytes and matches are 0 unless that run was wsr_batch_count_work. */
 typedef struct {
   uint64_t listed_postings;   /* sum over valid queries of sum_i df_i (shard-local lists) */
   uint64_t decoded_postings;  /* 128 x doc-id blocks actually decoded */

@@ -233,3 +233,27 @@ def test_search_log_pipeline_equals_batch(golden_dir):
     mask = np.arange(10)[None, :] < n1[:, None]
     assert np.array_equal(h1["doc_id"][mask], h2["doc_id"][mask])
     assert np.array_equal(h1["score"][mask].view(np.uint64), h2["score"][mask].view(np.uint64))
+
+
+def test_counting_pass_equals_plain_run(golden_dir):
+    """wsr_batch_count_work runs the counting instantiations of the kernels: same hits as
+    wsr_batch_run, and the work counters are filled (they stay 0 after a plain run)."""
+    from wiser_b200 import GpuVacuumEngine
+    from wiser_b200.engine import Batch
+    d = os.path.join(golden_dir, "zipf2k")
+    eng = GpuVacuumEngine(d).Load()
+    text = open(os.path.join(d, "queries.txt"), "rb").read()
+    b = Batch(eng, eng.parse_query_log(text, 10), 10)
+    b.run()
+    b.sync()
+    h1, n1 = b.fetch()
+    plain = b.stats()
+    assert plain.decoded_postings == 0 and plain.touched_bytes == 0 and plain.listed_postings > 0
+    b.count_work()
+    h2, n2 = b.fetch()
+    st = b.stats()
+    assert st.decoded_postings > 0 and st.touched_bytes > 0 and st.matches > 0
+    assert np.array_equal(n1, n2)
+    mask = np.arange(10)[None, :] < n1[:, None]
+    assert np.array_equal(h1["doc_id"][mask], h2["doc_id"][mask])
+    assert np.array_equal(h1["score"][mask].view(np.uint64), h2["score"][mask].view(np.uint64))

@@ -30,6 +30,7 @@ struct DevIndexView {
   uint32_t n_terms;
   uint32_t n_docs;
   uint32_t doc_lo;            // first doc id held by this shard (filter origin)
+  uint32_t n_filter_words;    // length of filters[] (bound for look-ahead prefetches)
 };
 
 // One planned query. unit_begin = index of its first work unit in its class queue.
@@ -77,8 +78,10 @@ struct BatchView {
 // class ids
 enum { kClassOne = 0, kClassTwo = 1, kClassMany = 2, kClassCollect = 3 };
 
+// count_work: instantiate the kernels with the work counters (decoded postings, touched bytes,
+// matches) switched on — the profiling pass; ordinary runs do not pay for the bookkeeping.
 void LaunchSearchClass(const DevIndexView &ix, const BatchView &b, int cls, int sm_count,
-                       cudaStream_t s);
+                       cudaStream_t s, bool count_work);
 void LaunchMerge(const BatchView &b, const uint32_t *multi_queries, uint32_t n_multi,
                  cudaStream_t s);
 void LaunchDecodeList(const DevIndexView &ix, uint32_t first_block, uint32_t n_blocks,

@@ -404,7 +404,7 @@ int UploadBatch(wsr_batch *b) {
 
 // Enqueues one pass of the batch on its stream: counters reset, search kernels per class,
 // unit merge, collect-mode epilogue. No host<->device copies.
-int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr) {
+int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr, bool count_work = false) {
   // ev (optional, 6 events): [0] start, [1] after class one, [2] two, [3] many, [4] collect,
   // [5] after merge + collect epilogue
   const size_t np = b->planned.size();
@@ -415,7 +415,7 @@ int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr) {
   if (b->n_collect) CU(cudaMemsetAsync(b->d_seg_count.p, 0, np * 4, b->stream));
   if (ev) CU(cudaEventRecord(ev[0], b->stream));
   for (int c = 0; c < 4; c++) {
-    LaunchSearchClass(b->idx->view, b->view, c, b->idx->sm_count, b->stream);
+    LaunchSearchClass(b->idx->view, b->view, c, b->idx->sm_count, b->stream, count_work);
     if (ev) CU(cudaEventRecord(ev[1 + c], b->stream));
     launches += b->class_units[c] ? 1 : 0;
   }
@@ -580,6 +580,7 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
   v.n_terms = (uint32_t)h.lists.size();
   v.n_docs = (uint32_t)h.n_docs;
   v.doc_lo = (uint32_t)h.doc_lo;
+  v.n_filter_words = (uint32_t)h.filters.size();
   v.positions = nullptr;
   v.blk_pos = nullptr;
   if (h.has_positions) {
@@ -848,6 +849,15 @@ int wsr_batch_profile(wsr_batch *b, float ms[6]) {
   for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
   CU(cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
   for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
+  return WSR_OK;
+}
+
+int wsr_batch_count_work(wsr_batch *b) {
+  if (!b) return Fail(WSR_ERR_ARG, "null argument");
+  CU(cudaSetDevice(b->idx->device));
+  int rc = EnqueueRun(b, nullptr, /*count_work=*/true);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(b->stream));
   return WSR_OK;
 }
 

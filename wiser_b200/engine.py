@@ -313,6 +313,10 @@ class Batch:
         check(lib().wsr_batch_profile(self._b, C.byref(ms)))
         return [float(x) for x in ms]
 
+    def count_work(self):
+        """One pass through the counting kernel instantiations; stats() then holds its counters."""
+        check(lib().wsr_batch_count_work(self._b))
+
     def stats(self) -> capi.BatchStats:
         s = capi.BatchStats()
         check(lib().wsr_batch_get_stats(self._b, C.byref(s)))
