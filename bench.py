@@ -383,11 +383,13 @@ def ours(a, rank, world, local_rank):
     if world == 1:
         hits_p = PinnedArray((n + 2, a.k), HIT_DTYPE)
         nh_p = PinnedArray((n + 2,), np.int32)
+        text_p = PinnedArray((len(text),), np.uint8)      # the step's input: the log text, pinned
+        text_p.array[:] = np.frombuffer(text, np.uint8)
 
         def e2e_step():
             nonlocal t_parse, t_search
             t0 = time.perf_counter()
-            h, c = eng.search_log(text, a.k, hits_p.array, nh_p.array)
+            h, c = eng.search_log(text_p.array, a.k, hits_p.array, nh_p.array)
             assert len(c) == n
             t_search += time.perf_counter() - t0
     else:
@@ -419,12 +421,20 @@ def ours(a, rank, world, local_rank):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": listed_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 64 + 4 * n),
+    if world == 1:
+        # the e2e path (device front end) must return exactly what the device-timed batch did
+        hb, nb = batch.fetch()
+        assert np.array_equal(nb, nh_p.array[:n]), "e2e path and timed batch disagree on hit counts"
+        m = np.arange(a.k)[None, :] < nb[:, None]
+        assert np.array_equal(hb["doc_id"][m], hits_p.array[:n]["doc_id"][m])
+        assert np.array_equal(hb["score"][m].view(np.uint64), hits_p.array[:n]["score"][m].view(np.uint64))
+    e2e = {"value": listed_all / e2e_s, "unit": UNIT,
+           "h2d_bytes_per_step": int(len(text)) if world == 1 else int(n * 64 + 4 * n),
            "d2h_bytes_per_step": int(n * a.k * 16 + n * 4), "ms_per_step": e2e_s * 1000.0,
            "queries_per_s": n / e2e_s,
            "parse_lookup_ms": 1000.0 * t_parse / e2e_steps, "search_ms": 1000.0 * t_search / e2e_steps,
-           "path": ("wsr_search_log: query-log text -> term lookup + planning (host threads) overlapped with "
-                    "H2D, kernels and D2H of the previous chunk; pinned host result buffers" if world == 1 else
+           "path": ("wsr_search_log: pinned query-log text -> H2D -> parse + term lookup + planning kernels "
+                    "(frontend.cu) -> search kernels -> D2H into pinned host result buffers" if world == 1 else
                     "query-log text -> wsr_parse_query_log -> wsr_batch_reset (plan + H2D) -> kernels -> "
                     "NCCL all-gather + merge kernel -> D2H of the merged top-k")}
 

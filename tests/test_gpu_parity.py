@@ -219,20 +219,42 @@ def test_generated_corpus_vs_oracle(tmp_path):
         check_full(fd, fs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], what=" ".join(q.terms))
 
 
-def test_search_log_pipeline_equals_batch(golden_dir):
-    """wsr_search_log (chunked, host/GPU overlapped) returns exactly what one wsr_search_batch does."""
+def _same_hits(h1, n1, h2, n2, k):
+    assert len(n2) == len(n1) and np.array_equal(n1, n2)
+    mask = np.arange(k)[None, :] < n1[:, None]
+    assert np.array_equal(h1["doc_id"][mask], h2["doc_id"][mask])
+    assert np.array_equal(h1["score"][mask].view(np.uint64), h2["score"][mask].view(np.uint64))
+
+
+def test_search_log_device_front_end_equals_host_planner(golden_dir):
+    """wsr_search_log parses, looks terms up and plans ON THE GPU (frontend.cu); it must return
+    exactly what the host parser + host planner + wsr_search_batch return, for every line shape
+    the reference's QueryProducerByLog accepts (query_pool.h:251-352)."""
     from wiser_b200 import GpuVacuumEngine
     d = os.path.join(golden_dir, "zipf2k")
     eng = GpuVacuumEngine(d).Load()
-    text = open(os.path.join(d, "queries.txt"), "rb").read()
-    text = b"\n".join(l for l in text.split(b"\n") if not l.startswith(b'"')) * 40   # > 64 KiB => several chunks
-    q = eng.parse_query_log(text, 10)
-    h1, n1, _, _ = eng.search_batch(q, 10)
-    h2, n2 = eng.search_log(text, 10)
-    assert len(n2) == len(n1) and np.array_equal(n1, n2)
-    mask = np.arange(10)[None, :] < n1[:, None]
-    assert np.array_equal(h1["doc_id"][mask], h2["doc_id"][mask])
-    assert np.array_equal(h1["score"][mask].view(np.uint64), h2["score"][mask].view(np.uint64))
+    base = open(os.path.join(d, "queries.txt"), "rb").read()
+    odd = b"\n".join([b"", b"   ", b"t0  t1", b" t0 t1 ", b'"t0 t1"', b'"', b'""', b'" t0"', b"nosuchterm t0",
+                      b"t0\r", b"\tt0 t3\t", b'"t1"', b"t1 t1", b'"t2 t2"', b"t0 t1 t2 t3 t4 t5 t6 t7"])
+    for text in (base * 12 + odd + b"\n",        # > 64 KiB, ends with a newline
+                 odd + b"\n" + base[:-1],        # last line without a newline
+                 b"t0", b"\n", b"\n\n t1 \n"):
+        for k in (10, 1, 32):
+            q = eng.parse_query_log(text, k)                       # host parser
+            h1, n1, _, _ = eng.search_batch(q, k)                  # host planner
+            h2, n2 = eng.search_log(text, k)                       # device front end
+            _same_hits(h1, n1, h2, n2, k)
+    # k > 32 goes through the host planner (collect class) and still matches
+    q = eng.parse_query_log(base, 40)
+    h1, n1, _, _ = eng.search_batch(q, 40)
+    h2, n2 = eng.search_log(base, 40)
+    _same_hits(h1, n1, h2, n2, 40)
+    # a line with more than 8 terms is refused by both front ends
+    bad = b"t0 t1\n" + b" ".join(b"t%d" % i for i in range(9)) + b"\n"
+    with pytest.raises(Exception):
+        eng.parse_query_log(bad, 10)
+    with pytest.raises(Exception):
+        eng.search_log(bad, 10)
 
 
 def test_counting_pass_equals_plain_run(golden_dir):

@@ -89,7 +89,7 @@ def lib():
     L.wsr_index_set_global_stats.argtypes = [vp, C.c_int64, C.c_int64, C.c_double, vp]
     L.wsr_index_local_stats.argtypes = [vp, vp, vp]
     L.wsr_batch_reset.argtypes = [vp, vp, C.c_int, C.c_int]
-    L.wsr_search_log.argtypes = [vp, cp, sz, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.wsr_search_log.argtypes = [vp, vp, sz, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.wsr_merge_topk_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     _lib = L
     return L

@@ -1,0 +1,195 @@
+// Device front end of the query-log path: the text of a query log goes to the GPU as it is and
+// comes out as the planned, class-sorted DevQuery array the search kernels consume.
+//
+//   reference                                                   here
+//   QueryProducerByLog: trim, phrase quotes, explode(' ')       ParsePlanKernel (one thread per line)
+//     (query_pool.h:251-352)
+//   TermTrieIndex::Find (term_index.h:136-144)                  DictFind: the host TermDict's table in HBM
+//   VacuumEngine::Search early outs (vacuum_engine.h:206-215)   ParsePlanKernel validity rules
+//   — (host PlanBatch in wsr_capi.cu)                           ParsePlanKernel + one scan + PlaceKernel
+//
+// The host planner (PlanBatch) stays the path for wsr_search_batch and for k > kMaxFastK; both
+// planners produce the same plan (tests/test_gpu_parity.py compares them).
+#include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
+
+#include "kernels.cuh"
+
+namespace wsr {
+namespace {
+
+constexpr uint32_t kEmptySlot = 0xffffffffu;
+
+__device__ __forceinline__ bool IsSpace(char c) {   // isspace() in the "C" locale
+  return c == ' ' || (c >= '\t' && c <= '\r');
+}
+
+// TermDict::Find (host_index.cc) on the device copy of the table.
+__device__ uint32_t DictFind(const DevDict &d, const char *s, uint32_t len) {
+  unsigned long long h = 0xcbf29ce484222325ull;
+  for (uint32_t i = 0; i < len; i++) { h ^= (unsigned char)s[i]; h *= 0x100000001b3ull; }
+  h ^= h >> 29;
+  const uint32_t tag = (uint32_t)(h >> 32);
+  uint32_t at = (uint32_t)h & d.mask;
+  for (;;) {
+    const uint2 slot = __ldg(&d.slots[at]);
+    if (slot.x == kEmptySlot) return WSR_TERM_ABSENT;
+    if (slot.y == tag) {
+      const uint32_t a = __ldg(&d.term_off[slot.x]), b = __ldg(&d.term_off[slot.x + 1]);
+      if (b - a == len) {
+        uint32_t i = 0;
+        while (i < len && __ldg(&d.arena[a + i]) == s[i]) i++;
+        if (i == len) return slot.x;
+      }
+    }
+    at = (at + 1) & d.mask;
+  }
+}
+
+// One thread per log line: parse -> term ids -> validity -> driver list, unit size, class.
+// tmp[i] is the query before placement (cand_begin holds its class, 255 = produces no work).
+__global__ void ParsePlanKernel(const char *__restrict__ text, uint32_t len,
+                                const uint32_t *__restrict__ nl, uint32_t n_nl, uint32_t n_lines,
+                                uint32_t k, const DevDict dict, const DevIndexView ix,
+                                DevQuery *__restrict__ tmp, PlanItem *__restrict__ item,
+                                uint32_t *__restrict__ err) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lines) return;
+  uint32_t a = i ? __ldg(&nl[i - 1]) + 1u : 0u;
+  uint32_t b = i < n_nl ? __ldg(&nl[i]) : len;
+  while (a < b && IsSpace(text[a])) a++;                 // utils::trim
+  while (b > a && IsSpace(text[b - 1])) b--;
+  uint32_t flags = 0;
+  if (b - a >= 1 && text[a] == '"' && text[b - 1] == '"') {   // QueryProducerByLog::IsPhrase
+    flags = 1;
+    a++;
+    if (b > a) b--;
+  }
+  DevQuery q;
+  memset(&q, 0, sizeof(q));
+  uint32_t n_terms = 0;
+  bool present = true, too_many = false;
+  for (uint32_t t = a; t < b;) {                          // utils::explode(line, ' ')
+    while (t < b && text[t] == ' ') t++;
+    uint32_t u = t;
+    while (u < b && text[u] != ' ') u++;
+    if (u > t) {
+      if (n_terms >= WSR_MAX_TERMS) { too_many = true; break; }
+      const uint32_t id = DictFind(dict, text + t, u - t);
+      present = present && id != WSR_TERM_ABSENT;
+      q.term[n_terms++] = id;
+    }
+    t = u;
+  }
+  PlanItem it;
+#pragma unroll
+  for (int j = 0; j < 8; j++) it.v[j] = 0;
+  uint32_t cls = 255;
+  if (too_many) atomicOr(err, 1u);
+  bool ok = !too_many && k > 0 && n_terms > 0 && present;   // vacuum_engine.h:206-215
+  uint32_t best = 0, best_df = 0xffffffffu;
+  unsigned long long all_blocks = 0;
+  if (ok) {
+    for (uint32_t t = 0; t < n_terms; t++) {
+      const uint4 li = __ldg(&ix.lists[q.term[t]]);
+      if (li.z == 0) ok = false;                           // nothing of this list on this shard
+      if (li.z < best_df) { best_df = li.z; best = t; }
+      all_blocks += li.y;
+    }
+  }
+  if (ok) {
+    const uint32_t drv_blocks = __ldg(&ix.lists[q.term[best]]).y;
+    const unsigned long long probe_blocks = all_blocks - drv_blocks;
+    // unit size: same rule as the host planner (PlanBatch)
+    const unsigned long long ratio = drv_blocks ? (probe_blocks + drv_blocks - 1) / drv_blocks : 0;
+    unsigned long long ub = 256ull / (1ull + ratio);
+    ub = ub < 1 ? 1 : ub > (unsigned long long)kUnitBlocks ? (unsigned long long)kUnitBlocks : ub;
+    q.n_terms = (uint8_t)n_terms;
+    q.flags = (flags && n_terms > 1) ? 1 : 0;              // a one-term "phrase" is a plain query
+    if (q.flags && ix.positions == nullptr) atomicOr(err, 2u);
+    q.unit_blocks = (uint16_t)ub;
+    q.k = k;
+    q.driver = best;
+    q.out_slot = i;
+    cls = n_terms == 1 ? kClassOne : n_terms == 2 ? kClassTwo : kClassMany;
+    q.n_units = cls == kClassOne ? 1u : (drv_blocks + (uint32_t)ub - 1u) / (uint32_t)ub;
+    it.v[cls] = 1;
+    it.v[3 + cls] = q.n_units;
+    if (q.n_units > 1) { it.v[6] = q.n_units; it.v[7] = 1; }
+  }
+  q.cand_begin = cls;
+  tmp[i] = q;
+  item[i] = it;
+}
+
+struct PlanAdd {
+  __device__ __forceinline__ PlanItem operator()(const PlanItem &x, const PlanItem &y) const {
+    PlanItem r;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r.v[j] = x.v[j] + y.v[j];
+    return r;
+  }
+};
+
+// Scatters tmp[] into the class-sorted plan (batch order kept within a class) and writes the
+// totals the host needs to size buffers and launch the search kernels.
+__global__ void PlaceKernel(const DevQuery *__restrict__ tmp, const PlanItem *__restrict__ item,
+                            const PlanItem *__restrict__ excl, uint32_t n_lines,
+                            DevQuery *__restrict__ planned, uint32_t *__restrict__ multi,
+                            PlanItem *__restrict__ totals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lines) return;
+  const PlanItem tot = PlanAdd()(excl[n_lines - 1], item[n_lines - 1]);
+  if (i == 0) *totals = tot;
+  DevQuery q = tmp[i];
+  const uint32_t cls = q.cand_begin;
+  if (cls == 255) return;
+  const PlanItem ex = excl[i];
+  uint32_t pos = ex.v[cls];
+  for (uint32_t c = 0; c < cls; c++) pos += tot.v[c];
+  q.unit_begin = ex.v[3 + cls];
+  q.cand_begin = 0;
+  if (q.n_units > 1) {
+    q.cand_begin = ex.v[6];
+    multi[ex.v[7]] = pos;
+  }
+  planned[pos] = q;
+}
+
+struct IsNewline {
+  const char *text;
+  __device__ __forceinline__ bool operator()(uint32_t i) const { return text[i] == '\n'; }
+};
+
+}  // namespace
+
+size_t FrontEndTempBytes(uint32_t len, uint32_t n_lines) {
+  size_t a = 0, b = 0;
+  thrust::counting_iterator<uint32_t> idx(0);
+  cub::DeviceSelect::If(nullptr, a, idx, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)len,
+                        IsNewline{nullptr});
+  cub::DeviceScan::ExclusiveScan(nullptr, b, (const PlanItem *)nullptr, (PlanItem *)nullptr,
+                                 PlanAdd(), PlanItem(), (int)n_lines);
+  return (a > b ? a : b) + 256;
+}
+
+void LaunchFrontEnd(const char *d_text, uint32_t len, uint32_t n_nl, uint32_t n_lines, uint32_t k,
+                    const DevDict &dict, const DevIndexView &ix, uint32_t *d_nl, uint32_t *d_n_nl,
+                    DevQuery *d_tmp, PlanItem *d_item, PlanItem *d_excl, DevQuery *d_planned,
+                    uint32_t *d_multi, PlanItem *d_totals, uint32_t *d_err, void *d_cub,
+                    size_t cub_bytes, cudaStream_t s) {
+  if (!n_lines) return;
+  // newline positions, ascending. Their number n_nl was counted by the host while the text was in
+  // flight (n_lines = n_nl, + 1 when the log does not end in '\n'), so no count is read back.
+  thrust::counting_iterator<uint32_t> idx(0);
+  size_t bytes = cub_bytes;
+  cub::DeviceSelect::If(d_cub, bytes, idx, d_nl, d_n_nl, (int)len, IsNewline{d_text}, s);
+  const uint32_t grid = (n_lines + 127) / 128;
+  ParsePlanKernel<<<grid, 128, 0, s>>>(d_text, len, d_nl, n_nl, n_lines, k, dict, ix, d_tmp, d_item,
+                                       d_err);
+  bytes = cub_bytes;
+  cub::DeviceScan::ExclusiveScan(d_cub, bytes, d_item, d_excl, PlanAdd(), PlanItem(), (int)n_lines, s);
+  PlaceKernel<<<grid, 128, 0, s>>>(d_tmp, d_item, d_excl, n_lines, d_planned, d_multi, d_totals);
+}
+
+}  // namespace wsr

@@ -117,8 +117,12 @@ class TermDict {
   // returns term id or 0xFFFFFFFF
   uint32_t Find(const char *s, size_t len) const;
   size_t Size() const { return offs_ ? offs_->size() - 1 : 0; }
- private:
+  // FNV-1a 64 with a final fold; slot = Hash & Mask(), linear probing. The device copy of the
+  // table (frontend.cu) uses the same function and probe order.
   static uint64_t Hash(const char *s, size_t len);
+  const std::vector<uint32_t> &Slots() const { return slots_; }
+  uint64_t Mask() const { return mask_; }
+ private:
   const std::vector<char> *arena_ = nullptr;
   const std::vector<uint64_t> *offs_ = nullptr;
   std::vector<uint32_t> slots_;

@@ -100,5 +100,29 @@ void LaunchCollectFinish(const BatchView &b, uint32_t n_collect, uint32_t n_entr
                          uint32_t *seg_begin, uint32_t *seg_end, int32_t *tmp_doc,
                          double *tmp_score, void *cub_tmp, size_t cub_tmp_bytes, cudaStream_t s);
 
+// ---- device front end of the query-log path (frontend.cu) -------------------------------------
+// The host TermDict's open-addressing table in HBM: slot = {term id (0xFFFFFFFF empty), upper 32
+// bits of the term's hash}; term bytes in arena[term_off[id] .. term_off[id + 1]).
+struct DevDict {
+  const uint2 *slots;
+  uint32_t mask;
+  const uint32_t *term_off;
+  const char *arena;
+};
+// Per-query plan contribution / running sums: v[0..2] queries per class (one, two, many),
+// v[3..5] work units per class, v[6] candidate-list units of multi-unit queries, v[7] their number.
+struct PlanItem {
+  uint32_t v[8];
+};
+size_t FrontEndTempBytes(uint32_t len, uint32_t n_lines);
+// Enqueues: newline positions -> parse + term lookup + per-query planning -> exclusive scan ->
+// class-sorted placement. d_totals receives the batch totals, d_err bit 0: a line with more than
+// WSR_MAX_TERMS terms, bit 1: a phrase query on an index without positions.
+void LaunchFrontEnd(const char *d_text, uint32_t len, uint32_t n_nl, uint32_t n_lines, uint32_t k,
+                    const DevDict &dict, const DevIndexView &ix, uint32_t *d_nl, uint32_t *d_n_nl,
+                    DevQuery *d_tmp, PlanItem *d_item, PlanItem *d_excl, DevQuery *d_planned,
+                    uint32_t *d_multi, PlanItem *d_totals, uint32_t *d_err, void *d_cub,
+                    size_t cub_bytes, cudaStream_t s);
+
 }  // namespace wsr
 #endif

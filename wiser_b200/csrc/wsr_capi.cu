@@ -168,6 +168,12 @@ struct wsr_index {
   DevBuf<uint32_t> d_filters;
   DevBuf<uint2> d_list_flt;
   DevBuf<uint32_t> d_positions, d_blk_pos;
+  // device copy of the term dictionary for the query-log front end (frontend.cu)
+  DevBuf<uint2> d_dict_slots;
+  DevBuf<uint32_t> d_term_off;
+  DevBuf<char> d_arena;
+  DevDict dict = {nullptr, 0, nullptr, nullptr};
+  bool dict_on_device = false;
   DevIndexView view;
   int64_t n_blocks = 0, payload_bytes = 0, hbm_bytes = 0;
   uint32_t doc_base = 0;          // global id of this partition's doc 0
@@ -188,6 +194,7 @@ struct wsr_batch {
   std::vector<uint32_t> multi;       // planned indices of multi-unit queries
   uint32_t class_begin[5] = {0, 0, 0, 0, 0};
   uint32_t class_units[4] = {0, 0, 0, 0};
+  uint32_t np = 0, n_multi = 0;      // planned queries / multi-unit queries (either planner)
   uint32_t n_cand_units = 0, n_seg_entries = 0, n_collect = 0;
   uint64_t listed_postings = 0, listed_bytes = 0;
   uint32_t launches = 0;
@@ -205,6 +212,14 @@ struct wsr_batch {
   DevBuf<uint32_t> d_seg_count, d_seg_begin, d_seg_end;
   DevBuf<uint8_t> d_cub_tmp;
   size_t cub_tmp_bytes = 0;
+  // device front end (wsr_search_log): log text, newline positions, unplaced queries, scan
+  DevBuf<char> d_text;
+  DevBuf<uint32_t> d_nl, d_fe_small;   // d_fe_small: [0] newline count (unused), [1] error bits
+  DevBuf<DevQuery> d_tmp;
+  DevBuf<PlanItem> d_item, d_excl, d_totals;
+  DevBuf<uint8_t> d_fe_cub;
+  PinnedBuf<char> h_text;
+  PinnedBuf<uint32_t> h_totals;        // PlanItem (8 words) + error bits
   // pinned staging for the host-buffer API
   PinnedBuf<DevQuery> h_queries;
   PinnedBuf<wsr_hit> h_hits;
@@ -348,22 +363,29 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
     }
   };
   ParallelFor(T, place);
+  b->np = pos;
+  b->n_multi = multi;
   b->n_cand_units = cand;
   b->n_seg_entries = (uint32_t)seg;
   b->n_collect = b->class_begin[4] - b->class_begin[kClassCollect];
   return WSR_OK;
 }
 
-int UploadBatch(wsr_batch *b) {
-  const size_t np = b->planned.size();
-  CU(b->d_queries.Ensure(np + 1));
+// Sizes the device buffers of a planned batch (b->n, np, n_multi, n_cand_units, ... are set) and
+// fills the kernel view. d_queries / d_multi are (re)allocated only when `plan_on_host`: the device
+// planner has already written them.
+int PrepareBatch(wsr_batch *b, bool plan_on_host) {
+  const size_t np = b->np;
+  if (plan_on_host) {
+    CU(b->d_queries.Ensure(np + 1));
+    CU(b->d_multi.Ensure((size_t)b->n_multi + 1));
+  }
   CU(b->d_hits.Ensure((size_t)b->n * b->k_stride + 1));
   CU(b->d_n_hits.Ensure((size_t)b->n + 1));
   CU(b->d_cand.Ensure((size_t)b->n_cand_units * kMaxFastK + 1));
   CU(b->d_cand_n.Ensure((size_t)b->n_cand_units + 1));
   CU(b->d_thr.Ensure(np + 1));
   CU(b->d_counters.Ensure(1));
-  CU(b->d_multi.Ensure(b->multi.size() + 1));
   if (b->n_collect) {
     CU(b->d_seg_doc.Ensure(b->n_seg_entries + 1));
     CU(b->d_seg_doc_tmp.Ensure(b->n_seg_entries + 1));
@@ -375,15 +397,6 @@ int UploadBatch(wsr_batch *b) {
     CU(b->d_cub_tmp.Ensure(b->cub_tmp_bytes + 16));
   }
   CU(b->d_seg_count.Ensure(np + 1));
-  CU(b->h_queries.Ensure(np + 1));
-  CU(b->h_multi.Ensure(b->multi.size() + 1));
-  if (np) memcpy(b->h_queries.p, b->planned.data(), np * sizeof(DevQuery));
-  if (!b->multi.empty()) memcpy(b->h_multi.p, b->multi.data(), b->multi.size() * 4);
-  if (np) CU(cudaMemcpyAsync(b->d_queries.p, b->h_queries.p, np * sizeof(DevQuery),
-                             cudaMemcpyHostToDevice, b->stream));
-  if (!b->multi.empty())
-    CU(cudaMemcpyAsync(b->d_multi.p, b->h_multi.p, b->multi.size() * 4, cudaMemcpyHostToDevice,
-                       b->stream));
   BatchView &v = b->view;
   v.queries = b->d_queries.p;
   for (int c = 0; c < 5; c++) v.class_begin[c] = b->class_begin[c];
@@ -402,16 +415,33 @@ int UploadBatch(wsr_batch *b) {
   return WSR_OK;
 }
 
+// Host-planned batch: buffers + H2D of the plan.
+int UploadBatch(wsr_batch *b) {
+  const size_t np = b->np;
+  int rc = PrepareBatch(b, /*plan_on_host=*/true);
+  if (rc) return rc;
+  CU(b->h_queries.Ensure(np + 1));
+  CU(b->h_multi.Ensure((size_t)b->n_multi + 1));
+  if (np) memcpy(b->h_queries.p, b->planned.data(), np * sizeof(DevQuery));
+  if (b->n_multi) memcpy(b->h_multi.p, b->multi.data(), (size_t)b->n_multi * 4);
+  if (np) CU(cudaMemcpyAsync(b->d_queries.p, b->h_queries.p, np * sizeof(DevQuery),
+                             cudaMemcpyHostToDevice, b->stream));
+  if (b->n_multi)
+    CU(cudaMemcpyAsync(b->d_multi.p, b->h_multi.p, (size_t)b->n_multi * 4, cudaMemcpyHostToDevice,
+                       b->stream));
+  return WSR_OK;
+}
+
 // Enqueues one pass of the batch on its stream: counters reset, search kernels per class,
 // unit merge, collect-mode epilogue. No host<->device copies.
 int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr, bool count_work = false) {
   // ev (optional, 6 events): [0] start, [1] after class one, [2] two, [3] many, [4] collect,
   // [5] after merge + collect epilogue
-  const size_t np = b->planned.size();
+  const size_t np = b->np;
   uint32_t launches = 0;
   CU(cudaMemsetAsync(b->d_n_hits.p, 0, (size_t)b->n * sizeof(int32_t) + 4, b->stream));
   CU(cudaMemsetAsync(b->d_counters.p, 0, sizeof(DevCounters), b->stream));
-  if (!b->multi.empty()) CU(cudaMemsetAsync(b->d_thr.p, 0, np * 8, b->stream));
+  if (b->n_multi) CU(cudaMemsetAsync(b->d_thr.p, 0, np * 8, b->stream));
   if (b->n_collect) CU(cudaMemsetAsync(b->d_seg_count.p, 0, np * 4, b->stream));
   if (ev) CU(cudaEventRecord(ev[0], b->stream));
   for (int c = 0; c < 4; c++) {
@@ -419,8 +449,8 @@ int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr, bool count_work = false)
     if (ev) CU(cudaEventRecord(ev[1 + c], b->stream));
     launches += b->class_units[c] ? 1 : 0;
   }
-  if (!b->multi.empty()) {
-    LaunchMerge(b->view, b->d_multi.p, (uint32_t)b->multi.size(), b->stream);
+  if (b->n_multi) {
+    LaunchMerge(b->view, b->d_multi.p, b->n_multi, b->stream);
     launches++;
   }
   if (b->n_collect) {
@@ -594,6 +624,38 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
     ix->hbm_bytes += (int64_t)h.positions.size() * 4 + (int64_t)h.blk_pos.size() * 4;
     std::vector<uint32_t>().swap(h.positions);
     std::vector<uint32_t>().swap(h.blk_pos);
+  }
+  // term dictionary in HBM for the query-log front end: the host table's slots with a 32-bit tag
+  // (so most probes never touch the term bytes), 32-bit term offsets, the term arena
+  if (h.term_arena.size() < 0xfffffff0ull && h.dict.Mask() < 0xffffffffull && !h.lists.empty()) {
+    const std::vector<uint32_t> &slots = h.dict.Slots();
+    std::vector<uint2> ds(slots.size());
+    const int T = HostThreads(slots.size(), 1 << 16);
+    ParallelFor(T, [&](int t, int TT) {
+      const size_t lo = slots.size() * t / TT, hi = slots.size() * (t + 1) / TT;
+      for (size_t i = lo; i < hi; i++) {
+        const uint32_t id = slots[i];
+        uint32_t tag = 0;
+        if (id != 0xFFFFFFFFu)
+          tag = (uint32_t)(TermDict::Hash(h.term_arena.data() + h.term_off[id],
+                                          h.term_off[id + 1] - h.term_off[id]) >> 32);
+        ds[i] = make_uint2(id, tag);
+      }
+    });
+    std::vector<uint32_t> off32(h.term_off.begin(), h.term_off.end());
+    if (!cu(ix->d_dict_slots.Ensure(ds.size()), "cudaMalloc dict") ||
+        !cu(ix->d_term_off.Ensure(off32.size()), "cudaMalloc term_off") ||
+        !cu(ix->d_arena.Ensure(h.term_arena.size() + 1), "cudaMalloc term arena") ||
+        !cu(cudaMemcpy(ix->d_dict_slots.p, ds.data(), ds.size() * 8, cudaMemcpyHostToDevice), "H2D dict") ||
+        !cu(cudaMemcpy(ix->d_term_off.p, off32.data(), off32.size() * 4, cudaMemcpyHostToDevice), "H2D term_off") ||
+        !cu(cudaMemcpy(ix->d_arena.p, h.term_arena.data(), h.term_arena.size(), cudaMemcpyHostToDevice), "H2D arena"))
+      return fail(e);
+    ix->dict.slots = ix->d_dict_slots.p;
+    ix->dict.mask = (uint32_t)h.dict.Mask();
+    ix->dict.term_off = ix->d_term_off.p;
+    ix->dict.arena = ix->d_arena.p;
+    ix->dict_on_device = true;
+    ix->hbm_bytes += (int64_t)ds.size() * 8 + (int64_t)off32.size() * 4 + (int64_t)h.term_arena.size();
   }
   // the block arrays now live in HBM only
   std::vector<uint8_t>().swap(h.payload);
@@ -987,11 +1049,119 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
   return rc;
 }
 
+namespace {
+
+// wsr_search_log with the front end on the GPU: the log text is the only input that crosses
+// PCIe; parsing, term lookup and planning run as kernels (frontend.cu), the host reads back 36
+// bytes of totals to size the candidate buffers and launch the class kernels.
+int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
+                      int32_t *n_hits, int cap_q, int *n_queries) {
+  wsr_batch *b = AcquirePooled(idx);
+  if (!b) return Fail(WSR_ERR_CUDA, "cannot create batch");
+  struct Release {
+    wsr_index *i; wsr_batch *b;
+    ~Release() { cudaStreamSynchronize(b->stream); ReleasePooled(i, b); }
+  } release{idx, b};
+  // text -> device (staged through pinned memory unless the caller's buffer already is)
+  CU(b->d_text.Ensure(len + 1));
+  const char *src = text;
+  if (!IsPinned(text)) {
+    CU(b->h_text.Ensure(len + 1));
+    memcpy(b->h_text.p, text, len);
+    src = b->h_text.p;
+  }
+  CU(cudaMemcpyAsync(b->d_text.p, src, len, cudaMemcpyHostToDevice, b->stream));
+  // line count on the host while the copy is in flight (QueryLogReader semantics: every '\n'
+  // ends a line; a last line without one still counts)
+  size_t n_nl = 0;
+  {
+    const int T = HostThreads(len, 1 << 18);
+    std::vector<size_t> cnt(T, 0);
+    ParallelFor(T, [&](int t, int TT) {
+      const char *p = text + len * t / TT, *e = text + len * (t + 1) / TT;
+      size_t c = 0;
+      while (p < e && (p = (const char *)memchr(p, '\n', e - p)) != nullptr) { c++; p++; }
+      cnt[t] = c;
+    });
+    for (size_t c : cnt) n_nl += c;
+  }
+  const size_t n_lines = n_nl + (text[len - 1] != '\n' ? 1 : 0);
+  if (n_lines > (size_t)cap_q) return Fail(WSR_ERR_ARG, "result buffers too small");
+  const uint32_t n = (uint32_t)n_lines;
+  CU(b->d_nl.Ensure(n_nl + 1));
+  CU(b->d_fe_small.Ensure(2));
+  CU(b->d_tmp.Ensure(n));
+  CU(b->d_item.Ensure(n));
+  CU(b->d_excl.Ensure(n));
+  CU(b->d_totals.Ensure(1));
+  CU(b->d_queries.Ensure((size_t)n + 1));
+  CU(b->d_multi.Ensure((size_t)n + 1));
+  CU(b->h_totals.Ensure(9));
+  const size_t cub_bytes = FrontEndTempBytes((uint32_t)len, n);
+  CU(b->d_fe_cub.Ensure(cub_bytes));
+  CU(cudaMemsetAsync(b->d_fe_small.p, 0, 8, b->stream));
+  LaunchFrontEnd(b->d_text.p, (uint32_t)len, (uint32_t)n_nl, n, (uint32_t)k, idx->dict, idx->view,
+                 b->d_nl.p, b->d_fe_small.p, b->d_tmp.p, b->d_item.p, b->d_excl.p, b->d_queries.p,
+                 b->d_multi.p, b->d_totals.p, b->d_fe_small.p + 1, b->d_fe_cub.p, cub_bytes, b->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(b->h_totals.p, b->d_totals.p, 32, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaMemcpyAsync(b->h_totals.p + 8, b->d_fe_small.p + 1, 4, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  const uint32_t *tot = b->h_totals.p;
+  if (tot[8] & 1u) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
+  if (tot[8] & 2u)
+    return Fail(WSR_ERR_UNSUPPORTED, "phrase query on an index opened without WSR_OPEN_POSITIONS");
+  b->n = (int)n;
+  b->k_stride = k;
+  b->planned.clear();
+  b->multi.clear();
+  uint32_t pos = 0;
+  for (int c = 0; c < 3; c++) {
+    b->class_begin[c] = pos;
+    pos += tot[c];
+    b->class_units[c] = tot[3 + c];
+  }
+  b->class_begin[3] = b->class_begin[4] = pos;
+  b->class_units[3] = 0;
+  b->np = pos;
+  b->n_multi = tot[7];
+  b->n_cand_units = tot[6];
+  b->n_seg_entries = b->n_collect = 0;
+  b->listed_postings = b->listed_bytes = 0;   // not tallied by the device planner
+  int rc = PrepareBatch(b, /*plan_on_host=*/false);
+  if (rc == WSR_OK) rc = EnqueueRun(b);
+  if (rc) return rc;
+  const size_t nh = (size_t)n * k;
+  const bool pinned = IsPinned(hits) && IsPinned(n_hits);
+  if (pinned) {
+    CU(cudaMemcpyAsync(hits, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(n_hits, b->d_n_hits.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+  } else {
+    CU(b->h_hits.Ensure(nh + 1));
+    CU(b->h_n_hits.Ensure((size_t)n + 1));
+    CU(cudaMemcpyAsync(b->h_hits.p, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(b->h_n_hits.p, b->d_n_hits.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    memcpy(hits, b->h_hits.p, nh * sizeof(wsr_hit));
+    memcpy(n_hits, b->h_n_hits.p, (size_t)n * 4);
+  }
+  *n_queries = (int)n;
+  return WSR_OK;
+}
+
+}  // namespace
+
 int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
                    int32_t *n_hits, int cap_q, int *n_queries) {
   if (!idx || (!text && len) || k < 1 || !hits || !n_hits || !n_queries || cap_q < 0)
     return Fail(WSR_ERR_ARG, "bad argument");
   CU(cudaSetDevice(idx->device));
+  // k <= kMaxFastK (no collect class) and a dictionary in HBM: parse and plan on the GPU.
+  // WSR_HOST_FRONTEND=1 forces the host parser/planner (the same one wsr_search_batch uses).
+  static const bool host_frontend = getenv("WSR_HOST_FRONTEND") && atoi(getenv("WSR_HOST_FRONTEND")) != 0;
+  if (!host_frontend && idx->dict_on_device && k <= kMaxFastK && len > 0 && len < 0xfffffff0ull)
+    return SearchLogOnDevice(idx, text, len, k, hits, n_hits, cap_q, n_queries);
   // chunk boundaries on line starts: up to 4 chunks of at least 128 KiB of text each
   const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(4, len >> 17));
   std::vector<size_t> cut(n_chunks + 1, len);

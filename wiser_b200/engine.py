@@ -190,13 +190,18 @@ class GpuVacuumEngine:
     def search_log(self, text: bytes, k: int, hits=None, n_hits=None):
         """wsr_search_log: whole query-log text -> (hits[n,k], n_hits[n]); parse, GPU and copies
         pipelined inside the library."""
-        cap = text.count(b"\n") + 2
+        if isinstance(text, np.ndarray):       # e.g. a pinned uint8 buffer holding the log
+            ptr, length = C.c_void_p(text.ctypes.data), int(text.size)
+            cap = len(n_hits) if n_hits is not None else int(np.count_nonzero(text == 10)) + 2
+        else:
+            ptr, length = C.cast(C.c_char_p(text), C.c_void_p), len(text)
+            cap = text.count(b"\n") + 2
         if hits is None:
             hits = np.zeros((cap, k), HIT_DTYPE)
         if n_hits is None:
             n_hits = np.zeros(cap, np.int32)
         n = C.c_int(0)
-        check(lib().wsr_search_log(self._h, text, len(text), k, hits.ctypes.data, n_hits.ctypes.data,
+        check(lib().wsr_search_log(self._h, ptr, length, k, hits.ctypes.data, n_hits.ctypes.data,
                                    min(cap, len(n_hits)), C.byref(n)))
         return hits[:n.value], n_hits[:n.value]
 
