@@ -168,6 +168,10 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
 wsr_batch *wsr_batch_create(wsr_index *idx, const wsr_query *queries, int n, int k_stride);
 /* Re-plans and re-uploads an existing batch object with a new set of queries (buffers reused). */
 int wsr_batch_reset(wsr_batch *b, const wsr_query *queries, int n, int k_stride);
+/* Same from query-log text (the wsr_search_log front end: for k <= 32 the text is copied to the
+ * GPU and parsed, looked up and planned there). *n_queries receives the number of log lines;
+ * the batch's k_stride becomes k. */
+int wsr_batch_reset_log(wsr_batch *b, const char *text, size_t len, int k, int *n_queries);
 void wsr_batch_destroy(wsr_batch *b);
 int wsr_batch_run(wsr_batch *b);                       /* asynchronous on the batch stream */
 int wsr_batch_sync(wsr_batch *b);

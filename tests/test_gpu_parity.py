@@ -244,6 +244,15 @@ def test_search_log_device_front_end_equals_host_planner(golden_dir):
             h1, n1, _, _ = eng.search_batch(q, k)                  # host planner
             h2, n2 = eng.search_log(text, k)                       # device front end
             _same_hits(h1, n1, h2, n2, k)
+    # the same front end behind the device-resident batch API (multi-GPU path)
+    from wiser_b200.engine import Batch
+    q = eng.parse_query_log(base, 10)
+    h1, n1, _, _ = eng.search_batch(q, 10)
+    b = Batch(eng, q[:1], 10)
+    assert b.reset_log(base, 10) == len(q)
+    b.run()
+    h2, n2 = b.fetch()
+    _same_hits(h1, n1, h2, n2, 10)
     # k > 32 goes through the host planner (collect class) and still matches
     q = eng.parse_query_log(base, 40)
     h1, n1, _, _ = eng.search_batch(q, 40)

@@ -40,7 +40,7 @@ EXPORTS = [
     "wsr_index_close", "wsr_index_get_info", "wsr_term_lookup", "wsr_term_at", "wsr_decode_list",
     "wsr_decode_all", "wsr_search", "wsr_search_batch", "wsr_batch_create", "wsr_batch_destroy",
     "wsr_batch_run", "wsr_batch_sync", "wsr_batch_fetch", "wsr_batch_device_results",
-    "wsr_batch_time", "wsr_batch_get_stats", "wsr_merge_topk_device", "wsr_batch_profile", "wsr_batch_count_work",
+    "wsr_batch_time", "wsr_batch_get_stats", "wsr_merge_topk_device", "wsr_batch_profile", "wsr_batch_count_work", "wsr_batch_reset_log",
     "wsr_parse_query_log", "wsr_index_set_global_stats", "wsr_index_local_stats", "wsr_batch_reset", "wsr_search_log",
 ]
 
@@ -85,6 +85,7 @@ def lib():
     L.wsr_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.wsr_batch_profile.argtypes = [vp, C.POINTER(C.c_float * 6)]
     L.wsr_batch_count_work.argtypes = [vp]
+    L.wsr_batch_reset_log.argtypes = [vp, vp, sz, C.c_int, C.POINTER(C.c_int)]
     L.wsr_parse_query_log.argtypes = [vp, cp, sz, C.c_int, vp, C.c_int, C.POINTER(C.c_int)]
     L.wsr_index_set_global_stats.argtypes = [vp, C.c_int64, C.c_int64, C.c_double, vp]
     L.wsr_index_local_stats.argtypes = [vp, vp, vp]

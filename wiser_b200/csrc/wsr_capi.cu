@@ -815,6 +815,11 @@ int wsr_decode_all(wsr_index *idx, uint64_t *checksum, float *kernel_ms) {
   return WSR_OK;
 }
 
+namespace {
+bool DeviceFrontEndUsable(const wsr_index *idx, size_t len, int k);
+int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q);
+}  // namespace
+
 wsr_batch *wsr_batch_create(wsr_index *idx, const wsr_query *queries, int n, int k_stride) {
   if (!idx || (!queries && n > 0) || n < 0 || k_stride < 1) {
     Fail(WSR_ERR_ARG, "bad argument");
@@ -835,6 +840,25 @@ int wsr_batch_reset(wsr_batch *b, const wsr_query *queries, int n, int k_stride)
   CU(cudaSetDevice(b->idx->device));
   int rc = PlanBatch(b, queries, n, k_stride);
   if (rc == WSR_OK) rc = UploadBatch(b);
+  return rc;
+}
+
+int wsr_batch_reset_log(wsr_batch *b, const char *text, size_t len, int k, int *n_queries) {
+  if (!b || (!text && len) || k < 1 || !n_queries) return Fail(WSR_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(b->idx->device));
+  if (DeviceFrontEndUsable(b->idx, len, k)) {
+    const int rc = PlanLogOnDevice(b, text, len, k, 0x7fffffff);
+    if (rc == WSR_OK) *n_queries = b->n;
+    return rc;
+  }
+  size_t lines = 1;
+  for (size_t i = 0; i < len; i++) lines += text[i] == '\n';
+  std::vector<wsr_query> qs(lines + 1);
+  int n = 0;
+  int rc = wsr_parse_query_log(b->idx, text, len, k, qs.data(), (int)qs.size(), &n);
+  if (rc == WSR_OK) rc = PlanBatch(b, qs.data(), n, k);
+  if (rc == WSR_OK) rc = UploadBatch(b);
+  if (rc == WSR_OK) *n_queries = n;
   return rc;
 }
 
@@ -1054,14 +1078,10 @@ namespace {
 // wsr_search_log with the front end on the GPU: the log text is the only input that crosses
 // PCIe; parsing, term lookup and planning run as kernels (frontend.cu), the host reads back 36
 // bytes of totals to size the candidate buffers and launch the class kernels.
-int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
-                      int32_t *n_hits, int cap_q, int *n_queries) {
-  wsr_batch *b = AcquirePooled(idx);
-  if (!b) return Fail(WSR_ERR_CUDA, "cannot create batch");
-  struct Release {
-    wsr_index *i; wsr_batch *b;
-    ~Release() { cudaStreamSynchronize(b->stream); ReleasePooled(i, b); }
-  } release{idx, b};
+// Plans batch b from log text on the GPU (text H2D, frontend.cu kernels, 36 bytes of totals back)
+// and prepares its buffers; the batch is then ready for EnqueueRun.
+int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q) {
+  wsr_index *idx = b->idx;
   // text -> device (staged through pinned memory unless the caller's buffer already is)
   CU(b->d_text.Ensure(len + 1));
   const char *src = text;
@@ -1128,7 +1148,24 @@ int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_h
   b->n_cand_units = tot[6];
   b->n_seg_entries = b->n_collect = 0;
   b->listed_postings = b->listed_bytes = 0;   // not tallied by the device planner
-  int rc = PrepareBatch(b, /*plan_on_host=*/false);
+  return PrepareBatch(b, /*plan_on_host=*/false);
+}
+
+bool DeviceFrontEndUsable(const wsr_index *idx, size_t len, int k) {
+  static const bool host_frontend = getenv("WSR_HOST_FRONTEND") && atoi(getenv("WSR_HOST_FRONTEND")) != 0;
+  return !host_frontend && idx->dict_on_device && k <= kMaxFastK && len > 0 && len < 0xfffffff0ull;
+}
+
+int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
+                      int32_t *n_hits, int cap_q, int *n_queries) {
+  wsr_batch *b = AcquirePooled(idx);
+  if (!b) return Fail(WSR_ERR_CUDA, "cannot create batch");
+  struct Release {
+    wsr_index *i; wsr_batch *b;
+    ~Release() { cudaStreamSynchronize(b->stream); ReleasePooled(i, b); }
+  } release{idx, b};
+  int rc = PlanLogOnDevice(b, text, len, k, cap_q);
+  const uint32_t n = (uint32_t)b->n;
   if (rc == WSR_OK) rc = EnqueueRun(b);
   if (rc) return rc;
   const size_t nh = (size_t)n * k;
@@ -1159,8 +1196,7 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
   CU(cudaSetDevice(idx->device));
   // k <= kMaxFastK (no collect class) and a dictionary in HBM: parse and plan on the GPU.
   // WSR_HOST_FRONTEND=1 forces the host parser/planner (the same one wsr_search_batch uses).
-  static const bool host_frontend = getenv("WSR_HOST_FRONTEND") && atoi(getenv("WSR_HOST_FRONTEND")) != 0;
-  if (!host_frontend && idx->dict_on_device && k <= kMaxFastK && len > 0 && len < 0xfffffff0ull)
+  if (DeviceFrontEndUsable(idx, len, k))
     return SearchLogOnDevice(idx, text, len, k, hits, n_hits, cap_q, n_queries);
   // chunk boundaries on line starts: up to 4 chunks of at least 128 KiB of text each
   const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(4, len >> 17));

@@ -294,6 +294,18 @@ class Batch:
         self.n, self.k_stride = len(qarr), k_stride
         check(lib().wsr_batch_reset(self._b, qarr.ctypes.data, self.n, k_stride))
 
+    def reset_log(self, text, k: int) -> int:
+        """wsr_batch_reset_log: re-plan this batch from query-log text (bytes or a pinned uint8
+        array); parse, term lookup and planning run on the GPU. Returns the number of queries."""
+        if isinstance(text, np.ndarray):
+            ptr, length = C.c_void_p(text.ctypes.data), int(text.size)
+        else:
+            ptr, length = C.cast(C.c_char_p(text), C.c_void_p), len(text)
+        n = C.c_int(0)
+        check(lib().wsr_batch_reset_log(self._b, ptr, length, k, C.byref(n)))
+        self.n, self.k_stride = n.value, k
+        return n.value
+
     def run(self):
         check(lib().wsr_batch_run(self._b))
 
