@@ -47,7 +47,7 @@ def log(*a):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--docs", type=int, default=5_000_000, help="documents PER GPU (weak scaling)")
@@ -117,15 +117,48 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region: an NVML polling
+    thread (2 ms period, starts instantly — the timed region of the default run is < 100 ms);
+    falls back to an `nvidia-smi -lms` child when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, False
+        self.sm, self.reason_bits, self.mx = [], 0, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(get_reasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "100"],
@@ -139,6 +172,16 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            # NVML clocks-event reason bits (nvml.h): 0x8 hw_slowdown, 0x40 hw_thermal_slowdown,
+            # 0x20 sw_thermal_slowdown, 0x4 sw_power_cap
+            names = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                     (0x4, "sw_power_cap")]
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(n for bit, n in names if self.reason_bits & bit),
+                    "samples": len(self.sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -154,7 +197,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------
