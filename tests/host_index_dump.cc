@@ -66,6 +66,13 @@ int main(int argc, char **argv) {
         fwrite(rec, 4, 2, out);
       }
       if (docs[n - 1] != ix.blk_last[li.first_block + b]) { fprintf(stderr, "blk_last mismatch\n"); return 3; }
+      {
+        const BlockShape sh = UnpackShape(bi.bits);
+        for (int t = 0; t < 8; t++) {
+          const uint16_t want = sh.w0 <= 16 && 16 * t < n ? (uint16_t)(docs[16 * t] - bi.base_doc) : (uint16_t)0xFFFF;
+          if (ix.blk_heads[(size_t)(li.first_block + b) * 8 + t] != want) { fprintf(stderr, "blk_heads mismatch\n"); return 5; }
+        }
+      }
       total += n;
     }
     if (total != li.df_shard) { fprintf(stderr, "df mismatch\n"); return 4; }

@@ -102,7 +102,7 @@ __global__ void ParsePlanKernel(const char *__restrict__ text, uint32_t len,
     const unsigned long long probe_blocks = all_blocks - drv_blocks;
     // unit size: same rule as the host planner (PlanBatch)
     const unsigned long long ratio = drv_blocks ? (probe_blocks + drv_blocks - 1) / drv_blocks : 0;
-    unsigned long long ub = 256ull / (1ull + ratio);
+    unsigned long long ub = (unsigned long long)kUnitBudget / (1ull + ratio);
     ub = ub < 1 ? 1 : ub > (unsigned long long)kUnitBlocks ? (unsigned long long)kUnitBlocks : ub;
     q.n_terms = (uint8_t)n_terms;
     q.flags = (flags && n_terms > 1) ? 1 : 0;              // a one-term "phrase" is a plain query

@@ -133,6 +133,7 @@ struct Chunk {               // output of one slice of terms
   std::vector<uint64_t> list_alg_bytes;
   std::vector<BlockInfo> blk_info;
   std::vector<uint32_t> blk_last;
+  std::vector<uint16_t> blk_heads;   // 8 per block
   std::vector<uint8_t> payload;
   std::vector<uint32_t> positions;   // optional position column, absolute in-document positions
   std::vector<uint32_t> blk_pos;     // per block: index of its first position
@@ -279,6 +280,9 @@ struct Builder {
       PackTfRecords(tfr, nl, sh, &c->payload);
       c->blk_info.push_back(bi);
       c->blk_last.push_back(p);
+      // group heads: first doc (relative to base) of records 0, 4, .., 28 when they fit 16 bits
+      for (int t = 0; t < 8; t++)
+        c->blk_heads.push_back(sh.w0 <= 16 && 4 * t < nl ? (uint16_t)first[4 * t] : (uint16_t)0xFFFF);
       if (want_positions && !keep_pos) c->blk_pos.push_back(0u);
       if (keep_pos) {
         if (c->positions.size() > 0xFFFFFFF0ull) { c->err = "more than 2^32 positions"; return false; }
@@ -501,6 +505,7 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
   ix.list_alg_bytes.resize(n_terms);
   ix.blk_info.resize(tot_blocks);
   ix.blk_last.resize(tot_blocks);
+  ix.blk_heads.resize(tot_blocks * 8 + 8);
   ix.payload.assign(tot_payload + 1024, 0);  // tail pad: prefetchers read up to 512 B past a block
   ix.filters.assign(tot_flt + 1, 0u);
   ix.list_flt.resize(n_terms);
@@ -555,6 +560,9 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
       }
       if (!c.blk_last.empty())
         memcpy(ix.blk_last.data() + b0, c.blk_last.data(), c.blk_last.size() * 4);
+      if (!c.blk_heads.empty())
+        memcpy(ix.blk_heads.data() + b0 * 8, c.blk_heads.data(), c.blk_heads.size() * 2);
+      std::vector<uint16_t>().swap(c.blk_heads);
       if (!c.payload.empty()) memcpy(ix.payload.data() + pay_base[i], c.payload.data(), c.payload.size());
       Chunk().payload.swap(c.payload);
     }

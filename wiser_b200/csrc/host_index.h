@@ -24,6 +24,10 @@
 //                       the algorithmic bytes of the roofline; max_tfn = upper bound of
 //                       tf*(k1+1)/(tf+cache[norm]) over the block (block-max metadata).
 //   blk_last  u32[]     last doc id of each block (searched when skipping)
+//   blk_heads u16[8][]  per block the first doc (minus base_doc) of records 0, 4, .., 28 (0xFFFF past
+//                       the block's records, and for every entry when w0 > 16): an exact probe
+//                       picks its 4-record group with this ONE 16-byte load instead of seven
+//                       loads strided over the whole record stream (8 sectors -> 1)
 //   blk_max   f32[]     copy of max_tfn as its own array: single-term queries scan it coalesced
 //                       to bound the k-th score before touching any payload
 //   lists     uint4[]   per term {first_block, n_blocks, df_shard, df_global}
@@ -143,6 +147,7 @@ struct HostIndex {
   // blocks of this shard
   std::vector<BlockInfo> blk_info;
   std::vector<uint32_t> blk_last;
+  std::vector<uint16_t> blk_heads;  // 8 per block (see layout comment)
   std::vector<uint8_t> payload;
   std::vector<uint32_t> filters;
   std::vector<uint64_t> list_flt;     // low 32: first word, high 32: shift (0xFFFFFFFF none)

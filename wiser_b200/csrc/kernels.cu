@@ -230,7 +230,7 @@ struct CandRec {
   uint32_t pos_a;
 };
 struct __align__(16) ProbeScratch {
-  uint32_t win[32];              // the probe list's blk_last window, for per-lane block lookup
+  uint32_t win[128];             // the probe list's blk_last window, for per-lane block lookup
   CandRec cand[kHitCap];         // filter survivors awaiting the exact probe (doc ascending)
   HitRec hits[kHitCap];          // intersection hits awaiting scoring
 };
@@ -577,8 +577,9 @@ __device__ __forceinline__ bool FilterPass(const DevIndexView &ix, const ListFil
 }
 
 // Exact probe of ONE candidate per lane (filter survivors, doc ascending across lanes):
-// skip metadata -> block, 5-step search over the block's record heads -> record, one record
-// decode -> membership. Returns false when the list has nothing at or after the first candidate.
+// skip metadata -> block; blk_heads (one 16-byte load) -> 4-record group; the group's records in
+// one or two 16-byte loads -> record -> membership. Three dependent round trips, three sectors.
+// Returns false when the list has nothing at or after the first candidate.
 template <class ST>
 __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, uint32_t *win, bool has,
                                          uint32_t x, bool *hit, uint32_t *pos, int lane,
@@ -590,6 +591,7 @@ __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, u
   if (j_lo == kNoDoc) return false;
   uint32_t j;
   if (mx <= __shfl_sync(kFull, p.wl, 31)) {
+    // every candidate falls inside the 32-block register window
     __syncwarp();
     win[lane] = p.wl;
     __syncwarp();
@@ -601,45 +603,87 @@ __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, u
     j = p.wbase + c;
     if (c >= 32u) has = false;
   } else {
-    uint32_t lo = j_lo, hi = p.nb;
-    if (has) {
+    // the batch spans more: stage the next 96 entries too (coalesced, usually L2 hits) and search
+    // the 128-entry window in shared memory; only candidates beyond it walk blk_last in global
+    __syncwarp();
+    win[lane] = p.wl;
+#pragma unroll
+    for (uint32_t i = 1; i < 4; i++) {
+      const uint32_t at = p.wbase + 32u * i + (uint32_t)lane;
+      win[32u * i + lane] = at < p.nb ? __ldg(p.last + at) : kNoDoc;
+    }
+    __syncwarp();
+    if (!has || x <= win[127]) {
+      uint32_t c = 0;
+#pragma unroll
+      for (uint32_t s = 64; s; s >>= 1)
+        if (win[c + s - 1] < x) c += s;
+      c += win[c] < x;
+      j = p.wbase + c;
+    } else {
+      uint32_t lo = p.wbase + 128u, hi = p.nb;
       while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         if (__ldg(p.last + mid) < x) lo = mid + 1; else hi = mid;
       }
+      j = lo;
     }
-    j = lo;
   }
   if (j >= p.nb) has = false;
   uint4 info = make_uint4(0u, 0u, 0u, 0u);
   if (has) {
     info = __ldg(&ix.blk_info[p.first + j]);
+    const uint4 gh = __ldg(&ix.blk_heads[p.first + j]);
     const uint32_t bits = info.z;
     const uint32_t nl = (ShN(bits) + 3u) >> 2, rcs = ShRcode(bits), w0 = ShW0(bits);
     const uint32_t m0 = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
-    const uint32_t *rp = reinterpret_cast<const uint32_t *>(ix.payload + info.y);
     const uint32_t rel = x - info.x;     // x > base of its block
-    // last record whose head (first doc - base) <= rel. Two levels of INDEPENDENT loads (records
-    // 4,8,..,28, then the three inside the chosen group) instead of a 5-deep dependent chain:
-    // the probe is latency-bound, and the extra loads hit sectors the block search reads anyway.
-    uint32_t grp = 0;
+    uint32_t rec, e[4];
+    if (w0 <= 16u && rcs <= 1u) {
+      // group = number of group heads (records 4, 8, .., 28) that are <= rel; heads ascend
+      const uint32_t grp = (uint32_t)(4u < nl && (gh.x >> 16) <= rel) + (uint32_t)(8u < nl && (gh.y & 0xffffu) <= rel) +
+                           (uint32_t)(12u < nl && (gh.y >> 16) <= rel) + (uint32_t)(16u < nl && (gh.z & 0xffffu) <= rel) +
+                           (uint32_t)(20u < nl && (gh.z >> 16) <= rel) + (uint32_t)(24u < nl && (gh.w & 0xffffu) <= rel) +
+                           (uint32_t)(28u < nl && (gh.w >> 16) <= rel);
+      const uint4 *rp4 = ix.payload + info.y;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t add;
+      if (rcs == 0u) {
+        // four one-word records in one granule
+        const uint4 g = __ldg(rp4 + grp);
+        add = (uint32_t)(4u * grp + 1u < nl && (g.y & m0) <= rel) + (uint32_t)(4u * grp + 2u < nl && (g.z & m0) <= rel) +
+              (uint32_t)(4u * grp + 3u < nl && (g.w & m0) <= rel);
+        raw.x = add == 0u ? g.x : add == 1u ? g.y : add == 2u ? g.z : g.w;
+      } else {
+        // four two-word records in two granules (the head is in the low word: w0 <= 16)
+        const uint4 ga = __ldg(rp4 + 2u * grp);
+        uint4 gb = make_uint4(0xffffffffu, 0u, 0xffffffffu, 0u);
+        if (4u * grp + 2u < nl) gb = __ldg(rp4 + 2u * grp + 1u);
+        add = (uint32_t)(4u * grp + 1u < nl && (ga.z & m0) <= rel) + (uint32_t)(4u * grp + 2u < nl && (gb.x & m0) <= rel) +
+              (uint32_t)(4u * grp + 3u < nl && (gb.z & m0) <= rel);
+        raw.x = add == 0u ? ga.x : add == 1u ? ga.z : add == 2u ? gb.x : gb.z;
+        raw.y = add == 0u ? ga.y : add == 1u ? ga.w : add == 2u ? gb.y : gb.w;
+      }
+      rec = 4u * grp + add;
+      DecodeRaw(info, raw, e);
+    } else {
+      // wide blocks (span >= 2^16 docs or 16-byte records): two levels of strided head loads
+      const uint32_t *rp = reinterpret_cast<const uint32_t *>(ix.payload + info.y);
+      uint32_t grp = 0;
 #pragma unroll
-    for (uint32_t t = 1; t < 8; t++) {
-      const uint32_t mid = 4u * t;
-      if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) grp = t;   // heads ascend: last true wins
-    }
-    uint32_t rec = 4u * grp;
-    {
+      for (uint32_t t = 1; t < 8; t++) {
+        const uint32_t mid = 4u * t;
+        if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) grp = t;   // heads ascend: last true wins
+      }
       uint32_t add = 0;
 #pragma unroll
       for (uint32_t t = 1; t < 4; t++) {
         const uint32_t mid = 4u * grp + t;
         if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) add = t;
       }
-      rec += add;
+      rec = 4u * grp + add;
+      DecodeRecord(ix, info, rec, e);
     }
-    uint32_t e[4];
-    DecodeRecord(ix, info, rec, e);
     const int slot = e[0] == x ? 0 : e[1] == x ? 1 : e[2] == x ? 2 : e[3] == x ? 3 : -1;
     *hit = slot >= 0;
     *pos = ((p.first + j) << 7) | (4u * rec + (uint32_t)max(slot, 0));

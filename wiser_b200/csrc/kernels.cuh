@@ -11,13 +11,20 @@ namespace wsr {
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kMaxFastK = 32;      // top-k held one entry per lane
-constexpr int kUnitBlocks = 64;    // max driver-list blocks per warp work unit
+#ifndef WSR_UNIT_BLOCKS
+#define WSR_UNIT_BLOCKS 64
+#endif
+constexpr int kUnitBlocks = WSR_UNIT_BLOCKS;      // max driver-list blocks per warp work unit
+// a unit's budget in blocks, driver + the probe-list blocks they span: unit_blocks =
+// clamp(kUnitBudget / (1 + ratio), 1, kUnitBlocks), ratio = probe blocks per driver block
+constexpr int kUnitBudget = 4 * WSR_UNIT_BLOCKS;
 
 // Read-only view of the HBM-resident index (layout: host_index.h).
 struct DevIndexView {
   const uint4 *payload;       // 16 B granules
   const uint4 *blk_info;      // {base_doc, payload_off16, bits, max_tfn}
   const uint32_t *blk_last;
+  const uint4 *blk_heads;     // 8 x u16 per block: first doc (minus base) of records 0,4,..,28
   const uint4 *lists;         // {first_block, n_blocks, df_shard, df_global}
   const uint8_t *norms;
   const double *cache;        // 256 entries

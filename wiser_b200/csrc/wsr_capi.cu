@@ -160,6 +160,7 @@ struct wsr_index {
   DevBuf<uint4> d_payload;
   DevBuf<uint4> d_blk_info;
   DevBuf<uint32_t> d_blk_last;
+  DevBuf<uint4> d_blk_heads;
   DevBuf<uint4> d_lists;
   DevBuf<uint8_t> d_norms;
   DevBuf<double> d_cache;
@@ -290,7 +291,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
       // Unit size: a unit's work is its driver blocks plus the probe-list blocks they can
       // reach, so skewed queries (long probe lists) get fewer driver blocks per unit.
       const uint64_t ratio = drv.n_blocks ? (probe_blocks + drv.n_blocks - 1) / drv.n_blocks : 0;
-      const uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kUnitBlocks, 256 / (1 + ratio)));
+      const uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kUnitBlocks, (uint64_t)kUnitBudget / (1 + ratio)));
       dq.unit_blocks = (uint16_t)ub;
       dq.n_units = (drv.n_blocks + ub - 1) / ub;
       const int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
@@ -568,6 +569,7 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
   if (!cu(ix->d_payload.Ensure(n_gran), "cudaMalloc payload") ||
       !cu(ix->d_blk_info.Ensure(h.blk_info.size() + 1), "cudaMalloc blk_info") ||
       !cu(ix->d_blk_last.Ensure(h.blk_last.size() + 1), "cudaMalloc blk_last") ||
+      !cu(ix->d_blk_heads.Ensure(h.blk_heads.size() / 8 + 1), "cudaMalloc blk_heads") ||
       !cu(ix->d_lists.Ensure(h.lists.size() + 1), "cudaMalloc lists") ||
       !cu(ix->d_norms.Ensure(h.norms.size() + 1), "cudaMalloc norms") ||
       !cu(ix->d_cache.Ensure(256), "cudaMalloc cache") ||
@@ -584,6 +586,7 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
   if (!cu(cudaMemcpy(ix->d_payload.p, h.payload.data(), n_gran * 16, cudaMemcpyHostToDevice), "H2D payload") ||
       !cu(cudaMemcpy(ix->d_blk_info.p, h.blk_info.data(), h.blk_info.size() * 16, cudaMemcpyHostToDevice), "H2D blk_info") ||
       !cu(cudaMemcpy(ix->d_blk_last.p, h.blk_last.data(), h.blk_last.size() * 4, cudaMemcpyHostToDevice), "H2D blk_last") ||
+      !cu(cudaMemcpy(ix->d_blk_heads.p, h.blk_heads.data(), h.blk_heads.size() * 2, cudaMemcpyHostToDevice), "H2D blk_heads") ||
       !cu(cudaMemcpy(ix->d_lists.p, h.lists.data(), h.lists.size() * 16, cudaMemcpyHostToDevice), "H2D lists") ||
       !cu(cudaMemcpy(ix->d_norms.p, h.norms.data(), h.norms.size(), cudaMemcpyHostToDevice), "H2D norms") ||
       !cu(cudaMemcpy(ix->d_cache.p, h.cache, 256 * 8, cudaMemcpyHostToDevice), "H2D cache") ||
@@ -594,12 +597,13 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
     return fail(e);
   ix->n_blocks = (int64_t)h.blk_info.size();
   ix->payload_bytes = (int64_t)n_gran * 16;
-  ix->hbm_bytes = ix->payload_bytes + ix->n_blocks * 24 + (int64_t)h.lists.size() * 32 +
+  ix->hbm_bytes = ix->payload_bytes + ix->n_blocks * 40 + (int64_t)h.lists.size() * 32 +
                   (int64_t)h.filters.size() * 4 + (int64_t)h.norms.size() + 2048;
   DevIndexView &v = ix->view;
   v.payload = ix->d_payload.p;
   v.blk_info = ix->d_blk_info.p;
   v.blk_last = ix->d_blk_last.p;
+  v.blk_heads = ix->d_blk_heads.p;
   v.lists = ix->d_lists.p;
   v.norms = ix->d_norms.p;
   v.cache = ix->d_cache.p;
@@ -661,6 +665,7 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
   std::vector<uint8_t>().swap(h.payload);
   std::vector<BlockInfo>().swap(h.blk_info);
   std::vector<uint32_t>().swap(h.blk_last);
+  std::vector<uint16_t>().swap(h.blk_heads);
   std::vector<uint32_t>().swap(h.filters);
   return ix.release();
 }
