@@ -5,6 +5,9 @@
 // calls the reference's own public classes:
 //   build     linedoc -> vacuum dir       (VacuumInvertedIndexDumper, DocLengthCharStore,
 //                                          ChunkedDocStoreDumper; flash_engine_dumper.h:263-830)
+//   buildbloom linedoc (with bloom columns) -> vacuum dir carrying the Bloom-begin/-end sections,
+//             the pipeline of tests_18.cc:283-310: QqMemEngineDelta::Serialize + BloomDumper +
+//             FlashEngineDumper(dir, true).LoadQqMemDump().Dump()
 //   replay    query log -> top-k results  (CreateSearchEngine + VacuumEngine::Search,
 //                                          engine_factory.h:33-50, vacuum_engine.h:201-258;
 //                                          log parsing = QueryProducerNoLoop, query_pool.h:251-311)
@@ -27,6 +30,7 @@
 int FLAGS_minloglevel = 2;
 int FLAGS_logtostderr = 1;
 
+#include "bloom_filter.h"
 #include "engine_factory.h"
 #include "flash_engine_dumper.h"
 #include "query_pool.h"
@@ -81,6 +85,29 @@ int CmdBuild(int argc, char **argv) {
   doc_store.Dump(dir + "/my.fdx", dir + "/my.fdt");
   remove((dir + "/fake.vacuum").c_str());
   fprintf(stderr, "built %d docs, %d terms -> %s\n", doc_id, (int)index.Size(), dir.c_str());
+  return 0;
+}
+
+int CmdBuildBloom(int argc, char **argv) {
+  if (argc < 4) {
+    fprintf(stderr, "usage: ref_tool buildbloom <linedoc with bloom columns> <out_dir>\n");
+    return 2;
+  }
+  const std::string linedoc = argv[2], dir = argv[3], tmp = dir + ".qqmem";
+  utils::RemoveDir(tmp);
+  utils::PrepareDir(dir);
+  auto engine = CreateSearchEngine("qq_mem_compressed");
+  engine->LoadLocalDocuments(linedoc, 100000000, "WITH_POSITIONS");
+  engine->Serialize(tmp);
+  BloomDumper bloom_dumper;
+  bloom_dumper.Load(linedoc);
+  bloom_dumper.Dump(tmp);
+  FlashEngineDumper engine_dumper(dir, true);
+  engine_dumper.LoadQqMemDump(tmp);
+  engine_dumper.Dump();
+  utils::RemoveDir(tmp);
+  remove((dir + "/fake.vacuum").c_str());
+  fprintf(stderr, "built bloom-enabled index, %d terms -> %s\n", engine->TermCount(), dir.c_str());
   return 0;
 }
 
@@ -227,6 +254,7 @@ int main(int argc, char **argv) {
   }
   std::string cmd = argv[1];
   if (cmd == "build") return CmdBuild(argc, argv);
+  if (cmd == "buildbloom") return CmdBuildBloom(argc, argv);
   if (cmd == "replay") return CmdReplay(argc, argv);
   if (cmd == "dumplists") return CmdDumpLists(argc, argv);
   if (cmd == "time") return CmdTime(argc, argv);

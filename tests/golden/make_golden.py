@@ -13,6 +13,8 @@ Per fixture directory:
   ref_top3.txt.gz                  same, k=3 (heap-eviction / tie behaviour)
   ref_full.txt.gz                  same, k=1e6 => full intersection with scores
   lists.npz                        every posting list decoded by the reference iterators
+bloom3/ and wikibloom4/ are built WITH the reference's Bloom-begin/-end sections (ref_tool
+buildbloom) and carry ref_top10_f{0,1,10}.txt.gz = results at bloom_enable_factor 0, 1, 10.
 """
 import os
 import shutil
@@ -98,6 +100,91 @@ def make_fixture(name, linedoc, queries, extra_ks=()):
     print(f"{name}: {len(queries)} queries, {sz / 1024:.0f} KiB")
 
 
+def token_sequences(linedoc):
+    """Per document the analysed token sequence, rebuilt from the tokenized + positions columns."""
+    out = []
+    for line in open(linedoc).read().split("\n")[1:]:
+        cols = line.split("\t")
+        if len(cols) < 5:
+            continue
+        terms = cols[2].split(" ")          # title, body, tokenized, offsets, positions, ...
+        bags = cols[4].split(".")[:len(terms)]
+        seq = {}
+        for t, bag in zip(terms, bags):
+            for p in bag.split(";"):
+                if p:
+                    seq[int(p)] = t
+        out.append([seq[i] for i in sorted(seq)])
+    return out
+
+
+def make_bloom_fixture(name, linedoc, queries):
+    """Index WITH the Bloom-begin/-end sections (ref_tool buildbloom = tests_18.cc:283-310). The
+    reference is replayed with bloom_enable_factor 0, 1 and 10; the filter is a shortcut that must
+    not change results, which is asserted here, and all three files are committed."""
+    import gzip
+    out = os.path.join(HERE, name)
+    work = os.path.join(TMP, name)
+    shutil.rmtree(out, ignore_errors=True)
+    shutil.rmtree(work, ignore_errors=True)
+    os.makedirs(out)
+    run(REF_TOOL, "buildbloom", linedoc, work)
+    qpath = os.path.join(out, "queries.txt")
+    with open(qpath, "w") as f:
+        for q in queries:
+            f.write(q + "\n")
+    for fn in ("my.tip", "my.vacuum", "my.doc_length"):
+        shutil.copy(os.path.join(work, fn), os.path.join(out, fn))
+    write_stub_doc_store(out)
+    texts = {}
+    for factor in (0, 1, 10):
+        fn = os.path.join(out, f"ref_top10_f{factor}.txt")
+        run(REF_TOOL, "replay", out, qpath, "10", fn, str(factor))
+        texts[factor] = open(fn).read()
+    assert texts[0] == texts[1] == texts[10], "bloom_enable_factor changed the reference's results"
+    run(REF_TOOL, "replay", out, qpath, "1000000", os.path.join(out, "ref_full.txt"), "1")
+    dump_lists_npz(out, os.path.join(out, "lists.npz"))
+    z = np.load(os.path.join(out, "lists.npz"))
+    with open(os.path.join(out, "terms.txt"), "w") as f:
+        for t, a, b in zip(z["terms"], z["offsets"][:-1], z["offsets"][1:]):
+            f.write(f"{t} {int(b - a)}\n")
+    for fn in sorted(os.listdir(out)):
+        if fn.startswith("ref_") and fn.endswith(".txt"):
+            with open(os.path.join(out, fn), "rb") as fi, \
+                    gzip.GzipFile(os.path.join(out, fn + ".gz"), "wb", mtime=0) as fo:
+                fo.write(fi.read())
+            os.remove(os.path.join(out, fn))
+    sz = sum(os.path.getsize(os.path.join(out, f)) for f in os.listdir(out))
+    print(f"{name}: {len(queries)} queries, {sz / 1024:.0f} KiB (bloom factors 0/1/10 agree)")
+
+
+def bloom_fixtures():
+    import random
+    # F. the reference's bi-Bloom 3-doc fixture (a / a a b / a b c) and the phrases tests_18.cc
+    #    expects to find ("a b", "b c") and not to find ("a x", "x c")
+    make_bloom_fixture("bloom3", os.path.join(REF_TESTDATA, "iter_test_3_docs_tf_bi-bloom"),
+                       ["a", "b", "c", "z", '"a b"', '"b c"', '"a x"', '"x c"', '"a c"', '"b a"', '"a a"',
+                        '"a b c"', '"a a b"', '"b c a"', "a b", "b c", "a b c", '"a"', "a a"])
+    # G. the 4-article Wikipedia fixture with prefix/suffix Bloom columns: n-grams that occur,
+    #    shuffled ones that mostly do not, plain ANDs and single terms
+    ld = os.path.join(REF_TESTDATA, "wiki_linedoc.toy.pre-suf-bloom")
+    seqs = token_sequences(ld)
+    rng = random.Random(31)
+    qs = []
+    for n, cnt in ((2, 300), (3, 120), (4, 40), (5, 15)):
+        for _ in range(cnt):
+            s = seqs[rng.randrange(len(seqs))]
+            i = rng.randrange(len(s) - n)
+            qs.append('"' + " ".join(s[i:i + n]) + '"')
+    vocab = sorted({t for s in seqs for t in s})
+    for n, cnt in ((2, 200), (3, 60)):
+        for _ in range(cnt):
+            qs.append('"' + " ".join(rng.choice(vocab) for _ in range(n)) + '"')
+    qs += [" ".join(rng.sample(vocab, 2)) for _ in range(150)]
+    qs += vocab[::7]
+    make_bloom_fixture("wikibloom4", ld, qs)
+
+
 def hello3_linedoc(path):
     # The 3-doc engine of the reference's tests.cc:407-421 ("hello world", "hello wisconsin",
     # "hello world big world"), written as WITH_POSITIONS linedoc.
@@ -125,6 +212,10 @@ def main():
         sys.exit("oracle/_ref/ref_tool missing: run `make -C oracle ref` (needs /root/reference)")
     shutil.rmtree(TMP, ignore_errors=True)
     os.makedirs(TMP)
+    if sys.argv[1:] == ["bloom"]:          # only the Bloom-enabled fixtures
+        bloom_fixtures()
+        return
+    bloom_fixtures()
 
     # A. known-answer 3-doc engine
     ld = os.path.join(TMP, "hello3.linedoc")

@@ -80,6 +80,32 @@ def test_full_intersection_vs_reference(engines, name):
                        what=" ".join(q.terms))
 
 
+@pytest.mark.parametrize("name", ["bloom3", "wikibloom4"])
+@pytest.mark.parametrize("factor", [0, 1, 10])
+def test_bloom_enabled_indexes_vs_reference(golden_dir, name, factor):
+    """Indexes carrying the reference's Bloom-begin/-end sections (tests_18.cc:283-359): phrase and
+    plain results equal the reference's at every bloom_enable_factor (the GPU path verifies the
+    positions themselves, so the factor cannot change anything), top-10 and full intersections."""
+    from wiser_b200 import GpuVacuumEngine, SearchQuery
+    d = os.path.join(golden_dir, name)
+    eng = GpuVacuumEngine(d, bloom_enable_factor=factor).Load()
+    ref = read_ref_results(os.path.join(d, f"ref_top10_f{factor}.txt.gz"))
+    full = read_ref_results(os.path.join(d, "ref_full.txt.gz"))
+    qs = [SearchQuery(*parse_query_line(l), n_results=10) for l in open(os.path.join(d, "queries.txt"))]
+    res = eng.SearchBatch(qs)
+    assert len(res) == len(ref)
+    for q, r, (rd, rs, rdf), (fd, fs, _) in zip(qs, res, ref, full):
+        assert r.doc_freqs == rdf, q.terms
+        check_topk(rd, rs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], fd, fs,
+                   what=" ".join(q.terms))
+    for q in qs:
+        q.n_results = 100
+    res = eng.SearchBatch(qs)
+    for q, r, (fd, fs, fdf) in zip(qs, res, full):
+        check_full(fd, fs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], what=" ".join(q.terms))
+    eng.close()
+
+
 def test_single_query_api_and_known_answers(engines):
     from wiser_b200 import SearchQuery
     eng, _, _ = engines["hello3"]

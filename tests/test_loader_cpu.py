@@ -36,7 +36,7 @@ def read_dump(path):
     return out
 
 
-@pytest.mark.parametrize("name", ["hello3", "abc3", "wiki4", "zipf2k"])
+@pytest.mark.parametrize("name", ["hello3", "abc3", "wiki4", "zipf2k", "bloom3", "wikibloom4"])
 def test_layout_decodes_to_reference_lists(golden_dir, dump_tool, tmp_path, name):
     d = os.path.join(golden_dir, name)
     out = str(tmp_path / "dump.bin")

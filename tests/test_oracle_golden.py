@@ -31,7 +31,38 @@ def test_search_matches_reference(golden_dir, name, k, fn):
         assert odfs == dfs, q
 
 
-@pytest.mark.parametrize("name", FIXTURES)
+BLOOM_FIXTURES = ["bloom3", "wikibloom4"]
+
+
+@pytest.mark.parametrize("name", BLOOM_FIXTURES)
+@pytest.mark.parametrize("k,fn", [(10, "ref_top10_f0.txt.gz"), (10, "ref_top10_f1.txt.gz"),
+                                  (10, "ref_top10_f10.txt.gz"), (1000000, "ref_full.txt.gz")])
+def test_search_matches_reference_on_bloom_indexes(golden_dir, name, k, fn):
+    """Indexes written WITH the Bloom-begin/-end sections (tests_18.cc:283-359): the reference's
+    results at bloom_enable_factor 0, 1 and 10 are identical, and the oracle (which reads the
+    positions and never the filters) reproduces them bit for bit."""
+    d = os.path.join(golden_dir, name)
+    ix = OracleIndex(d)
+    ref = read_ref_results(os.path.join(d, fn))
+    qs = _queries(d)
+    assert len(ref) == len(qs)
+    for (q, is_phrase), (docs, scores, dfs) in zip(qs, ref):
+        od, os_, odfs = ix.search(q, k, is_phrase=is_phrase)
+        assert np.array_equal(od, docs), q
+        assert np.array_equal(os_.view(np.uint64), scores.view(np.uint64)), q
+        assert odfs == dfs, q
+
+
+def test_bloom3_known_phrases(golden_dir):
+    """tests_18.cc:331-356: phrases "a b" and "b c" are found, "a x" and "x c" are not."""
+    ix = OracleIndex(os.path.join(golden_dir, "bloom3"))
+    assert len(ix.search(["a", "b"], 5, is_phrase=True)[0]) == 2
+    assert len(ix.search(["b", "c"], 5, is_phrase=True)[0]) == 1
+    for q in (["a", "x"], ["x", "c"], ["a", "c"], ["b", "a"]):
+        assert len(ix.search(q, 5, is_phrase=True)[0]) == 0
+
+
+@pytest.mark.parametrize("name", FIXTURES + BLOOM_FIXTURES)
 def test_decode_matches_reference_iterators(golden_dir, name):
     d = os.path.join(golden_dir, name)
     ix = OracleIndex(d)
