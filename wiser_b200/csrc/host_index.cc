@@ -137,6 +137,7 @@ struct Chunk {               // output of one slice of terms
   std::vector<uint8_t> payload;
   std::vector<uint32_t> positions;   // optional position column, absolute in-document positions
   std::vector<uint32_t> blk_pos;     // per block: index of its first position
+  std::vector<uint16_t> rec_pos;     // per block 32 entries: positions before record r
   bool no_positions = false;         // some list of the chunk has no position column
   int64_t postings = 0, postings_global = 0;
   std::string err;
@@ -283,12 +284,23 @@ struct Builder {
       // group heads: first doc (relative to base) of records 0, 4, .., 28 when they fit 16 bits
       for (int t = 0; t < 8; t++)
         c->blk_heads.push_back(sh.w0 <= 16 && 4 * t < nl ? (uint16_t)first[4 * t] : (uint16_t)0xFFFF);
-      if (want_positions && !keep_pos) c->blk_pos.push_back(0u);
+      if (want_positions && !keep_pos) {
+        c->blk_pos.push_back(0u);
+        c->rec_pos.insert(c->rec_pos.end(), 32, (uint16_t)0);
+      }
       if (keep_pos) {
         if (c->positions.size() > 0xFFFFFFF0ull) { c->err = "more than 2^32 positions"; return false; }
         c->blk_pos.push_back((uint32_t)c->positions.size());
         uint64_t cnt = 0;
-        for (int i = 0; i < n; i++) cnt += (*tfs)[s + i];
+        uint16_t rp[32];
+        for (int i = 0; i < 4 * 32; i++) {
+          if ((i & 3) == 0) rp[i >> 2] = (uint16_t)std::min<uint64_t>(cnt, 0xFFFF);
+          if (i < n) cnt += (*tfs)[s + i];
+        }
+        // a block with 65535+ positions keeps the sentinel everywhere: the kernel then sums tfs
+        if (cnt >= 0xFFFF)
+          for (int r = 1; r < 32; r++) rp[r] = 0xFFFF;
+        c->rec_pos.insert(c->rec_pos.end(), rp, rp + 32);
         c->positions.insert(c->positions.end(), pos_vals.begin() + pos_at, pos_vals.begin() + pos_at + cnt);
         pos_at += cnt;
       }
@@ -512,6 +524,7 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
   if (ix.has_positions) {
     ix.positions.assign(tot_pos + 1, 0u);
     ix.blk_pos.assign(tot_blocks + 1, 0u);
+    ix.rec_pos.assign((tot_blocks + 1) * 32, (uint16_t)0);
   }
   std::vector<size_t> blk_base(chunks.size()), pay_base(chunks.size()), flt_base(chunks.size()),
       pos_base(chunks.size());
@@ -549,6 +562,8 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
       std::vector<uint32_t>().swap(c.filters);
       if (ix.has_positions) {
         for (size_t j = 0; j < c.blk_pos.size(); j++) ix.blk_pos[b0 + j] = c.blk_pos[j] + (uint32_t)pos_base[i];
+        if (!c.rec_pos.empty()) memcpy(ix.rec_pos.data() + b0 * 32, c.rec_pos.data(), c.rec_pos.size() * 2);
+        std::vector<uint16_t>().swap(c.rec_pos);
         if (!c.positions.empty())
           memcpy(ix.positions.data() + pos_base[i], c.positions.data(), c.positions.size() * 4);
         std::vector<uint32_t>().swap(c.positions);

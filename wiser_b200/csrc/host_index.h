@@ -44,6 +44,9 @@
 //                       through the skip list, flash_iterators.h:558-661) with the deltas summed
 //   blk_pos   u32[]     index into positions[] of each block's first posting; a posting's run
 //                       starts at blk_pos + sum of the tfs before it in the block
+//   rec_pos   u16[32][] per block: number of positions before record r (postings 0..4r-1), so the
+//                       run of posting 4r+i starts at blk_pos + rec_pos[r] + the i tfs before it in
+//                       the record; all 0xFFFF (r >= 1) when the block holds >= 65535 positions
 //   norms     u8[]      DocLengthCharStore bytes indexed by GLOBAL doc id
 //   cache     f64[256]  Bm25Similarity::cache_ (scoring.h:85-90)
 #ifndef WSR_HOST_INDEX_H
@@ -154,6 +157,7 @@ struct HostIndex {
   bool has_positions = false;
   std::vector<uint32_t> positions;
   std::vector<uint32_t> blk_pos;
+  std::vector<uint16_t> rec_pos;    // 32 per block
   std::vector<uint64_t> list_alg_bytes;  // algorithmic bytes of all blocks of each list
   int64_t n_postings = 0, n_postings_global = 0;
   int shard = 0, n_shards = 1;

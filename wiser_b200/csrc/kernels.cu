@@ -708,35 +708,39 @@ struct PosRun {
 };
 // tf of posting `pos` and the start of its run in positions[]: the block's first position index
 // plus the tfs of the postings before it in the block.
+__device__ __forceinline__ void LoadTfs4(const uint4 *src, uint32_t tc, uint32_t r, uint32_t t[4]) {
+  if (tc == 0) {
+    const uint32_t v = __ldg(reinterpret_cast<const unsigned short *>(src) + r);
+    t[0] = v & 15u; t[1] = (v >> 4) & 15u; t[2] = (v >> 8) & 15u; t[3] = v >> 12;
+  } else if (tc == 1) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src) + r);
+    t[0] = v & 255u; t[1] = (v >> 8) & 255u; t[2] = (v >> 16) & 255u; t[3] = v >> 24;
+  } else {
+    const uint4 v = __ldg(src + r);
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+}
 __device__ __forceinline__ PosRun PositionsOf(const DevIndexView &ix, uint32_t pos) {
-  const uint32_t blk = pos >> 7, slot = pos & 127u;
+  const uint32_t blk = pos >> 7, slot = pos & 127u, rec = slot >> 2;
   const uint4 info = __ldg(&ix.blk_info[blk]);
+  const uint32_t first = __ldg(&ix.blk_pos[blk]);
+  uint32_t before = rec ? (uint32_t)__ldg(&ix.rec_pos[(size_t)blk * 32u + rec]) : 0u;
   const uint32_t bits = info.z, tc = ShTcode(bits);
   const uint4 *src = ix.payload + info.y + DocGranules(bits);
-  uint32_t before = 0, tf = 0;
-  for (uint32_t r = 0; r <= (slot >> 2); r++) {
-    uint32_t t[4];
-    if (tc == 0) {
-      const uint32_t v = __ldg(reinterpret_cast<const unsigned short *>(src) + r);
-      t[0] = v & 15u; t[1] = (v >> 4) & 15u; t[2] = (v >> 8) & 15u; t[3] = v >> 12;
-    } else if (tc == 1) {
-      const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(src) + r);
-      t[0] = v & 255u; t[1] = (v >> 8) & 255u; t[2] = (v >> 16) & 255u; t[3] = v >> 24;
-    } else {
-      const uint4 v = __ldg(src + r);
-      t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
-    }
-    if (r < (slot >> 2)) {
+  uint32_t t[4];
+  if (before == 0xFFFFu) {   // block with >= 65535 positions: sum the tfs of the records before
+    before = 0;
+    for (uint32_t r = 0; r < rec; r++) {
+      LoadTfs4(src, tc, r, t);
       before += t[0] + t[1] + t[2] + t[3];
-    } else {
-      const uint32_t s = slot & 3u;
-      before += (s > 0 ? t[0] : 0u) + (s > 1 ? t[1] : 0u) + (s > 2 ? t[2] : 0u);
-      tf = s == 0 ? t[0] : s == 1 ? t[1] : s == 2 ? t[2] : t[3];
     }
   }
+  LoadTfs4(src, tc, rec, t);
+  const uint32_t s = slot & 3u;
+  before += (s > 0 ? t[0] : 0u) + (s > 1 ? t[1] : 0u) + (s > 2 ? t[2] : 0u);
   PosRun run;
-  run.p = ix.positions + __ldg(&ix.blk_pos[blk]) + before;
-  run.n = tf;
+  run.p = ix.positions + first + before;
+  run.n = s == 0 ? t[0] : s == 1 ? t[1] : s == 2 ? t[2] : t[3];
   return run;
 }
 // exists p in a with p + 1 in b
@@ -769,16 +773,23 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
     if (has) {
       const HitRec h = ws->hits[base + lane];
       doc = (int)h.doc;
+      uint32_t tfa, tfb;
       if (q.flags & 1u) {   // phrase: query term 0 must be directly followed by term 1
         const PosRun ra = PositionsOf(ix, h.pos_a), rb = PositionsOf(ix, h.pos_b);
         keep = drv == 0 ? PhraseTwo(ra, rb) : PhraseTwo(rb, ra);
+        tfa = ra.n;           // a posting's run length IS its tf
+        tfb = rb.n;
         WSR_STAT(st.bytes += 4ull * (ra.n + rb.n););
+      } else {
+        tfa = TfAt(ix, h.pos_a);
+        tfb = TfAt(ix, h.pos_b);
       }
-      const uint32_t tfa = TfAt(ix, h.pos_a), tfb = TfAt(ix, h.pos_b);
-      const double cn = sh->cache[__ldg(ix.norms + h.doc)];
-      // query order: term 0 first (scoring.h:124-145)
-      s = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? tfa : tfb, cn));
-      s = __dadd_rn(s, TermScore(idf1, drv == 0 ? tfb : tfa, cn));
+      if (keep) {
+        const double cn = sh->cache[__ldg(ix.norms + h.doc)];
+        // query order: term 0 first (scoring.h:124-145)
+        s = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? tfa : tfb, cn));
+        s = __dadd_rn(s, TermScore(idf1, drv == 0 ? tfb : tfa, cn));
+      }
     }
     has = has && keep;
     if (COLLECT) CollectAppend(bv, q, qi, has, doc, s, lane);

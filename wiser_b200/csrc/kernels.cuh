@@ -34,6 +34,7 @@ struct DevIndexView {
   const uint2 *list_flt;      // per term {first filter word, shift g (0xFFFFFFFF: no filter)}
   const uint32_t *positions;  // optional: in-document token positions, postings back to back
   const uint32_t *blk_pos;    // optional: index into positions[] of each block's first posting
+  const uint16_t *rec_pos;    // optional: 32 per block, positions before record r of the block
   uint32_t n_terms;
   uint32_t n_docs;
   uint32_t doc_lo;            // first doc id held by this shard (filter origin)

@@ -169,6 +169,7 @@ struct wsr_index {
   DevBuf<uint32_t> d_filters;
   DevBuf<uint2> d_list_flt;
   DevBuf<uint32_t> d_positions, d_blk_pos;
+  DevBuf<uint16_t> d_rec_pos;
   // device copy of the term dictionary for the query-log front end (frontend.cu)
   DevBuf<uint2> d_dict_slots;
   DevBuf<uint32_t> d_term_off;
@@ -617,17 +618,22 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
   v.n_filter_words = (uint32_t)h.filters.size();
   v.positions = nullptr;
   v.blk_pos = nullptr;
+  v.rec_pos = nullptr;
   if (h.has_positions) {
     if (!cu(ix->d_positions.Ensure(h.positions.size() + 1), "cudaMalloc positions") ||
         !cu(ix->d_blk_pos.Ensure(h.blk_pos.size() + 1), "cudaMalloc blk_pos") ||
+        !cu(ix->d_rec_pos.Ensure(h.rec_pos.size() + 1), "cudaMalloc rec_pos") ||
+        !cu(cudaMemcpy(ix->d_rec_pos.p, h.rec_pos.data(), h.rec_pos.size() * 2, cudaMemcpyHostToDevice), "H2D rec_pos") ||
         !cu(cudaMemcpy(ix->d_positions.p, h.positions.data(), h.positions.size() * 4, cudaMemcpyHostToDevice), "H2D positions") ||
         !cu(cudaMemcpy(ix->d_blk_pos.p, h.blk_pos.data(), h.blk_pos.size() * 4, cudaMemcpyHostToDevice), "H2D blk_pos"))
       return fail(e);
     v.positions = ix->d_positions.p;
     v.blk_pos = ix->d_blk_pos.p;
-    ix->hbm_bytes += (int64_t)h.positions.size() * 4 + (int64_t)h.blk_pos.size() * 4;
+    v.rec_pos = ix->d_rec_pos.p;
+    ix->hbm_bytes += (int64_t)h.positions.size() * 4 + (int64_t)h.blk_pos.size() * 4 + (int64_t)h.rec_pos.size() * 2;
     std::vector<uint32_t>().swap(h.positions);
     std::vector<uint32_t>().swap(h.blk_pos);
+    std::vector<uint16_t>().swap(h.rec_pos);
   }
   // term dictionary in HBM for the query-log front end: the host table's slots with a 32-bit tag
   // (so most probes never touch the term bytes), 32-bit term offsets, the term arena
