@@ -433,122 +433,6 @@ __device__ __forceinline__ uint32_t ProbeFind(ProbeList &p, uint32_t x, int lane
   return (c == 32 || j >= p.nb) ? kNoDoc : j;
 }
 
-// Galloping probe of one list for the lane's four candidates d[i] (alive[i] says which to test).
-// On return alive[i] tells whether d[i] is in the list and pos[i] = (global block << 7) | slot.
-// Returns false when the list has nothing at or after the smallest candidate (nothing later in
-// the driver can match either).
-template <class ST>
-__device__ __forceinline__ bool ProbeCandidates(const DevIndexView &ix, ProbeList &p, uint32_t *win,
-                                                const uint32_t d[4], bool alive[4], uint32_t pos[4],
-                                                int lane, ST &st) {
-  uint32_t mn = kNoDoc, mx = 0u;
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-    if (alive[i]) { mn = min(mn, d[i]); mx = max(mx, d[i]); }
-  mn = __reduce_min_sync(kFull, mn);
-  if (mn == kNoDoc) return true;                       // nothing to test
-  mx = __reduce_max_sync(kFull, mx);
-  const uint32_t j_lo = ProbeFind(p, mn, lane);
-  if (j_lo == kNoDoc) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) alive[i] = false;
-    return false;
-  }
-  // ---- block of every candidate
-  uint32_t j[4];
-  if (mx <= __shfl_sync(kFull, p.wl, 31)) {
-    // all candidates fall inside the window: count window entries < d (5-step search in smem)
-    __syncwarp();
-    win[lane] = p.wl;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      uint32_t c = 0;
-#pragma unroll
-      for (uint32_t s = 16; s; s >>= 1)
-        if (win[c + s - 1] < d[i]) c += s;
-      c += win[c] < d[i];
-      j[i] = p.wbase + c;
-      if (c >= 32u || j[i] >= p.nb) alive[i] = false;
-    }
-  } else {
-    // skewed lists: the driver block spans more than a window of probe blocks
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      uint32_t lo = j_lo, hi = p.nb;
-      if (alive[i]) {
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (__ldg(p.last + mid) < d[i]) lo = mid + 1; else hi = mid;
-        }
-      }
-      j[i] = lo;
-      if (lo >= p.nb) alive[i] = false;
-    }
-  }
-  // ---- record of every candidate: last record whose first doc <= d (step-major for ILP)
-  uint4 info[4];
-  uint32_t rec[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    info[i] = make_uint4(0u, 0u, 0u, 0u);
-    rec[i] = 0;
-    if (alive[i]) info[i] = __ldg(&ix.blk_info[p.first + j[i]]);
-  }
-  uint32_t nl[4], rcs[4], m0[4], rel[4];
-  const uint32_t *rp[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const uint32_t bits = info[i].z, w0 = ShW0(bits);
-    nl[i] = alive[i] ? (ShN(bits) + 3u) >> 2 : 0u;
-    rcs[i] = ShRcode(bits);
-    m0[i] = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
-    rp[i] = reinterpret_cast<const uint32_t *>(ix.payload + info[i].y);
-    rel[i] = d[i] - info[i].x;
-  }
-#pragma unroll
-  for (uint32_t s = 16; s; s >>= 1) {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const uint32_t mid = rec[i] + s;
-      if (mid < nl[i] && (__ldg(rp[i] + (mid << rcs[i])) & m0[i]) <= rel[i]) rec[i] = mid;
-    }
-  }
-  // ---- decode that record and compare
-  uint32_t touched_n = 0, touched_b = 0;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    if (alive[i]) {
-      uint32_t e[4];
-      DecodeRecord(ix, info[i], rec[i], e);
-      const uint32_t x = d[i];
-      const int slot = e[0] == x ? 0 : e[1] == x ? 1 : e[2] == x ? 2 : e[3] == x ? 3 : -1;
-      alive[i] = slot >= 0;
-      pos[i] = ((p.first + j[i]) << 7) | (4u * rec[i] + (uint32_t)max(slot, 0));
-    }
-  }
-  // ---- accounting: every distinct probe block touched counts once (candidates are sorted by
-  // (lane, slot), so a block is new when it differs from the previous candidate's)
-  if constexpr (ST::kOn) {
-    uint32_t prev = __shfl_up_sync(kFull, j[3], 1);
-    if (lane == 0) prev = kNoDoc;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const bool has = info[i].z != 0u || info[i].y != 0u || info[i].x != 0u;
-      if (has && j[i] != prev) {
-        touched_n += ShN(info[i].z);
-        touched_b += AlgBytes(info[i].z, false);
-      }
-      if (has) prev = j[i];
-    }
-    // j[3] of the previous lane may be stale when that lane had dead slots; the count is
-    // bookkeeping for the roofline, never used for results
-    WSR_STAT(st.decoded += __reduce_add_sync(kFull, touched_n););
-    WSR_STAT(st.bytes += __reduce_add_sync(kFull, touched_b););
-  }
-  return true;
-}
-
 // Bloom pre-test of one candidate against a probe list's filter (no false negatives).
 struct ListFilter {
   const uint32_t *words;   // nullptr: the list has no filter, everything passes
@@ -571,9 +455,6 @@ __device__ __forceinline__ uint32_t FilterWord(const DevIndexView &ix, const Lis
                                                bool valid) {
   if (lf.words == nullptr || !valid) return 0xffffffffu;
   return __ldg(lf.words + ((doc - ix.doc_lo) >> lf.shift));
-}
-__device__ __forceinline__ bool FilterPass(const DevIndexView &ix, const ListFilter &lf, uint32_t doc) {
-  return FilterTest(FilterWord(ix, lf, doc, true), doc);
 }
 
 // Exact probe of ONE candidate per lane (filter survivors, doc ascending across lanes):
@@ -951,127 +832,213 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
 }
 
 // ---- 3..8-term units: QueryProcessor::ProcessMultipleTerms, query_processing.h:710-728 -------
-// The shortest list drives; the other lists are probed in query order with the same machinery,
-// candidates dying as soon as one list lacks them. Survivors are scored in place.
-template <int M, bool COLLECT, class ST>
-__device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
-                             uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
-                             const CtaShared *sh, ProbeScratch *ws, int lane, ST &st) {
-  const int m = (int)q.n_terms;
-  const int drv = (int)q.driver;
-  const int k = (int)q.k;
-  const bool multi = q.n_units > 1;
-  ProbeList pl[M];
-  double idf[M];
-  uint32_t first_a = 0;
+// The shortest list drives. A driver posting survives when it passes the Bloom filters of ALL
+// other lists; survivors are compacted in doc order and, 32 at a time (one per lane), probed
+// exactly list by list in query order — a candidate that misses a list is dropped before the
+// next one, which is the reference's "break on first mismatch". Matches are phrase-checked
+// (when asked) and scored in query order. The walk state of the other lists lives in shared
+// memory between batches, so the kernel fits 64 registers.
+struct ProbeState {          // a ProbeList parked in shared memory
+  uint32_t first, nb, wbase, flt_word, flt_shift, pad[3];
+  uint32_t wl[32];
+};
+struct __align__(16) MultiScratch {
+  ProbeScratch ps;                       // win + cand (hits[] unused)
+  ProbeState list[WSR_MAX_TERMS];
+};
+
+__device__ __forceinline__ ProbeList Unpark(const DevIndexView &ix, const ProbeState &st, int lane) {
+  ProbeList p;
+  p.first = st.first; p.nb = st.nb; p.wbase = st.wbase;
+  p.last = ix.blk_last + st.first;
+  p.wl = st.wl[lane];
+  return p;
+}
+__device__ __forceinline__ void Park(ProbeState &st, const ProbeList &p, int lane) {
+  st.wbase = p.wbase;
+  st.wl[lane] = p.wl;
+}
+
+// Probes up to 32 queued survivors (one per lane) against every non-driver list, verifies the
+// phrase and scores the matches. Returns false when some list is exhausted (the unit can stop).
+template <bool COLLECT, class ST>
+__device__ bool MultiBatch(const DevIndexView &ix, const BatchView &bv, const DevQuery &q, uint32_t qi,
+                           const CtaShared *sh, MultiScratch *ws, int base, int n, TopK &top,
+                           double &published, bool multi, int lane, ST &st) {
+  const int m = (int)q.n_terms, drv = (int)q.driver;
+  bool has = lane < n;
+  CandRec c;
+  c.doc = 0; c.pos_a = 0;
+  if (has) c = ws->ps.cand[base + lane];
+  uint32_t pos[WSR_MAX_TERMS];
 #pragma unroll
-  for (int t = 0; t < M; t++) {
-    idf[t] = 0.0;
-    if (t < m) {
-      const uint4 li = __ldg(&ix.lists[q.term[t]]);
-      idf[t] = __ldg(&ix.idf[q.term[t]]);
-      ProbeInit(pl[t], ix, li, lane);
-      if (t == drv) first_a = li.x;
+  for (int t = 0; t < WSR_MAX_TERMS; t++) pos[t] = c.pos_a;
+  bool more = true;
+#pragma unroll
+  for (int t = 0; t < WSR_MAX_TERMS; t++) {
+    if (t >= m || t == drv) continue;
+    if (!__any_sync(kFull, has)) break;          // every candidate already missed a list
+    ProbeList pl = Unpark(ix, ws->list[t], lane);
+    bool hit = false;
+    uint32_t pb = 0;
+    const bool some = ProbeOne(ix, pl, ws->ps.win, has, c.doc, &hit, &pb, lane, st);
+    __syncwarp();
+    Park(ws->list[t], pl, lane);
+    __syncwarp();
+    if (!some) { more = false; has = false; break; }
+    has = has && hit;
+    pos[t] = pb;
+  }
+  double s = 0.0;
+  if (has) {
+    uint32_t tf[WSR_MAX_TERMS];
+    bool keep = true;
+    if (q.flags & 1u) {
+      // positions of every term's posting in this doc: p in term 0, p + t in term t for all t
+      PosRun run[WSR_MAX_TERMS];
+#pragma unroll
+      for (int t = 0; t < WSR_MAX_TERMS; t++) {
+        run[t].p = nullptr; run[t].n = 0;
+        if (t < m) {
+          run[t] = PositionsOf(ix, pos[t]);
+          tf[t] = run[t].n;
+          WSR_STAT(st.bytes += 4ull * run[t].n;);
+        }
+      }
+      uint32_t ptr[WSR_MAX_TERMS];
+#pragma unroll
+      for (int t = 0; t < WSR_MAX_TERMS; t++) ptr[t] = 0;
+      bool found = false;
+      for (uint32_t a0 = 0; a0 < run[0].n && !found; a0++) {
+        const uint32_t p0 = __ldg(run[0].p + a0);
+        bool ok = true;
+#pragma unroll
+        for (int t = 1; t < WSR_MAX_TERMS; t++) {
+          if (t < m && ok) {
+            const uint32_t want = p0 + (uint32_t)t;
+            while (ptr[t] < run[t].n && __ldg(run[t].p + ptr[t]) < want) ptr[t]++;
+            ok = ptr[t] < run[t].n && __ldg(run[t].p + ptr[t]) == want;
+          }
+        }
+        found = ok;
+      }
+      keep = found;
+    } else {
+#pragma unroll
+      for (int t = 0; t < WSR_MAX_TERMS; t++)
+        if (t < m) tf[t] = TfAt(ix, pos[t]);
+    }
+    has = keep;
+    if (keep) {
+      // query order, fp64, one rounding per operation (scoring.h:124-145)
+      const double cn = sh->cache[__ldg(ix.norms + c.doc)];
+#pragma unroll
+      for (int t = 0; t < WSR_MAX_TERMS; t++)
+        if (t < m) s = __dadd_rn(s, TermScore(__ldg(&ix.idf[q.term[t]]), tf[t], cn));
     }
   }
+  const unsigned hm = __ballot_sync(kFull, has);
+  if (hm) {
+    WSR_STAT(st.matches += __popc(hm););
+    WSR_STAT(st.bytes += (8ull * m + 1ull) * __popc(hm););
+    if (COLLECT) CollectAppend(bv, q, qi, has, (int)c.doc, s, lane);
+    else OfferToTopK(bv, qi, multi, (int)q.k, has, s, (int)c.doc, top, published, lane);
+  }
+  return more;
+}
+
+template <bool COLLECT, class ST>
+__device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
+                             uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
+                             const CtaShared *sh, MultiScratch *ws, int lane, ST &st) {
+  const int m = (int)q.n_terms;
+  const int drv = (int)q.driver;
+  const bool multi = q.n_units > 1;
+  uint32_t first_a = 0;
+  __syncwarp();
+  for (int t = 0; t < m; t++) {
+    const uint4 li = __ldg(&ix.lists[q.term[t]]);
+    if (t == drv) { first_a = li.x; continue; }
+    const uint2 f = __ldg(&ix.list_flt[q.term[t]]);
+    ProbeState &ps = ws->list[t];
+    if (lane == 0) {
+      ps.first = li.x; ps.nb = li.y; ps.wbase = 0;
+      ps.flt_word = f.x; ps.flt_shift = f.y;     // shift 0xFFFFFFFF: no filter
+    }
+    ps.wl[lane] = (uint32_t)lane < li.y ? __ldg(ix.blk_last + li.x + lane) : kNoDoc;
+  }
+  __syncwarp();
   TopK top;
   TopKInit(top);
   double published = 0.0;
-  bool exhausted = false;
+  int nc = 0;
+  bool more = true;
 
-  for (uint32_t ja = b0; ja < b1 && !exhausted; ja++) {
-    const uint4 cur = __ldg(&ix.blk_info[first_a + ja]);
+  uint4 cur = __ldg(&ix.blk_info[first_a + b0]);
+  for (uint32_t ja = b0; ja < b1 && more; ja++) {
+    const uint4 nxt = ja + 1 < b1 ? __ldg(&ix.blk_info[first_a + ja + 1]) : cur;
     uint32_t d[4];
     DecodeDocs(ix, cur, lane, d);
     const uint32_t na = ShN(cur.z);
     WSR_STAT(st.decoded += na;);
     WSR_STAT(st.bytes += AlgBytes(cur.z, false););
-    bool al[4];
+    bool pass[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) al[i] = 4u * lane + i < na;
-    uint32_t posv[M][4];
-
+    for (int i = 0; i < 4; i++) pass[i] = 4u * lane + i < na;   // padded slots repeat the last doc
+    // Bloom filters of every other list; a term is skipped once nothing in the warp is alive
+    for (int t = 0; t < m; t++) {
+      if (t == drv) continue;
+      if (!__any_sync(kFull, pass[0] || pass[1] || pass[2] || pass[3])) break;
+      const uint32_t shift = ws->list[t].flt_shift;
+      if (shift == 0xffffffffu) continue;
+      const uint32_t *words = ix.filters + ws->list[t].flt_word;
+      uint32_t w[4];
 #pragma unroll
-    for (int t = 0; t < M; t++) {
-      if (t >= m || t == drv) continue;
-      const ListFilter lf = FilterOf(ix, q.term[t]);
+      for (int i = 0; i < 4; i++) w[i] = pass[i] ? __ldg(words + ((d[i] - ix.doc_lo) >> (shift & 31u))) : 0u;
 #pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (al[i] && !FilterPass(ix, lf, d[i])) al[i] = false;
+      for (int i = 0; i < 4; i++) pass[i] = pass[i] && FilterTest(w[i], d[i]);
     }
+    unsigned bm[4];
 #pragma unroll
-    for (int t = 0; t < M; t++) {
-      if (t >= m || t == drv) continue;
-      if (!ProbeCandidates(ix, pl[t], ws->win, d, al, posv[t], lane, st)) exhausted = true;
-    }
-
-    // survivors matched every list: score in QUERY order, fp64, one rounding per operation
-    bool hit[4];
-    double s64[4];
+    for (int i = 0; i < 4; i++) bm[i] = __ballot_sync(kFull, pass[i]);
+    if (bm[0] | bm[1] | bm[2] | bm[3]) {
+      const unsigned lt = (1u << lane) - 1u;
+      int at = nc + __popc(bm[0] & lt) + __popc(bm[1] & lt) + __popc(bm[2] & lt) + __popc(bm[3] & lt);
+      const uint32_t ga = (first_a + ja) << 7;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (al[i] && (q.flags & 1u)) {
-        // positions of every term's posting in this doc; p in term 0, p + t in term t for all t
-        PosRun run[M];
-#pragma unroll
-        for (int t = 0; t < M; t++) {
-          run[t].p = nullptr;
-          run[t].n = 0;
-          if (t < m) {
-            const uint32_t pos = t == drv ? (((first_a + ja) << 7) | (4u * lane + i)) : posv[t][i];
-            run[t] = PositionsOf(ix, pos);
-            WSR_STAT(st.bytes += 4ull * run[t].n;);
-          }
+      for (int i = 0; i < 4; i++) {
+        if (pass[i]) {
+          CandRec c;
+          c.doc = d[i];
+          c.pos_a = ga | (4u * lane + i);
+          ws->ps.cand[at++] = c;
         }
-        uint32_t ptr[M];
-#pragma unroll
-        for (int t = 0; t < M; t++) ptr[t] = 0;
-        bool found = false;
-        for (uint32_t a0 = 0; a0 < run[0].n && !found; a0++) {
-          const uint32_t p0 = __ldg(run[0].p + a0);
-          bool ok = true;
-#pragma unroll
-          for (int t = 1; t < M; t++) {
-            if (t < m && ok) {
-              const uint32_t want = p0 + (uint32_t)t;
-              while (ptr[t] < run[t].n && __ldg(run[t].p + ptr[t]) < want) ptr[t]++;
-              ok = ptr[t] < run[t].n && __ldg(run[t].p + ptr[t]) == want;
-            }
-          }
-          found = ok;
-        }
-        al[i] = found;
       }
-      hit[i] = al[i];
-      s64[i] = 0.0;
-      if (al[i]) {
-        const double cn = sh->cache[__ldg(ix.norms + d[i])];
-        double s = 0.0;
-#pragma unroll
-        for (int t = 0; t < M; t++) {
-          if (t < m) {
-            const uint32_t pos = t == drv ? (((first_a + ja) << 7) | (4u * lane + i)) : posv[t][i];
-            s = __dadd_rn(s, TermScore(idf[t], TfAt(ix, pos), cn));
-          }
-        }
-        s64[i] = s;
+      nc += __popc(bm[0]) + __popc(bm[1]) + __popc(bm[2]) + __popc(bm[3]);
+      __syncwarp();
+      int base = 0;
+      for (; nc - base >= 32 && more; base += 32)
+        more = MultiBatch<COLLECT>(ix, bv, q, qi, sh, ws, base, 32, top, published, multi, lane, st);
+      if (base) {   // move the leftover (< 32) to the front
+        CandRec c;
+        c.doc = 0; c.pos_a = 0;
+        const bool mv = base + lane < nc;
+        if (mv) c = ws->ps.cand[base + lane];
+        __syncwarp();
+        if (mv) ws->ps.cand[lane] = c;
+        nc -= base;
+        __syncwarp();
       }
     }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const unsigned hm = __ballot_sync(kFull, hit[i]);
-      if (!hm) continue;
-      WSR_STAT(st.matches += __popc(hm););
-      WSR_STAT(st.bytes += (8ull * m + 1ull) * __popc(hm););
-      if (COLLECT) CollectAppend(bv, q, qi, hit[i], (int)d[i], s64[i], lane);
-      else OfferToTopK(bv, qi, multi, k, hit[i], s64[i], (int)d[i], top, published, lane);
-    }
+    cur = nxt;
   }
+  if (nc && more) MultiBatch<COLLECT>(ix, bv, q, qi, sh, ws, 0, nc, top, published, multi, lane, st);
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
 }
 
-template <int CLASS> struct ScratchOf { typedef ProbeScratch type; };
+template <int CLASS> struct ScratchOf { typedef MultiScratch type; };
 template <> struct ScratchOf<kClassOne> { typedef NoScratch type; };
+template <> struct ScratchOf<kClassTwo> { typedef ProbeScratch type; };
 
 // Persistent search kernel of one query class: warps drain the class's unit queue.
 template <int CLASS, bool STATS>
@@ -1110,11 +1077,11 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
     } else if constexpr (CLASS == kClassTwo) {
       ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     } else if constexpr (CLASS == kClassMany) {
-      ProcessMulti<WSR_MAX_TERMS, false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
+      ProcessMulti<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     } else {
       if (q.n_terms == 1) ProcessOneTerm<true>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
-      else if (q.n_terms == 2) ProcessTwo<true>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
-      else ProcessMulti<WSR_MAX_TERMS, true>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
+      else if (q.n_terms == 2) ProcessTwo<true>(ix, bv, q, qi, local, b0, b1, &sh, &ws->ps, lane, st);
+      else ProcessMulti<true>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     }
     units++;
   }
