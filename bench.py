@@ -12,8 +12,9 @@ One STEP = one pass of the whole query log through the engine.
 
 value  = listed postings/s (unit of SURVEY §8d: sum of the df of every query term), inputs
          resident in HBM, device-timed with CUDA events on the launching stream.
-e2e    = the same metric through the host-buffer C-ABI call: query-log text -> term lookup ->
-         wsr_search_batch (H2D of the planned batch, kernels, D2H of the top-k) per step.
+e2e    = the same metric through the host-buffer C-ABI call wsr_search_log: pinned query-log
+         text -> H2D -> parse/term-lookup/planning kernels -> search kernels -> D2H of the top-k
+         into pinned host buffers, every step (N>1: wsr_batch_reset_log + NCCL all-gather + merge).
 roofline = algorithmic bytes of the blocks the dominant kernel actually read (B_touched,
          SURVEY §8d) / its CUDA-event duration, against the measured HBM copy bandwidth.
 cpu_baseline = the unmodified reference engine (oracle/_ref/ref_tool, kind "reference"; the
