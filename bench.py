@@ -285,7 +285,7 @@ def workload_config(a, cinfo, sample_queries=None, n_gpus=1):
                      f"{a.workload} query log ({sample_queries or a.queries} queries/step, "
                      f"gen_synthetic_log.py-style, high df >= {a.high_df}); BM25 AND top-{a.k}"),
         "docs_per_gpu": a.docs, "postings_per_gpu": cinfo["postings"], "queries_per_step": sample_queries or a.queries,
-        "k": a.k, "partitioning": f"document-partitioned x{n_gpus}" if n_gpus > 1 else "single index",
+        "k": a.k, "partitioning": (f"document-partitioned x{n_gpus}, top-k exchange: all-to-all of query slices + slice merge + all-gather" if n_gpus > 1 else "single index"),
         "l2": "inputs larger than L2: one step streams GBs of distinct posting blocks (126 MB L2)",
     }
 
@@ -466,6 +466,27 @@ def ours(a, rank, world, local_rank):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    if world > 1:
+        # cross-check of the exchange (outside every timed region): the scatter exchange used in
+        # the timed steps must give, on every rank, what a plain all-gather + full merge gives
+        batch.run()
+        shard.gather_merge(batch)
+        h_sc, n_sc = shard.fetch_merged(batch)
+        h_sc, n_sc = h_sc.copy(), n_sc.copy()
+        used = shard.exchange
+        shard.exchange = "allgather"
+        batch.run()
+        shard.gather_merge(batch)
+        h_ag, n_ag = shard.fetch_merged(batch)
+        shard.exchange = used
+        assert np.array_equal(n_sc, n_ag), "scatter and all-gather exchanges disagree on hit counts"
+        m = np.arange(a.k)[None, :] < n_ag[:, None]
+        assert np.array_equal(h_sc["doc_id"][m], h_ag["doc_id"][m])
+        assert np.array_equal(h_sc["score"][m].view(np.uint64), h_ag["score"][m].view(np.uint64))
+        # ... and the e2e path (device front end) the same
+        he = hits_t.numpy().view(HIT_DTYPE).reshape(n, a.k)
+        assert np.array_equal(nh_t.numpy(), n_ag)
+        assert np.array_equal(he["doc_id"][m], h_ag["doc_id"][m])
     if world == 1:
         # the e2e path (device front end) must return exactly what the device-timed batch did
         hb, nb = batch.fetch()

@@ -91,3 +91,68 @@ def test_combine_partition_stats_is_order_stable():
     total, bases, avg = combine_partition_stats([5, 7, 9], [10.0, 20.0, 30.0])
     assert total == 21 and bases == [0, 5, 12]
     assert avg == ((10.0 * 5 + 20.0 * 7) + 30.0 * 9) / 21
+
+
+def _scatter_worker(rank, world, port, n, k, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wiser_b200.dist import exchange_slices, merge_topk_host, slice_bounds
+    from wiser_b200.capi import HIT_DTYPE
+    # every shard's top-k of n queries (seeded per shard; doc ids disjoint between shards)
+    rng = np.random.default_rng(100 + rank)
+    hits = np.zeros((n, k), HIT_DTYPE)
+    nh = rng.integers(0, k + 1, n).astype(np.int32)
+    for i in range(n):
+        sc = np.sort(rng.integers(1, 50, nh[i]).astype(np.float64))[::-1]     # many ties across shards
+        hits["score"][i, :nh[i]] = sc
+        hits["doc_id"][i, :nh[i]] = rank * 100000 + np.sort(rng.choice(1000, nh[i], replace=False))
+    s, lo = slice_bounds(n, world)
+    recv_h = torch.zeros(world * max(1, s) * k * 16, dtype=torch.uint8)
+    recv_n = torch.zeros(world * max(1, s), dtype=torch.int32)
+    mine = exchange_slices(torch.from_numpy(hits.view(np.uint8).reshape(-1).copy()), torch.from_numpy(nh.copy()),
+                           n, k, rank, world, recv_h, recv_n)
+    assert mine == lo[rank + 1] - lo[rank]
+    g = recv_h[:world * mine * k * 16].numpy().view(HIT_DTYPE).reshape(world, mine, k)
+    gn = recv_n[:world * mine].numpy().reshape(world, mine)
+    m_h, m_n = merge_topk_host(g, gn, k)
+    # all-gather of the merged (padded) slices: the first n queries of the result are in order
+    pad_h = np.zeros((max(1, s), k), HIT_DTYPE)
+    pad_n = np.zeros(max(1, s), np.int32)
+    pad_h[:mine], pad_n[:mine] = m_h, m_n
+    full_h = [torch.zeros(max(1, s) * k * 16, dtype=torch.uint8) for _ in range(world)]
+    full_n = [torch.zeros(max(1, s), dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(full_h, torch.from_numpy(pad_h.view(np.uint8).reshape(-1).copy()))
+    dist.all_gather(full_n, torch.from_numpy(pad_n.copy()))
+    res_h = torch.cat(full_h).numpy().view(HIT_DTYPE).reshape(-1, k)[:n]
+    res_n = torch.cat(full_n).numpy()[:n]
+    # checker: the plain all-gather of everything, merged in one piece
+    all_h = [torch.zeros(n * k * 16, dtype=torch.uint8) for _ in range(world)]
+    all_n = [torch.zeros(n, dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(all_h, torch.from_numpy(hits.view(np.uint8).reshape(-1).copy()))
+    dist.all_gather(all_n, torch.from_numpy(nh.copy()))
+    ref_h, ref_n = merge_topk_host(np.stack([t.numpy().view(HIT_DTYPE).reshape(n, k) for t in all_h]),
+                                   np.stack([t.numpy() for t in all_n]), k)
+    ok = bool(np.array_equal(res_n, ref_n))
+    for i in range(n):
+        ok = ok and np.array_equal(res_h[i, :ref_n[i]], ref_h[i, :ref_n[i]])
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,k", [(7, 3), (8, 10), (1, 2), (33, 1)])
+def test_scatter_exchange_equals_allgather_merge_world2(n, k):
+    """The scatter exchange (all-to-all of query slices -> slice merge -> all-gather of merged
+    slices) returns what merging a plain all-gather returns, for ragged and tiny batches."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() + 17 * n + k) % 300
+    ps = [ctx.Process(target=_scatter_worker, args=(r, 2, port, n, k, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+    assert got == [(0, True), (1, True)]
