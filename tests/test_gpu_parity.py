@@ -208,21 +208,25 @@ def test_partition_directories_with_global_stats(golden_dir):
 
 
 def test_generated_corpus_vs_oracle(tmp_path):
-    """A 60k-doc corpus from the native generator (multi-thousand-posting lists, skewed AND,
-    3-5 term queries): GPU top-10 vs the CPU oracle on the same directory, bit-exact scores."""
+    """A 200k-doc corpus from the native generator (multi-thousand-posting lists, skewed AND,
+    3-5 term queries, phrases; doc ids beyond 2^16, so sparse lists have blocks spanning more than
+    65536 docs: 32-bit record heads, 16-byte records, the probe's wide-block path): GPU top-10 vs
+    the CPU oracle on the same directory, bit-exact scores."""
     import subprocess
     import gen_query_log
     from wiser_b200 import GpuVacuumEngine, SearchQuery
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     d = str(tmp_path / "c")
-    subprocess.check_call([os.path.join(root, "wiser_b200", "wsr_gen_corpus"), "--out", d, "--docs", "60000",
-                           "--vocab", "80000", "--seed", "11", "--positions", "1"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([os.path.join(root, "wiser_b200", "wsr_gen_corpus"), "--out", d, "--docs", "200000",
+                           "--vocab", "150000", "--seed", "11", "--positions", "1"], stdout=subprocess.DEVNULL)
     groups = gen_query_log.load_groups(os.path.join(d, "terms.txt"), 3000)
     lines = (gen_query_log.generate("two_term", groups, 400, 1) +
              gen_query_log.generate("two_term_hh", groups, 150, 2) +
              gen_query_log.generate("multi_term", groups, 150, 3) +
              gen_query_log.generate("single_high", groups, 60, 4) +
              gen_query_log.generate("single_low", groups, 60, 5) +
+             gen_query_log.generate("two_term_ll", groups, 300, 8) +
+             gen_query_log.generate("two_term_lh", groups, 200, 9) +
              gen_query_log.generate("phrase2", groups, 200, 6) +
              gen_query_log.generate("phrase3", groups, 80, 7))
     eng = GpuVacuumEngine(d).Load()
