@@ -1164,7 +1164,7 @@ int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q
 
 bool DeviceFrontEndUsable(const wsr_index *idx, size_t len, int k) {
   static const bool host_frontend = getenv("WSR_HOST_FRONTEND") && atoi(getenv("WSR_HOST_FRONTEND")) != 0;
-  return !host_frontend && idx->dict_on_device && k <= kMaxFastK && len > 0 && len < 0xfffffff0ull;
+  return !host_frontend && idx->dict_on_device && k <= kMaxFastK && len > 0 && len < 0x7ffffff0ull;   // cub counts in int
 }
 
 int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
