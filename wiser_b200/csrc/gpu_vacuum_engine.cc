@@ -29,14 +29,6 @@ GpuVacuumEngine::GpuVacuumEngine(const std::string engine_dir_path, int bloom_en
     : dir_(engine_dir_path), bloom_enable_factor_(bloom_enable_factor), opt_(opt) {}
 
 GpuVacuumEngine::~GpuVacuumEngine() {
-  if (batcher_.joinable()) {
-    {
-      std::lock_guard<std::mutex> g(mu_);
-      stop_ = true;
-    }
-    cv_submit_.notify_all();
-    batcher_.join();
-  }
   if (idx_) wsr_index_close(idx_);
 }
 
@@ -46,7 +38,6 @@ void GpuVacuumEngine::Load() {
   idx_ = wsr_index_open_ex(dir_.c_str(), opt_.device, opt_.shard, opt_.n_shards, opt_.loader_threads,
                            opt_.load_positions ? WSR_OPEN_POSITIONS : 0u, err, sizeof(err));
   if (!idx_) Fatal(std::string("wsr_index_open: ") + err);
-  batcher_ = std::thread([this]() { BatcherLoop(); });
 }
 
 int GpuVacuumEngine::TermCount() const {
@@ -95,8 +86,31 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
   {
     std::unique_lock<std::mutex> lk(mu_);
     pending_.push_back(&p);
-    cv_submit_.notify_one();
-    cv_done_.wait(lk, [&]() { return p.done; });
+    std::vector<Pending *> take;
+    while (!p.done) {
+      if (inflight_ < std::max(1, opt_.max_inflight) && !pending_.empty()) {
+        // lead: everything queued so far (this caller is in it unless another leader took it)
+        inflight_++;
+        if (opt_.coalesce_window_us > 0 && (int)pending_.size() < opt_.coalesce_max_batch)
+          cv_.wait_for(lk, std::chrono::microseconds(opt_.coalesce_window_us),
+                       [&]() { return (int)pending_.size() >= opt_.coalesce_max_batch; });
+        take.clear();
+        if ((int)pending_.size() <= opt_.coalesce_max_batch) {
+          take.swap(pending_);
+        } else {
+          take.assign(pending_.begin(), pending_.begin() + opt_.coalesce_max_batch);
+          pending_.erase(pending_.begin(), pending_.begin() + opt_.coalesce_max_batch);
+        }
+        lk.unlock();
+        RunBatch(take);
+        lk.lock();
+        for (Pending *t : take) t->done = true;
+        inflight_--;
+        cv_.notify_all();
+      } else {
+        cv_.wait(lk);
+      }
+    }
   }
   if (p.rc != 0) Fatal(std::string("wsr_search_batch: ") + wsr_last_error());
   for (int i = 0; i < p.n_hits; i++) {
@@ -108,47 +122,26 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
   return result;
 }
 
-// The batch scheduler's front half: gathers concurrent Search() callers for up to
-// coalesce_window_us (or coalesce_max_batch requests) and submits them as ONE GPU batch.
-void GpuVacuumEngine::BatcherLoop() {
-  std::vector<Pending *> take;
-  std::vector<wsr_query> qs;
-  std::vector<wsr_hit> hits;
-  std::vector<int32_t> n_hits;
-  for (;;) {
-    {
-      std::unique_lock<std::mutex> lk(mu_);
-      cv_submit_.wait(lk, [&]() { return stop_ || !pending_.empty(); });
-      if (stop_ && pending_.empty()) return;
-      if ((int)pending_.size() < opt_.coalesce_max_batch && opt_.coalesce_window_us > 0) {
-        cv_submit_.wait_for(lk, std::chrono::microseconds(opt_.coalesce_window_us), [&]() {
-          return stop_ || (int)pending_.size() >= opt_.coalesce_max_batch;
-        });
-      }
-      take.swap(pending_);
-    }
-    uint32_t k_stride = 1;
-    qs.clear();
-    for (Pending *p : take) {
-      qs.push_back(p->q);
-      if (p->q.k > k_stride) k_stride = p->q.k;
-    }
-    hits.resize(qs.size() * (size_t)k_stride);
-    n_hits.assign(qs.size(), 0);
-    const int rc = wsr_search_batch(idx_, qs.data(), (int)qs.size(), (int)k_stride, hits.data(),
-                                    n_hits.data(), nullptr, nullptr);
-    {
-      std::lock_guard<std::mutex> g(mu_);
-      for (size_t i = 0; i < take.size(); i++) {
-        Pending *p = take[i];
-        p->rc = rc;
-        p->n_hits = rc == 0 ? n_hits[i] : 0;
-        for (int j = 0; j < p->n_hits; j++) p->hits[j] = hits[i * (size_t)k_stride + j];
-        p->done = true;
-      }
-    }
-    cv_done_.notify_all();
-    take.clear();
+// One coalesced batch on the calling (leader) thread: submit, then hand every caller its hits.
+void GpuVacuumEngine::RunBatch(const std::vector<Pending *> &take) {
+  thread_local std::vector<wsr_query> qs;
+  thread_local std::vector<wsr_hit> hits;
+  thread_local std::vector<int32_t> n_hits;
+  uint32_t k_stride = 1;
+  qs.clear();
+  for (Pending *p : take) {
+    qs.push_back(p->q);
+    if (p->q.k > k_stride) k_stride = p->q.k;
+  }
+  hits.resize(qs.size() * (size_t)k_stride);
+  n_hits.assign(qs.size(), 0);
+  const int rc = wsr_search_batch(idx_, qs.data(), (int)qs.size(), (int)k_stride, hits.data(),
+                                  n_hits.data(), nullptr, nullptr);
+  for (size_t i = 0; i < take.size(); i++) {
+    Pending *p = take[i];
+    p->rc = rc;
+    p->n_hits = rc == 0 ? n_hits[i] : 0;
+    for (int j = 0; j < p->n_hits; j++) p->hits[j] = hits[i * (size_t)k_stride + j];
   }
 }
 

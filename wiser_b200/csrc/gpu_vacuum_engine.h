@@ -79,7 +79,10 @@ struct GpuEngineOptions {
   int loader_threads = 0;            // 0 = all cores
   bool load_positions = true;        // position column in HBM: needed by phrase queries
   int coalesce_max_batch = 4096;     // Search() callers coalesced per launch
-  int coalesce_window_us = 100;      // how long the batcher waits for more callers
+  int coalesce_window_us = 0;        // extra wait for more callers before a launch (0: none —
+                                     // callers that arrive while a batch runs form the next one)
+  int max_inflight = 2;              // batches in flight at once (host work of one overlaps the
+                                     // GPU work of the other)
 };
 
 class GpuVacuumEngine : public SearchEngineServiceNew {
@@ -92,8 +95,11 @@ class GpuVacuumEngine : public SearchEngineServiceNew {
   void Load() override;
   int TermCount() const override;
   std::map<std::string, int> PostinglistSizes(const TermList &terms) override;
-  // Re-entrant: concurrent callers are coalesced into one GPU batch (the reference serves
-  // Search from N threads on one shared engine, grpc_server_impl.h:309-328).
+  // Re-entrant: concurrent callers are coalesced into GPU batches (the reference serves Search
+  // from N threads on one shared engine, grpc_server_impl.h:309-328). Leader/follower combining:
+  // a caller that finds fewer than max_inflight batches running takes everything queued
+  // (itself included), runs it as one batch on its own thread and wakes the others; callers
+  // arriving meanwhile form the next batch. A lone caller pays no hand-off at all.
   SearchResult Search(const SearchQuery &query) override;
   // As VacuumEngine (vacuum_engine.h:260-276): not implemented, fatal.
   void AddDocument(const DocInfo doc_info) override;
@@ -109,7 +115,7 @@ class GpuVacuumEngine : public SearchEngineServiceNew {
  private:
   struct Pending;
   bool ToWsrQuery(const SearchQuery &q, wsr_query *out) const;
-  void BatcherLoop();
+  void RunBatch(const std::vector<Pending *> &take);
 
   std::string dir_;
   int bloom_enable_factor_;
@@ -117,10 +123,9 @@ class GpuVacuumEngine : public SearchEngineServiceNew {
   wsr_index *idx_ = nullptr;
   // request coalescer
   std::mutex mu_;
-  std::condition_variable cv_submit_, cv_done_;
+  std::condition_variable cv_;
   std::vector<Pending *> pending_;
-  std::thread batcher_;
-  bool stop_ = false;
+  int inflight_ = 0;
 };
 
 // engine_factory.h:33-50 extended with the gpu: scheme; throws std::runtime_error otherwise.

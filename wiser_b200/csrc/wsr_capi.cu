@@ -202,12 +202,16 @@ struct wsr_batch {
   uint32_t launches = 0;
   // device
   DevBuf<DevQuery> d_queries;
-  DevBuf<wsr_hit> d_hits;
-  DevBuf<int32_t> d_n_hits;
+  // results: ONE allocation [hits n*k_stride | n_hits n | DevCounters] so that one memset clears
+  // counts + counters and one D2H brings hits + counts back
+  DevBuf<uint8_t> d_out;
+  wsr_hit *out_hits = nullptr;
+  int32_t *out_n = nullptr;
+  DevCounters *out_cnt = nullptr;
+  size_t out_hits_bytes = 0, out_n_bytes = 0;
   DevBuf<wsr_hit> d_cand;
   DevBuf<int32_t> d_cand_n;
   DevBuf<unsigned long long> d_thr;
-  DevBuf<DevCounters> d_counters;
   DevBuf<uint32_t> d_multi;
   DevBuf<int32_t> d_seg_doc, d_seg_doc_tmp;
   DevBuf<double> d_seg_score, d_seg_score_tmp;
@@ -224,8 +228,7 @@ struct wsr_batch {
   PinnedBuf<uint32_t> h_totals;        // PlanItem (8 words) + error bits
   // pinned staging for the host-buffer API
   PinnedBuf<DevQuery> h_queries;
-  PinnedBuf<wsr_hit> h_hits;
-  PinnedBuf<int32_t> h_n_hits;
+  PinnedBuf<uint8_t> h_out;            // same layout as d_out (hits | n_hits)
   PinnedBuf<uint32_t> h_multi;
   BatchView view;
 };
@@ -382,12 +385,15 @@ int PrepareBatch(wsr_batch *b, bool plan_on_host) {
     CU(b->d_queries.Ensure(np + 1));
     CU(b->d_multi.Ensure((size_t)b->n_multi + 1));
   }
-  CU(b->d_hits.Ensure((size_t)b->n * b->k_stride + 1));
-  CU(b->d_n_hits.Ensure((size_t)b->n + 1));
+  b->out_hits_bytes = ((size_t)b->n * b->k_stride * sizeof(wsr_hit) + 15) / 16 * 16;
+  b->out_n_bytes = ((size_t)b->n * 4 + 4 + 15) / 16 * 16;
+  CU(b->d_out.Ensure(b->out_hits_bytes + b->out_n_bytes + sizeof(DevCounters) + 16));
+  b->out_hits = reinterpret_cast<wsr_hit *>(b->d_out.p);
+  b->out_n = reinterpret_cast<int32_t *>(b->d_out.p + b->out_hits_bytes);
+  b->out_cnt = reinterpret_cast<DevCounters *>(b->d_out.p + b->out_hits_bytes + b->out_n_bytes);
   CU(b->d_cand.Ensure((size_t)b->n_cand_units * kMaxFastK + 1));
   CU(b->d_cand_n.Ensure((size_t)b->n_cand_units + 1));
   CU(b->d_thr.Ensure(np + 1));
-  CU(b->d_counters.Ensure(1));
   if (b->n_collect) {
     CU(b->d_seg_doc.Ensure(b->n_seg_entries + 1));
     CU(b->d_seg_doc_tmp.Ensure(b->n_seg_entries + 1));
@@ -403,12 +409,12 @@ int PrepareBatch(wsr_batch *b, bool plan_on_host) {
   v.queries = b->d_queries.p;
   for (int c = 0; c < 5; c++) v.class_begin[c] = b->class_begin[c];
   for (int c = 0; c < 4; c++) v.class_units[c] = b->class_units[c];
-  v.hits = b->d_hits.p;
-  v.n_hits = b->d_n_hits.p;
+  v.hits = b->out_hits;
+  v.n_hits = b->out_n;
   v.cand = b->d_cand.p;
   v.cand_n = b->d_cand_n.p;
   v.thr = b->d_thr.p;
-  v.counters = b->d_counters.p;
+  v.counters = b->out_cnt;
   v.k_stride = (uint32_t)b->k_stride;
   v.doc_base = b->idx->doc_base;
   v.seg_doc = b->d_seg_doc.p;
@@ -441,8 +447,7 @@ int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr, bool count_work = false)
   // [5] after merge + collect epilogue
   const size_t np = b->np;
   uint32_t launches = 0;
-  CU(cudaMemsetAsync(b->d_n_hits.p, 0, (size_t)b->n * sizeof(int32_t) + 4, b->stream));
-  CU(cudaMemsetAsync(b->d_counters.p, 0, sizeof(DevCounters), b->stream));
+  CU(cudaMemsetAsync(b->out_n, 0, b->out_n_bytes + sizeof(DevCounters), b->stream));   // counts + counters
   if (b->n_multi) CU(cudaMemsetAsync(b->d_thr.p, 0, np * 8, b->stream));
   if (b->n_collect) CU(cudaMemsetAsync(b->d_seg_count.p, 0, np * 4, b->stream));
   if (ev) CU(cudaEventRecord(ev[0], b->stream));
@@ -892,28 +897,27 @@ int wsr_batch_fetch(wsr_batch *b, wsr_hit *hits, int32_t *n_hits) {
   if (!b) return Fail(WSR_ERR_ARG, "null batch");
   CU(cudaSetDevice(b->idx->device));
   const size_t nh = (size_t)b->n * b->k_stride;
-  if (hits && nh) {
-    if (IsPinned(hits)) {
-      CU(cudaMemcpyAsync(hits, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
-    } else {
-      CU(b->h_hits.Ensure(nh));
-      CU(cudaMemcpyAsync(b->h_hits.p, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
-    }
+  const bool direct = hits && n_hits && IsPinned(hits) && IsPinned(n_hits);
+  if (direct) {        // DMA straight into the caller's pinned buffers
+    if (nh) CU(cudaMemcpyAsync(hits, b->out_hits, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+    if (b->n) CU(cudaMemcpyAsync(n_hits, b->out_n, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return WSR_OK;
   }
-  if (n_hits && b->n) {
-    CU(b->h_n_hits.Ensure(b->n));
-    CU(cudaMemcpyAsync(b->h_n_hits.p, b->d_n_hits.p, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
-  }
+  // one D2H of [hits | n_hits] into pinned staging, then out to the caller's arrays
+  const size_t bytes = b->out_hits_bytes + (size_t)b->n * 4;
+  CU(b->h_out.Ensure(bytes + 16));
+  if (b->n) CU(cudaMemcpyAsync(b->h_out.p, b->d_out.p, bytes, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
-  if (hits && nh && !IsPinned(hits)) memcpy(hits, b->h_hits.p, nh * sizeof(wsr_hit));
-  if (n_hits && b->n) memcpy(n_hits, b->h_n_hits.p, (size_t)b->n * 4);
+  if (hits && nh) memcpy(hits, b->h_out.p, nh * sizeof(wsr_hit));
+  if (n_hits && b->n) memcpy(n_hits, b->h_out.p + b->out_hits_bytes, (size_t)b->n * 4);
   return WSR_OK;
 }
 
 int wsr_batch_device_results(wsr_batch *b, void **d_hits, void **d_n_hits, void **stream) {
   if (!b) return Fail(WSR_ERR_ARG, "null batch");
-  if (d_hits) *d_hits = b->d_hits.p;
-  if (d_n_hits) *d_n_hits = b->d_n_hits.p;
+  if (d_hits) *d_hits = b->out_hits;
+  if (d_n_hits) *d_n_hits = b->out_n;
   if (stream) *stream = (void *)b->stream;
   return WSR_OK;
 }
@@ -1043,7 +1047,7 @@ int wsr_batch_get_stats(wsr_batch *b, wsr_batch_stats *s) {
   if (!b || !s) return Fail(WSR_ERR_ARG, "null argument");
   CU(cudaSetDevice(b->idx->device));
   DevCounters c;
-  CU(cudaMemcpyAsync(&c, b->d_counters.p, sizeof(c), cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaMemcpyAsync(&c, b->out_cnt, sizeof(c), cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
   s->listed_postings = b->listed_postings;
   s->listed_bytes = b->listed_bytes;
@@ -1182,17 +1186,16 @@ int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_h
   const size_t nh = (size_t)n * k;
   const bool pinned = IsPinned(hits) && IsPinned(n_hits);
   if (pinned) {
-    CU(cudaMemcpyAsync(hits, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaMemcpyAsync(n_hits, b->d_n_hits.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(hits, b->out_hits, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(n_hits, b->out_n, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
   } else {
-    CU(b->h_hits.Ensure(nh + 1));
-    CU(b->h_n_hits.Ensure((size_t)n + 1));
-    CU(cudaMemcpyAsync(b->h_hits.p, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaMemcpyAsync(b->h_n_hits.p, b->d_n_hits.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+    const size_t bytes = b->out_hits_bytes + (size_t)n * 4;
+    CU(b->h_out.Ensure(bytes + 16));
+    CU(cudaMemcpyAsync(b->h_out.p, b->d_out.p, bytes, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
-    memcpy(hits, b->h_hits.p, nh * sizeof(wsr_hit));
-    memcpy(n_hits, b->h_n_hits.p, (size_t)n * 4);
+    memcpy(hits, b->h_out.p, nh * sizeof(wsr_hit));
+    memcpy(n_hits, b->h_out.p + b->out_hits_bytes, (size_t)n * 4);
   }
   *n_queries = (int)n;
   return WSR_OK;
@@ -1228,8 +1231,8 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
     if (!pend[s].live) return WSR_OK;
     CU(cudaStreamSynchronize(bt[s]->stream));
     if (!pinned) {
-      memcpy(hits + (size_t)pend[s].q0 * k, bt[s]->h_hits.p, (size_t)pend[s].n * k * sizeof(wsr_hit));
-      memcpy(n_hits + pend[s].q0, bt[s]->h_n_hits.p, (size_t)pend[s].n * 4);
+      memcpy(hits + (size_t)pend[s].q0 * k, bt[s]->h_out.p, (size_t)pend[s].n * k * sizeof(wsr_hit));
+      memcpy(n_hits + pend[s].q0, bt[s]->h_out.p + bt[s]->out_hits_bytes, (size_t)pend[s].n * 4);
     }
     pend[s].live = false;
     return WSR_OK;
@@ -1259,13 +1262,12 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
     if (rc) break;
     const size_t nh = (size_t)n * k;
     if (pinned) {
-      if (nh) CU(cudaMemcpyAsync(hits + (size_t)done_q * k, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
-      if (n) CU(cudaMemcpyAsync(n_hits + done_q, b->d_n_hits.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+      if (nh) CU(cudaMemcpyAsync(hits + (size_t)done_q * k, b->out_hits, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
+      if (n) CU(cudaMemcpyAsync(n_hits + done_q, b->out_n, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
     } else {
-      CU(b->h_hits.Ensure(nh + 1));
-      CU(b->h_n_hits.Ensure((size_t)n + 1));
-      if (nh) CU(cudaMemcpyAsync(b->h_hits.p, b->d_hits.p, nh * sizeof(wsr_hit), cudaMemcpyDeviceToHost, b->stream));
-      if (n) CU(cudaMemcpyAsync(b->h_n_hits.p, b->d_n_hits.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+      const size_t bytes = b->out_hits_bytes + (size_t)n * 4;
+      CU(b->h_out.Ensure(bytes + 16));
+      if (n) CU(cudaMemcpyAsync(b->h_out.p, b->d_out.p, bytes, cudaMemcpyDeviceToHost, b->stream));
     }
     pend[s].q0 = done_q;
     pend[s].n = n;
