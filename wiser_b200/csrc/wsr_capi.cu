@@ -255,6 +255,23 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
   std::vector<Part> part(T);
   b->tmp.resize((size_t)n);
   b->tmp_cls.resize((size_t)n);
+  // Small batches (the Search() serving path) cannot fill the GPU with 64-block units: one warp
+  // would walk a long list alone while thousands idle, and the query's latency is that walk.
+  // Cap the unit size so that the batch yields about one unit per resident warp.
+  uint64_t unit_cap = kUnitBlocks;
+  if (n <= 1024) {
+    uint64_t drv_blocks = 0;
+    for (int i = 0; i < n; i++) {
+      const wsr_query &q = queries[i];
+      if (q.n_terms < 2 || q.n_terms > WSR_MAX_TERMS) continue;
+      uint32_t best = 0xffffffffu;
+      for (uint32_t t2 = 0; t2 < q.n_terms; t2++)
+        if (q.term_ids[t2] < n_terms_index) best = std::min(best, ix->host.lists[q.term_ids[t2]].n_blocks);
+      if (best != 0xffffffffu) drv_blocks += best;
+    }
+    const uint64_t warps = (uint64_t)ix->sm_count * 32;
+    unit_cap = std::max<uint64_t>(4, std::min<uint64_t>(kUnitBlocks, drv_blocks / warps + 1));
+  }
   auto classify = [&](int t, int TT) {
     Part &p = part[t];
     const int lo = (int)((int64_t)n * t / TT), hi = (int)((int64_t)n * (t + 1) / TT);
@@ -295,7 +312,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
       // Unit size: a unit's work is its driver blocks plus the probe-list blocks they can
       // reach, so skewed queries (long probe lists) get fewer driver blocks per unit.
       const uint64_t ratio = drv.n_blocks ? (probe_blocks + drv.n_blocks - 1) / drv.n_blocks : 0;
-      const uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(kUnitBlocks, (uint64_t)kUnitBudget / (1 + ratio)));
+      const uint32_t ub = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(unit_cap, (uint64_t)kUnitBudget / (1 + ratio)));
       dq.unit_blocks = (uint16_t)ub;
       dq.n_units = (drv.n_blocks + ub - 1) / ub;
       const int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
