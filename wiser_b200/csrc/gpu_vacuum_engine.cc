@@ -22,6 +22,10 @@ struct GpuVacuumEngine::Pending {
   int32_t n_hits = 0;
   bool done = false;
   int rc = 0;
+  // own wake-up: a finished batch wakes exactly its callers. The condition variable belongs to
+  // the calling THREAD (shared ownership), so a leader may notify after releasing the lock
+  // without racing the caller's return.
+  std::shared_ptr<std::condition_variable> cv;
 };
 
 GpuVacuumEngine::GpuVacuumEngine(const std::string engine_dir_path, int bloom_enable_factor,
@@ -83,7 +87,10 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
     result.doc_freqs.push_back((int)df);
   }
   p.hits.resize(p.q.k);
+  thread_local std::shared_ptr<std::condition_variable> my_cv = std::make_shared<std::condition_variable>();
+  p.cv = my_cv;
   {
+    std::vector<std::shared_ptr<std::condition_variable>> wake;
     std::unique_lock<std::mutex> lk(mu_);
     pending_.push_back(&p);
     std::vector<Pending *> take;
@@ -92,8 +99,8 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
         // lead: everything queued so far (this caller is in it unless another leader took it)
         inflight_++;
         if (opt_.coalesce_window_us > 0 && (int)pending_.size() < opt_.coalesce_max_batch)
-          cv_.wait_for(lk, std::chrono::microseconds(opt_.coalesce_window_us),
-                       [&]() { return (int)pending_.size() >= opt_.coalesce_max_batch; });
+          p.cv->wait_for(lk, std::chrono::microseconds(opt_.coalesce_window_us),
+                        [&]() { return (int)pending_.size() >= opt_.coalesce_max_batch; });
         take.clear();
         if ((int)pending_.size() <= opt_.coalesce_max_batch) {
           take.swap(pending_);
@@ -104,11 +111,19 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
         lk.unlock();
         RunBatch(take);
         lk.lock();
-        for (Pending *t : take) t->done = true;
         inflight_--;
-        cv_.notify_all();
+        wake.clear();
+        for (Pending *t : take) {
+          t->done = true;
+          if (t != &p) wake.push_back(t->cv);
+        }
+        // hand the free slot to a queued caller (arrivals that find a free slot lead themselves)
+        if (!pending_.empty()) wake.push_back(pending_.front()->cv);
+        lk.unlock();
+        for (auto &c : wake) c->notify_one();     // outside the lock: woken callers do not pile up on it
+        lk.lock();
       } else {
-        cv_.wait(lk);
+        p.cv->wait(lk);
       }
     }
   }

@@ -123,7 +123,6 @@ class GpuVacuumEngine : public SearchEngineServiceNew {
   wsr_index *idx_ = nullptr;
   // request coalescer
   std::mutex mu_;
-  std::condition_variable cv_;
   std::vector<Pending *> pending_;
   int inflight_ = 0;
 };
