@@ -29,3 +29,20 @@ def test_replay_driver_matches_reference(golden_dir, tmp_path, mode, extra):
     for line, (gd, gs, gdf), (rd, rs, rdf), (fd, fs, _) in zip(lines, got, ref, full):
         assert gdf == rdf, line
         check_topk(rd, rs, gd, gs, fd, fs, what=line)
+
+
+def test_replay_batchlog_timing_passes_use_the_device_front_end(golden_dir, tmp_path):
+    """-repeat=3 with -dump: pass 0 goes through wsr_search_batch (it needs doc_freqs), passes 1-2
+    send the log text through wsr_search_log (GPU front end); all passes must find the same hits."""
+    import json
+    d = os.path.join(golden_dir, "zipf2k")
+    out = str(tmp_path / "dump.txt")
+    log = subprocess.check_output([REPLAY, f"-engine=gpu:vacuum_dump:{d}", f"-query_path={d}/queries.txt",
+                                   "-n_results=10", "-exp_mode=batchlog", "-batch_size=700", "-repeat=3",
+                                   f"-dump={out}"]).decode()
+    js = json.loads([l for l in log.split("\n") if l.startswith("WSR_REPLAY_JSON")][0][len("WSR_REPLAY_JSON"):])
+    got = read_ref_results(out)
+    one_pass = sum(len(g[0]) for g in got)
+    assert js["queries"] == 3 * len(got)
+    assert js["result_entries"] == 3 * one_pass
+    assert js["listed_postings"] == 3 * sum(sum(g[2]) for g in got)

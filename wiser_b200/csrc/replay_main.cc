@@ -8,7 +8,9 @@
 //
 //   -engine=gpu:vacuum_dump:<dir>   engine URL (engine_factory.h scheme + gpu:)
 //   -query_path=<file>              query log
-//   -exp_mode=batchlog|locallog     batchlog: whole log through wsr_search_batch in batches
+//   -exp_mode=batchlog|locallog     batchlog: whole log in batches of -batch_size lines through
+//                                             wsr_search_log (text -> GPU front end); the pass that
+//                                             writes -dump uses wsr_search_batch (it needs doc_freqs)
 //                                   locallog: n_threads client threads calling Search()
 //                                             (LocalLogTreatmentExecutor, engine_bench.cc:214-290)
 //   -n_threads=N  -n_results=K  -batch_size=B  -repeat=R  -dump=<file>
@@ -118,18 +120,49 @@ int main(int argc, char **argv) {
     std::vector<uint32_t> dfs((size_t)B * WSR_MAX_TERMS);
     std::vector<int32_t> ndf(B);
     if (!hits || !n_hits) { fprintf(stderr, "pinned alloc failed\n"); return 1; }
+    // line starts, so that a batch of B queries is a contiguous piece of the log text
+    std::vector<size_t> line_at;
+    for (size_t p = 0; p < text.size();) {
+      line_at.push_back(p);
+      const size_t e = text.find('\n', p);
+      p = e == std::string::npos ? text.size() : e + 1;
+    }
+    line_at.push_back(text.size());
+    // listed postings of one pass (sum of the df of every term of every answerable query)
+    uint64_t listed_per_rep = 0;
+    for (int i = 0; i < n; i++) {
+      const wsr_query &q = qs[i];
+      bool ok = q.k > 0 && q.n_terms > 0;
+      for (uint32_t t = 0; ok && t < q.n_terms; t++) ok = q.term_ids[t] != WSR_TERM_ABSENT;
+      for (uint32_t t = 0; ok && t < q.n_terms; t++) {
+        uint32_t df_t = 0;
+        wsr_term_at(idx, q.term_ids[t], nullptr, 0, &df_t);
+        listed_per_rep += df_t;
+      }
+    }
     const auto t0 = std::chrono::steady_clock::now();
     for (int rep = 0; rep < repeat; rep++) {
+      const bool dumping = df && rep == 0;
       for (int lo = 0; lo < n; lo += B) {
         const int m = std::min(B, n - lo);
-        if (wsr_search_batch(idx, qs.data() + lo, m, n_results, hits, n_hits, dfs.data(), ndf.data()) != 0) {
-          fprintf(stderr, "search: %s\n", wsr_last_error());
-          return 1;
+        if (dumping) {
+          // doc_freqs are wanted: host-parsed queries through wsr_search_batch
+          if (wsr_search_batch(idx, qs.data() + lo, m, n_results, hits, n_hits, dfs.data(), ndf.data()) != 0) {
+            fprintf(stderr, "search: %s\n", wsr_last_error());
+            return 1;
+          }
+        } else {
+          // timing passes: the text itself goes to the GPU (parse + lookup + plan as kernels)
+          int got = 0;
+          if (wsr_search_log(idx, text.data() + line_at[lo], line_at[lo + m] - line_at[lo], n_results, hits,
+                             n_hits, B, &got) != 0 || got != m) {
+            fprintf(stderr, "search_log: %s\n", wsr_last_error());
+            return 1;
+          }
         }
         for (int i = 0; i < m; i++) {
           entries += n_hits[i];
-          for (int t = 0; t < ndf[i]; t++) listed += dfs[(size_t)i * WSR_MAX_TERMS + t];
-          if (df && rep == 0) {
+          if (dumping) {
             fprintf(df, "%d %d", n_hits[i], ndf[i]);
             for (int j = 0; j < n_hits[i]; j++)
               fprintf(df, " %d %a", hits[(size_t)i * n_results + j].doc_id, hits[(size_t)i * n_results + j].score);
@@ -139,6 +172,7 @@ int main(int argc, char **argv) {
         }
         n_queries += m;
       }
+      listed += listed_per_rep;
     }
     secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     wsr_host_free(hits);
