@@ -65,6 +65,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-sample", type=int, default=200)
     ap.add_argument("--dir", default=os.environ.get("WSR_BENCH_DIR", "/tmp/wsr_bench"))
+    ap.add_argument("--query-filter", default="", choices=["", "dense_partner", "no_dense_partner"],
+                    help="analysis only: keep the queries whose longest list has df >= docs/16, or the others")
     return ap.parse_args()
 
 
@@ -92,6 +94,27 @@ def ensure_corpus(a, part=0, n_parts=1):
 
 
 def ensure_query_log(a, corpus_dir):
+    path = _ensure_query_log(a, corpus_dir)
+    if not a.query_filter:
+        return path
+    fpath = path[:-4] + f"_{a.query_filter}.txt"
+    if not os.path.exists(fpath):
+        df = {}
+        for line in open(os.path.join(corpus_dir, "terms.txt")):
+            t, d = line.split()
+            df[t] = int(d)
+        keep = []
+        for line in open(path):
+            dense = max(df.get(t, 0) for t in line.replace('"', "").split()) >= a.docs // 16
+            if dense == (a.query_filter == "dense_partner"):
+                keep.append(line)
+        with open(fpath, "w") as f:
+            f.writelines(keep)
+        log(f"filtered log {fpath}: {len(keep)} queries")
+    return fpath
+
+
+def _ensure_query_log(a, corpus_dir):
     import gen_query_log
     path = os.path.join(corpus_dir, f"q_{a.workload}_n{a.queries}_h{a.high_df}_s{a.seed}.txt")
     if not os.path.exists(path):
