@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of library variants on one box: args are variant[:ppw[:workload]]
+# Developer tool: A/B of library variants on one GPU box (same corpus, same log). Build variants as
+# _var/libwsr_<name>.so (e.g. with -D switches), then: gpurun -- bash tools/ab_variants.sh base <name>[:ppw[:workload]] ...
 cp wiser_b200/libwsr.so /tmp/libwsr_base.so
 for spec in "$@"; do
   IFS=: read v ppw wl <<< "$spec"
