@@ -190,6 +190,7 @@ int main(int argc, char **argv) {
   }
   if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
   const auto t0 = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
 
   int fd = open(linedoc.c_str(), O_RDONLY);
   struct stat st;
@@ -218,6 +219,7 @@ int main(int argc, char **argv) {
     return nl ? nl : data + size;
   };
 
+  const double t_lines = since();
   // ---- pass 1: documents -> per-range term accumulators (parallel over contiguous doc ranges)
   const int n_parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads * 4, (n_docs + 255) / 256));
   std::vector<Part> parts(n_parts);
@@ -250,6 +252,7 @@ int main(int argc, char **argv) {
   for (const Part &p : parts)
     if (!p.err.empty()) { fprintf(stderr, "%s\n", p.err.c_str()); return 1; }
 
+  const double t_parse = since();
   // ---- global term table, bytewise sorted
   std::vector<std::string_view> terms;
   {
@@ -268,6 +271,7 @@ int main(int argc, char **argv) {
     for (uint32_t l = 0; l < parts[pi].names.size(); l++)
       where[gid[parts[pi].names[l]]].push_back({(uint32_t)pi, l});
 
+  const double t_merge = since();
   // ---- pass 2: term-major encoding in chunks of terms (parallel)
   std::vector<uint64_t> weight(terms.size() + 1, 0);
   for (size_t t = 0; t < terms.size(); t++) {
@@ -311,6 +315,7 @@ int main(int argc, char **argv) {
     worker();
     for (auto &t : pool) t.join();
   }
+  const double t_encode = since();
   std::vector<uint32_t> doc_len;
   doc_len.reserve(n_docs);
   for (const Part &p : parts) doc_len.insert(doc_len.end(), p.doc_len.begin(), p.doc_len.end());
@@ -322,8 +327,10 @@ int main(int argc, char **argv) {
     return 1;
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   printf("{\"docs\": %zu, \"terms\": %llu, \"postings\": %llu, \"vacuum_bytes\": %llu, \"positions\": %s, "
-         "\"seconds\": %.2f, \"threads\": %d}\n",
+         "\"seconds\": %.2f, \"threads\": %d, \"stage_seconds\": {\"lines\": %.2f, \"parse\": %.2f, "
+         "\"term_table\": %.2f, \"encode\": %.2f, \"write\": %.2f}}\n",
          n_docs, (unsigned long long)n_lists, (unsigned long long)postings, (unsigned long long)file_size,
-         positions ? "true" : "false", secs, threads);
+         positions ? "true" : "false", secs, threads, t_lines, t_parse - t_lines, t_merge - t_parse,
+         t_encode - t_merge, secs - t_encode);
   return 0;
 }
