@@ -274,6 +274,19 @@ def test_search_log_device_front_end_equals_host_planner(golden_dir):
             h1, n1, _, _ = eng.search_batch(q, k)                  # host planner
             h2, n2 = eng.search_log(text, k)                       # device front end
             _same_hits(h1, n1, h2, n2, k)
+    # sparse results: after one call whose results fill under 10 % of n*k, wsr_search_log packs the
+    # hits on the GPU and scatters them on the host; dense logs go back to the direct copy
+    sparse = b"nosuchterm t0\n" * 3000 + b"t0 t1\nt2\n" + b"t0 nosuchterm\n" * 2000 + b"t3 t1\n"
+    q = eng.parse_query_log(sparse, 10)
+    h1, n1, _, _ = eng.search_batch(q, 10)
+    for _ in range(3):
+        h2, n2 = eng.search_log(sparse, 10)
+        _same_hits(h1, n1, h2, n2, 10)
+    q = eng.parse_query_log(base, 10)
+    h1, n1, _, _ = eng.search_batch(q, 10)
+    for _ in range(2):
+        h2, n2 = eng.search_log(base, 10)
+        _same_hits(h1, n1, h2, n2, 10)
     # the same front end behind the device-resident batch API (multi-GPU path)
     from wiser_b200.engine import Batch
     q = eng.parse_query_log(base, 10)

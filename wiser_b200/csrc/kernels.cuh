@@ -132,5 +132,13 @@ void LaunchFrontEnd(const char *d_text, uint32_t len, uint32_t n_nl, uint32_t n_
                     uint32_t *d_multi, PlanItem *d_totals, uint32_t *d_err, void *d_cub,
                     size_t cub_bytes, cudaStream_t s);
 
+// Dense packing of a batch's results for the D2H copy: offsets = exclusive sum of n_hits over
+// n + 1 slots (d_off[n] = total), then packed[off[q] + j] = hits[q*k + j] for j < n_hits[q].
+size_t PackTempBytes(uint32_t n);
+void LaunchResultOffsets(const int32_t *d_n_hits, int32_t *d_off, uint32_t n, void *d_cub, size_t cub_bytes,
+                         cudaStream_t s);
+void LaunchPackResults(const wsr_hit *d_hits, const int32_t *d_n_hits, const int32_t *d_off, uint32_t n,
+                       uint32_t k, wsr_hit *d_packed, cudaStream_t s);
+
 }  // namespace wsr
 #endif
