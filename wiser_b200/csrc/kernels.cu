@@ -36,7 +36,8 @@ constexpr double kK1Plus1 = 1.2 + 1;   // (k1_ + 1) evaluated in double, scoring
 #ifndef WSR_PF_MULT
 #define WSR_PF_MULT 2u   // look-ahead of the filter prefetch, in driver-block spans
 #endif
-constexpr int kHitCap = 160;           // 31 queued + 128 new hits of one pass
+constexpr int kCandCap = 160;          // survivors: 31 carried over + up to 128 of one driver block
+constexpr int kHitCap = 64;            // hits: 31 queued + up to 32 of one probe batch
 
 // ---- block shape (host_index.h PackShape) --------------------------------------------------
 __device__ __forceinline__ uint32_t ShW0(uint32_t b) { return (b & 31u) + 1u; }
@@ -231,7 +232,7 @@ struct CandRec {
 };
 struct __align__(16) ProbeScratch {
   uint32_t win[128];             // the probe list's blk_last window, for per-lane block lookup
-  CandRec cand[kHitCap];         // filter survivors awaiting the exact probe (doc ascending)
+  CandRec cand[kCandCap];        // filter survivors awaiting the exact probe (doc ascending)
   HitRec hits[kHitCap];          // intersection hits awaiting scoring
 };
 struct __align__(16) NoScratch { uint32_t unused; };
