@@ -156,3 +156,15 @@ def test_scatter_exchange_equals_allgather_merge_world2(n, k):
     for p in ps:
         p.join(timeout=60)
     assert got == [(0, True), (1, True)]
+
+
+def test_slice_bounds_cover_every_query_once():
+    from wiser_b200.dist import slice_bounds
+    for n in (0, 1, 7, 8, 9, 100000, 100003):
+        for world in (1, 2, 3, 8):
+            s, lo = slice_bounds(n, world)
+            assert lo[0] == 0 and lo[-1] == n and len(lo) == world + 1
+            sizes = [lo[r + 1] - lo[r] for r in range(world)]
+            assert all(0 <= x <= s for x in sizes) and sum(sizes) == n
+            # slice r starts at r*s: the all-gather of s-padded slices is the result in query order
+            assert all(lo[r] == min(n, r * s) for r in range(world))
