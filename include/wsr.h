@@ -140,7 +140,8 @@ int wsr_decode_list(wsr_index *idx, uint32_t term_id, uint32_t *docs, uint32_t *
 int wsr_decode_all(wsr_index *idx, uint64_t *checksum, float *kernel_ms);
 
 /* ---- Search(): VacuumEngine::Search (vacuum_engine.h:201-258) ----------------------------
- * String-term single query, blocking; flags = WSR_QUERY_PHRASE for SearchQuery::is_phrase. hits must hold k entries, doc_freqs n_terms entries.
+ * String-term single query, blocking; flags = WSR_QUERY_PHRASE for SearchQuery::is_phrase.
+ * hits must hold k entries, doc_freqs n_terms entries.
  * *n_doc_freqs is 0 when the reference returns early with an empty result, else n_terms. */
 int wsr_search(wsr_index *idx, const char *const *terms, const size_t *term_lens, int n_terms,
                int k, unsigned flags, wsr_hit *hits, int *n_hits, uint32_t *doc_freqs,
@@ -154,11 +155,16 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
                      wsr_hit *hits, int32_t *n_hits, uint32_t *doc_freqs,
                      int32_t *n_doc_freqs);
 
-/* Replays a whole query log given as TEXT (the replay driver's inner loop): the log is cut into
- * chunks; while the GPU works on chunk i the host parses / looks up / plans chunk i+1 and the
- * results of chunk i-1 travel back, all inside this one blocking call. hits: cap_q * k entries
- * (query i at hits[i*k]); n_hits: cap_q entries; *n_queries receives the number of log lines.
- * Pinned buffers (wsr_host_alloc) are written by DMA directly. */
+/* Replays a whole query log given as TEXT — the replay driver's inner loop: QueryProducerByLog
+ * (query_pool.h:251-352: one query per line, trimmed, a "quoted" line is a phrase, terms split on
+ * ' ') + TermTrieIndex::Find (term_index.h:136-144) + VacuumEngine::Search per line, in one
+ * blocking call. For k <= 32 only the text crosses PCIe: it is parsed, looked up in the HBM copy
+ * of the term dictionary and planned by kernels (csrc/frontend.cu); larger k (or
+ * WSR_HOST_FRONTEND=1) parse and plan on host threads, in up to 4 chunks overlapped with the GPU.
+ * hits: cap_q * k entries (query i at hits[i*k], entries past n_hits[i] unspecified); n_hits:
+ * cap_q entries; *n_queries receives the number of log lines. Pinned buffers (wsr_host_alloc) are
+ * written by DMA directly; logs whose results are sparse come back packed and are scattered into
+ * hits[] by host threads. A line with more than WSR_MAX_TERMS terms fails the call. */
 int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
                    int32_t *n_hits, int cap_q, int *n_queries);
 
