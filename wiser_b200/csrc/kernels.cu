@@ -1108,17 +1108,30 @@ MergeUnitsKernel(const BatchView bv, const uint32_t *__restrict__ multi, uint32_
   const int k = (int)q.k;
   TopK top;
   TopKInit(top);
-  for (uint32_t u = 0; u < q.n_units; u++) {
-    const int n = bv.cand_n[g0 + u];
-    wsr_hit h;
-    h.doc_id = 0x7fffffff; h.score = -1.0;
-    if (lane < n) h = bv.cand[(size_t)(g0 + u) * kMaxFastK + lane];
-    const double kth = top.count == k ? TopKKth(top, k) : -1.0;
-    unsigned m = __ballot_sync(kFull, lane < n && !(h.score < kth));
-    while (m) {
-      const int src = __ffs(m) - 1;
-      m &= m - 1;
-      TopKInsert(top, k, __shfl_sync(kFull, h.score, src), __shfl_sync(kFull, h.doc_id, src), lane);
+  // four units at a time: all of their counts and candidate rows are requested before any is
+  // folded in (the candidate slots of a unit always exist, 32 per unit, so the row load does not
+  // have to wait for the count) — the merge is a chain of small dependent loads otherwise
+  for (uint32_t u0 = 0; u0 < q.n_units; u0 += 4) {
+    int cnt[4];
+    wsr_hit row[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const bool on = u0 + i < q.n_units;
+      cnt[i] = on ? bv.cand_n[g0 + u0 + i] : 0;
+      row[i].doc_id = 0x7fffffff; row[i].reserved = 0; row[i].score = -1.0;
+      if (on) row[i] = bv.cand[(size_t)(g0 + u0 + i) * kMaxFastK + lane];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int n = cnt[i];
+      const wsr_hit h = row[i];
+      const double kth = top.count == k ? TopKKth(top, k) : -1.0;
+      unsigned m = __ballot_sync(kFull, lane < n && !(h.score < kth));
+      while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        TopKInsert(top, k, __shfl_sync(kFull, h.score, src), __shfl_sync(kFull, h.doc_id, src), lane);
+      }
     }
   }
   if (lane < top.count) {
