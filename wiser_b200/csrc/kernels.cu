@@ -1043,7 +1043,7 @@ template <> struct ScratchOf<kClassTwo> { typedef ProbeScratch type; };
 
 // Persistent search kernel of one query class: warps drain the class's unit queue.
 template <int CLASS, bool STATS>
-__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? 4 : CLASS == kClassMany ? 3 : 1)
+__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? 4 : CLASS == kClassMany ? 3 : CLASS == kClassOne ? 8 : 1)
 SearchKernel(const DevIndexView ix, const BatchView bv) {
   __shared__ CtaShared sh;
   __shared__ typename ScratchOf<CLASS>::type scratch[kWarpsPerCta];
