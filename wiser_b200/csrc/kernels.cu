@@ -957,16 +957,36 @@ __device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const 
   const bool multi = q.n_units > 1;
   uint32_t first_a = 0;
   __syncwarp();
-  for (int t = 0; t < m; t++) {
-    const uint4 li = __ldg(&ix.lists[q.term[t]]);
-    if (t == drv) { first_a = li.x; continue; }
-    const uint2 f = __ldg(&ix.list_flt[q.term[t]]);
-    ProbeState &ps = ws->list[t];
-    if (lane == 0) {
-      ps.first = li.x; ps.nb = li.y; ps.wbase = 0;
-      ps.flt_word = f.x; ps.flt_shift = f.y;     // shift 0xFFFFFFFF: no filter
+  {
+    // Unit prologue: the list records, filter descriptors and blk_last windows of all terms are
+    // requested in two batches of independent loads (a short driver list makes the whole unit a
+    // few dependent round trips long, so every one saved counts).
+    uint4 li[WSR_MAX_TERMS];
+    uint2 lf[WSR_MAX_TERMS];
+#pragma unroll
+    for (int t = 0; t < WSR_MAX_TERMS; t++) {
+      li[t] = make_uint4(0u, 0u, 0u, 0u);
+      lf[t] = make_uint2(0u, 0xffffffffu);
+      if (t < m) {
+        li[t] = __ldg(&ix.lists[q.term[t]]);
+        lf[t] = __ldg(&ix.list_flt[q.term[t]]);
+      }
     }
-    ps.wl[lane] = (uint32_t)lane < li.y ? __ldg(ix.blk_last + li.x + lane) : kNoDoc;
+    uint32_t wl[WSR_MAX_TERMS];
+#pragma unroll
+    for (int t = 0; t < WSR_MAX_TERMS; t++)
+      wl[t] = (t < m && t != drv && (uint32_t)lane < li[t].y) ? __ldg(ix.blk_last + li[t].x + lane) : kNoDoc;
+#pragma unroll
+    for (int t = 0; t < WSR_MAX_TERMS; t++) {
+      if (t >= m) continue;
+      if (t == drv) { first_a = li[t].x; continue; }
+      ProbeState &ps = ws->list[t];
+      if (lane == 0) {
+        ps.first = li[t].x; ps.nb = li[t].y; ps.wbase = 0;
+        ps.flt_word = lf[t].x; ps.flt_shift = lf[t].y;     // shift 0xFFFFFFFF: no filter
+      }
+      ps.wl[lane] = wl[t];
+    }
   }
   __syncwarp();
   TopK top;
