@@ -221,7 +221,7 @@ int main(int argc, char **argv) {
 
   const double t_lines = since();
   // ---- pass 1: documents -> per-range term accumulators (parallel over contiguous doc ranges)
-  const int n_parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads * 4, (n_docs + 255) / 256));
+  const int n_parts = (int)std::max<size_t>(1, std::min<size_t>((size_t)threads * 2, (n_docs + 255) / 256));
   std::vector<Part> parts(n_parts);
   for (int i = 0; i < n_parts; i++) {
     parts[i].doc_begin = n_docs * i / n_parts;
@@ -265,12 +265,29 @@ int main(int argc, char **argv) {
   std::unordered_map<std::string_view, uint32_t> gid;
   gid.reserve(terms.size() * 2);
   for (size_t i = 0; i < terms.size(); i++) gid.emplace(terms[i], (uint32_t)i);
-  // per part: local id -> global id; per global term: the parts that hold it, in doc order
+  // per part: local id -> global id (parallel lookups in the read-only table); per global term:
+  // the parts that hold it, in doc order
+  std::vector<std::vector<uint32_t>> to_global(n_parts);
+  {
+    std::atomic<int> next{0};
+    auto worker = [&]() {
+      for (;;) {
+        const int pi = next.fetch_add(1);
+        if (pi >= n_parts) return;
+        const Part &p = parts[pi];
+        std::vector<uint32_t> &g = to_global[pi];
+        g.resize(p.names.size());
+        for (size_t l = 0; l < p.names.size(); l++) g[l] = gid.find(p.names[l])->second;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+  }
   std::vector<std::vector<std::pair<uint32_t, uint32_t>>> where(terms.size());   // (part, local id)
   for (int pi = 0; pi < n_parts; pi++)
-    for (uint32_t l = 0; l < parts[pi].names.size(); l++)
-      where[gid[parts[pi].names[l]]].push_back({(uint32_t)pi, l});
-
+    for (uint32_t l = 0; l < to_global[pi].size(); l++) where[to_global[pi][l]].push_back({(uint32_t)pi, l});
   const double t_merge = since();
   // ---- pass 2: term-major encoding in chunks of terms (parallel)
   std::vector<uint64_t> weight(terms.size() + 1, 0);
