@@ -190,19 +190,6 @@ __device__ __forceinline__ double TopKKth(const TopK &t, int k) {
   return __shfl_sync(kFull, t.s, k - 1);   // meaningful when count == k
 }
 
-// 32-ary cooperative search: last planned query in [lo, hi) whose unit_begin <= u.
-__device__ __forceinline__ uint32_t FindQuery(const DevQuery *__restrict__ q, uint32_t lo,
-                                              uint32_t hi, uint32_t u, int lane) {
-  while (hi - lo > 1) {
-    const uint32_t step = (hi - lo + 31u) >> 5;
-    const uint32_t idx = lo + (uint32_t)lane * step;
-    const bool le = idx < hi && __ldg(&q[idx].unit_begin) <= u;
-    const int cnt = __popc(__ballot_sync(kFull, le));
-    lo += (uint32_t)(cnt - 1) * step;
-    hi = min(lo + step, hi);
-  }
-  return lo;
-}
 
 // Work counters of a warp (roofline bookkeeping, never used for results). Counting costs ~7 % of
 // the two-term kernel, so ordinary runs instantiate the kernels with ON = false and only the
@@ -1076,7 +1063,6 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
   const int lane = threadIdx.x & 31;
   auto *ws = &scratch[threadIdx.x >> 5];
   (void)ws;
-  const uint32_t q_lo = bv.class_begin[CLASS], q_hi = bv.class_begin[CLASS + 1];
   const uint32_t n_units = bv.class_units[CLASS];
   UnitStatsT<STATS> st = {0ull, 0ull, 0ull};
   unsigned long long units = 0;
@@ -1085,7 +1071,7 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
     if (lane == 0) u = atomicAdd(&bv.counters->next_unit[CLASS], 1u);
     u = __shfl_sync(kFull, u, 0);
     if (u >= n_units) break;
-    const uint32_t qi = FindQuery(bv.queries, q_lo, q_hi, u, lane);
+    const uint32_t qi = __ldg(&bv.unit_query[bv.class_unit_base[CLASS] + u]);
     const DevQuery q = bv.queries[qi];
     const uint32_t local = u - q.unit_begin;
     // driver list block range of this unit
@@ -1114,6 +1100,18 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
     }
     atomicAdd(&bv.counters->units, units);
   }
+}
+
+// unit -> query map of a planned batch: the persistent kernels take a unit number from their
+// class queue and need its query; one load here replaces a 4-level search over unit_begin.
+__global__ void UnitMapKernel(const BatchView bv, uint32_t *__restrict__ unit_query, uint32_t n_planned) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_planned) return;
+  const DevQuery q = bv.queries[i];
+  uint32_t c = 0;
+  while (c < 3 && i >= bv.class_begin[c + 1]) c++;
+  uint32_t *dst = unit_query + bv.class_unit_base[c] + q.unit_begin;
+  for (uint32_t u = 0; u < q.n_units; u++) dst[u] = i;
 }
 
 // One warp per multi-unit query: folds the units' candidate lists into the final top-k.
@@ -1362,6 +1360,11 @@ void LaunchSearchClass(const DevIndexView &ix, const BatchView &b, int c, int sm
                        cudaStream_t s, bool count_work) {
   if (count_work) LaunchSearchClassT<true>(ix, b, c, sm_count, s);
   else LaunchSearchClassT<false>(ix, b, c, sm_count, s);
+}
+
+void LaunchUnitMap(const BatchView &b, uint32_t *unit_query, uint32_t n_planned, cudaStream_t s) {
+  if (!n_planned) return;
+  UnitMapKernel<<<(n_planned + 255) / 256, 256, 0, s>>>(b, unit_query, n_planned);
 }
 
 void LaunchMerge(const BatchView &b, const uint32_t *multi_queries, uint32_t n_multi,

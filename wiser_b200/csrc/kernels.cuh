@@ -67,6 +67,8 @@ struct DevCounters {
 
 struct BatchView {
   const DevQuery *queries;     // class-sorted; class c occupies [class_begin[c], class_begin[c+1])
+  const uint32_t *unit_query;  // work unit -> planned query; class c's units start at class_unit_base[c]
+  uint32_t class_unit_base[4];
   uint32_t class_begin[5];
   uint32_t class_units[4];
   wsr_hit *hits;               // n * k_stride
@@ -90,6 +92,8 @@ enum { kClassOne = 0, kClassTwo = 1, kClassMany = 2, kClassCollect = 3 };
 // matches) switched on — the profiling pass; ordinary runs do not pay for the bookkeeping.
 void LaunchSearchClass(const DevIndexView &ix, const BatchView &b, int cls, int sm_count,
                        cudaStream_t s, bool count_work);
+// Fills unit_query[] from the planned queries (one thread per query writes its n_units entries).
+void LaunchUnitMap(const BatchView &b, uint32_t *unit_query, uint32_t n_planned, cudaStream_t s);
 void LaunchMerge(const BatchView &b, const uint32_t *multi_queries, uint32_t n_multi,
                  cudaStream_t s);
 void LaunchDecodeList(const DevIndexView &ix, uint32_t first_block, uint32_t n_blocks,

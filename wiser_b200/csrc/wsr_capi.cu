@@ -205,6 +205,7 @@ struct wsr_batch {
   uint32_t launches = 0;
   // device
   DevBuf<DevQuery> d_queries;
+  DevBuf<uint32_t> d_unit_query;
   // results: ONE allocation [hits n*k_stride | n_hits n | DevCounters] so that one memset clears
   // counts + counters and one D2H brings hits + counts back
   DevBuf<uint8_t> d_out;
@@ -433,6 +434,12 @@ int PrepareBatch(wsr_batch *b, bool plan_on_host) {
   CU(b->d_seg_count.Ensure(np + 1));
   BatchView &v = b->view;
   v.queries = b->d_queries.p;
+  {
+    uint32_t base = 0;
+    for (int c = 0; c < 4; c++) { v.class_unit_base[c] = base; base += b->class_units[c]; }
+    CU(b->d_unit_query.Ensure((size_t)base + 1));
+    v.unit_query = b->d_unit_query.p;
+  }
   for (int c = 0; c < 5; c++) v.class_begin[c] = b->class_begin[c];
   for (int c = 0; c < 4; c++) v.class_units[c] = b->class_units[c];
   v.hits = b->out_hits;
@@ -463,6 +470,8 @@ int UploadBatch(wsr_batch *b) {
   if (b->n_multi)
     CU(cudaMemcpyAsync(b->d_multi.p, b->h_multi.p, (size_t)b->n_multi * 4, cudaMemcpyHostToDevice,
                        b->stream));
+  LaunchUnitMap(b->view, b->d_unit_query.p, (uint32_t)np, b->stream);
+  CU(cudaGetLastError());
   return WSR_OK;
 }
 
@@ -1189,7 +1198,11 @@ int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q
   b->n_cand_units = tot[6];
   b->n_seg_entries = b->n_collect = 0;
   b->listed_postings = b->listed_bytes = 0;   // not tallied by the device planner
-  return PrepareBatch(b, /*plan_on_host=*/false);
+  const int rc = PrepareBatch(b, /*plan_on_host=*/false);
+  if (rc) return rc;
+  LaunchUnitMap(b->view, b->d_unit_query.p, b->np, b->stream);
+  CU(cudaGetLastError());
+  return WSR_OK;
 }
 
 bool DeviceFrontEndUsable(const wsr_index *idx, size_t len, int k) {
