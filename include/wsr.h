@@ -148,7 +148,8 @@ int wsr_search(wsr_index *idx, const char *const *terms, const size_t *term_lens
                int *n_doc_freqs);
 
 /* Batched Search over HOST buffers: the query batch is copied to the device, processed by
- * the batch scheduler in one pass, and the results copied back (all inside the call).
+ * the batch scheduler in one pass, and the results copied back (all inside the call). Batches
+ * of >= 8192 queries with k_stride <= 32 are planned on the GPU, smaller ones by host threads.
  * hits: n * k_stride entries (query i at hits[i*k_stride]); n_hits: n entries;
  * doc_freqs (may be NULL): n * WSR_MAX_TERMS entries, n_doc_freqs (may be NULL): n entries. */
 int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stride,

@@ -256,6 +256,46 @@ def _same_hits(h1, n1, h2, n2, k):
     assert np.array_equal(h1["score"][mask].view(np.uint64), h2["score"][mask].view(np.uint64))
 
 
+def _host_planned(eng, q, k):
+    """wsr_search_batch in chunks small enough (< 8192 queries) to be planned by the HOST planner."""
+    hs, ns = [], []
+    for lo in range(0, len(q), 4000):
+        h, n, _, _ = eng.search_batch(q[lo:lo + 4000], k)
+        hs.append(h)
+        ns.append(n)
+    if not hs:
+        return eng.search_batch(q, k)[:2]
+    return np.concatenate(hs), np.concatenate(ns)
+
+
+def test_search_batch_device_planner_equals_host_planner(golden_dir):
+    """Batches of >= 8192 queries (k <= 32) are planned on the GPU from the wsr_query array; the
+    result must equal what the host planner gives for the same queries, and misuse must fail."""
+    from wiser_b200 import GpuVacuumEngine
+    d = os.path.join(golden_dir, "zipf2k")
+    eng = GpuVacuumEngine(d).Load()
+    base = open(os.path.join(d, "queries.txt"), "rb").read()
+    q = eng.parse_query_log(base * 3, 10)          # ~14k queries incl. phrases, missing terms, 8-term queries
+    assert len(q) >= 8192
+    h1, n1 = _host_planned(eng, q, 10)
+    h2, n2, _, _ = eng.search_batch(q, 10)
+    _same_hits(h1, n1, h2, n2, 10)
+    q3 = q.copy()
+    q3["k"] = 3                                    # per-query k below the stride
+    h1, n1 = _host_planned(eng, q3, 10)
+    h2, n2, _, _ = eng.search_batch(q3, 10)
+    _same_hits(h1, n1, h2, n2, 10)
+    bad = q.copy()
+    bad["k"][100] = 11                             # k > k_stride
+    with pytest.raises(Exception):
+        eng.search_batch(bad, 10)
+    bad = q.copy()
+    bad["term_ids"][200, 0] = 0x7fffffff           # term id outside the index
+    bad["n_terms"][200] = 1
+    with pytest.raises(Exception):
+        eng.search_batch(bad, 10)
+
+
 def test_search_log_device_front_end_equals_host_planner(golden_dir):
     """wsr_search_log parses, looks terms up and plans ON THE GPU (frontend.cu); it must return
     exactly what the host parser + host planner + wsr_search_batch return, for every line shape
@@ -271,7 +311,7 @@ def test_search_log_device_front_end_equals_host_planner(golden_dir):
                  b"t0", b"\n", b"\n\n t1 \n"):
         for k in (10, 1, 32):
             q = eng.parse_query_log(text, k)                       # host parser
-            h1, n1, _, _ = eng.search_batch(q, k)                  # host planner
+            h1, n1 = _host_planned(eng, q, k)                      # host planner
             h2, n2 = eng.search_log(text, k)                       # device front end
             _same_hits(h1, n1, h2, n2, k)
     # sparse results: after one call whose results fill under 10 % of n*k, wsr_search_log packs the

@@ -46,6 +46,75 @@ __device__ uint32_t DictFind(const DevDict &d, const char *s, uint32_t len) {
   }
 }
 
+// Validity, driver list, unit size and class of one query whose term ids are in q.term[] — the
+// device statement of the host planner's per-query work (PlanBatch in wsr_capi.cu). tmp[i] is the
+// query before placement (cand_begin holds its class, 255 = produces no work).
+__device__ __forceinline__ void PlanOne(const DevIndexView &ix, DevQuery &q, uint32_t n_terms, uint32_t flags,
+                                        uint32_t k, uint32_t i, bool resolvable, DevQuery *__restrict__ tmp,
+                                        PlanItem *__restrict__ item, uint32_t *__restrict__ err) {
+  PlanItem it;
+#pragma unroll
+  for (int j = 0; j < 8; j++) it.v[j] = 0;
+  uint32_t cls = 255;
+  bool ok = resolvable && k > 0 && n_terms > 0;             // vacuum_engine.h:206-215
+  uint32_t best = 0, best_df = 0xffffffffu;
+  unsigned long long all_blocks = 0;
+  if (ok) {
+    for (uint32_t t = 0; t < n_terms; t++) {
+      const uint4 li = __ldg(&ix.lists[q.term[t]]);
+      if (li.z == 0) ok = false;                           // nothing of this list on this shard
+      if (li.z < best_df) { best_df = li.z; best = t; }
+      all_blocks += li.y;
+    }
+  }
+  if (ok) {
+    const uint32_t drv_blocks = __ldg(&ix.lists[q.term[best]]).y;
+    const unsigned long long probe_blocks = all_blocks - drv_blocks;
+    // unit size: same rule as the host planner (PlanBatch)
+    const unsigned long long ratio = drv_blocks ? (probe_blocks + drv_blocks - 1) / drv_blocks : 0;
+    unsigned long long ub = (unsigned long long)kUnitBudget / (1ull + ratio);
+    ub = ub < 1 ? 1 : ub > (unsigned long long)kUnitBlocks ? (unsigned long long)kUnitBlocks : ub;
+    q.n_terms = (uint8_t)n_terms;
+    q.flags = (flags && n_terms > 1) ? 1 : 0;              // a one-term "phrase" is a plain query
+    if (q.flags && ix.positions == nullptr) atomicOr(err, 2u);
+    q.unit_blocks = (uint16_t)ub;
+    q.k = k;
+    q.driver = best;
+    q.out_slot = i;
+    cls = n_terms == 1 ? kClassOne : n_terms == 2 ? kClassTwo : kClassMany;
+    q.n_units = cls == kClassOne ? 1u : (drv_blocks + (uint32_t)ub - 1u) / (uint32_t)ub;
+    it.v[cls] = 1;
+    it.v[3 + cls] = q.n_units;
+    if (q.n_units > 1) { it.v[6] = q.n_units; it.v[7] = 1; }
+  }
+  q.cand_begin = cls;
+  tmp[i] = q;
+  item[i] = it;
+}
+
+// Same planning from term ids the host already resolved (wsr_search_batch): one thread per
+// wsr_query. err bit 2: k > k_stride or a term id outside the index.
+__global__ void PlanQueriesKernel(const wsr_query *__restrict__ in, uint32_t n, uint32_t k_stride,
+                                  const DevIndexView ix, DevQuery *__restrict__ tmp,
+                                  PlanItem *__restrict__ item, uint32_t *__restrict__ err) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const wsr_query w = in[i];
+  DevQuery q;
+  memset(&q, 0, sizeof(q));
+  bool resolvable = true;
+  uint32_t n_terms = w.n_terms;
+  if (n_terms > WSR_MAX_TERMS) { atomicOr(err, 1u); n_terms = 0; resolvable = false; }
+  if (w.k > k_stride) { atomicOr(err, 4u); resolvable = false; }
+  for (uint32_t t = 0; t < n_terms; t++) {
+    const uint32_t id = w.term_ids[t];
+    q.term[t] = id;
+    if (id == WSR_TERM_ABSENT) resolvable = false;                      // vacuum_engine.h:213-215
+    else if (id >= ix.n_terms) { atomicOr(err, 4u); resolvable = false; }
+  }
+  PlanOne(ix, q, n_terms, w.flags & 1u, w.k, i, resolvable, tmp, item, err);
+}
+
 // One thread per log line: parse -> term ids -> validity -> driver list, unit size, class.
 // tmp[i] is the query before placement (cand_begin holds its class, 255 = produces no work).
 __global__ void ParsePlanKernel(const char *__restrict__ text, uint32_t len,
@@ -81,45 +150,8 @@ __global__ void ParsePlanKernel(const char *__restrict__ text, uint32_t len,
     }
     t = u;
   }
-  PlanItem it;
-#pragma unroll
-  for (int j = 0; j < 8; j++) it.v[j] = 0;
-  uint32_t cls = 255;
   if (too_many) atomicOr(err, 1u);
-  bool ok = !too_many && k > 0 && n_terms > 0 && present;   // vacuum_engine.h:206-215
-  uint32_t best = 0, best_df = 0xffffffffu;
-  unsigned long long all_blocks = 0;
-  if (ok) {
-    for (uint32_t t = 0; t < n_terms; t++) {
-      const uint4 li = __ldg(&ix.lists[q.term[t]]);
-      if (li.z == 0) ok = false;                           // nothing of this list on this shard
-      if (li.z < best_df) { best_df = li.z; best = t; }
-      all_blocks += li.y;
-    }
-  }
-  if (ok) {
-    const uint32_t drv_blocks = __ldg(&ix.lists[q.term[best]]).y;
-    const unsigned long long probe_blocks = all_blocks - drv_blocks;
-    // unit size: same rule as the host planner (PlanBatch)
-    const unsigned long long ratio = drv_blocks ? (probe_blocks + drv_blocks - 1) / drv_blocks : 0;
-    unsigned long long ub = (unsigned long long)kUnitBudget / (1ull + ratio);
-    ub = ub < 1 ? 1 : ub > (unsigned long long)kUnitBlocks ? (unsigned long long)kUnitBlocks : ub;
-    q.n_terms = (uint8_t)n_terms;
-    q.flags = (flags && n_terms > 1) ? 1 : 0;              // a one-term "phrase" is a plain query
-    if (q.flags && ix.positions == nullptr) atomicOr(err, 2u);
-    q.unit_blocks = (uint16_t)ub;
-    q.k = k;
-    q.driver = best;
-    q.out_slot = i;
-    cls = n_terms == 1 ? kClassOne : n_terms == 2 ? kClassTwo : kClassMany;
-    q.n_units = cls == kClassOne ? 1u : (drv_blocks + (uint32_t)ub - 1u) / (uint32_t)ub;
-    it.v[cls] = 1;
-    it.v[3 + cls] = q.n_units;
-    if (q.n_units > 1) { it.v[6] = q.n_units; it.v[7] = 1; }
-  }
-  q.cand_begin = cls;
-  tmp[i] = q;
-  item[i] = it;
+  PlanOne(ix, q, n_terms, flags, k, i, !too_many && present, tmp, item, err);
 }
 
 struct PlanAdd {
@@ -184,6 +216,18 @@ size_t FrontEndTempBytes(uint32_t len, uint32_t n_lines) {
   cub::DeviceScan::ExclusiveScan(nullptr, b, (const PlanItem *)nullptr, (PlanItem *)nullptr,
                                  PlanAdd(), PlanItem(), (int)n_lines);
   return (a > b ? a : b) + 256;
+}
+
+void LaunchPlanQueries(const wsr_query *d_in, uint32_t n, uint32_t k_stride, const DevIndexView &ix,
+                       DevQuery *d_tmp, PlanItem *d_item, PlanItem *d_excl, DevQuery *d_planned,
+                       uint32_t *d_multi, PlanItem *d_totals, uint32_t *d_err, void *d_cub, size_t cub_bytes,
+                       cudaStream_t s) {
+  if (!n) return;
+  const uint32_t grid = (n + 127) / 128;
+  PlanQueriesKernel<<<grid, 128, 0, s>>>(d_in, n, k_stride, ix, d_tmp, d_item, d_err);
+  size_t bytes = cub_bytes;
+  cub::DeviceScan::ExclusiveScan(d_cub, bytes, d_item, d_excl, PlanAdd(), PlanItem(), (int)n, s);
+  PlaceKernel<<<grid, 128, 0, s>>>(d_tmp, d_item, d_excl, n, d_planned, d_multi, d_totals);
 }
 
 size_t PackTempBytes(uint32_t n) {

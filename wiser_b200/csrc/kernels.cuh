@@ -136,6 +136,14 @@ void LaunchFrontEnd(const char *d_text, uint32_t len, uint32_t n_nl, uint32_t n_
                     uint32_t *d_multi, PlanItem *d_totals, uint32_t *d_err, void *d_cub,
                     size_t cub_bytes, cudaStream_t s);
 
+// Planning of a batch whose term ids the host already resolved (wsr_search_batch): per-query
+// planning kernel -> exclusive scan -> placement, as in LaunchFrontEnd. d_err bit 0: more than
+// WSR_MAX_TERMS terms, bit 1: phrase query without positions, bit 2: k > k_stride or bad term id.
+void LaunchPlanQueries(const wsr_query *d_in, uint32_t n, uint32_t k_stride, const DevIndexView &ix,
+                       DevQuery *d_tmp, PlanItem *d_item, PlanItem *d_excl, DevQuery *d_planned,
+                       uint32_t *d_multi, PlanItem *d_totals, uint32_t *d_err, void *d_cub, size_t cub_bytes,
+                       cudaStream_t s);
+
 // Dense packing of a batch's results for the D2H copy: offsets = exclusive sum of n_hits over
 // n + 1 slots (d_off[n] = total), then packed[off[q] + j] = hits[q*k + j] for j < n_hits[q].
 size_t PackTempBytes(uint32_t n);

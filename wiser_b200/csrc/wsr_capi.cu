@@ -226,6 +226,8 @@ struct wsr_batch {
   DevBuf<char> d_text;
   DevBuf<uint32_t> d_nl, d_fe_small;   // d_fe_small: [0] newline count (unused), [1] error bits
   DevBuf<DevQuery> d_tmp;
+  DevBuf<wsr_query> d_wq;              // wsr_search_batch: the caller's queries, planned on the GPU
+  PinnedBuf<wsr_query> h_wq;
   DevBuf<PlanItem> d_item, d_excl, d_totals;
   DevBuf<uint8_t> d_fe_cub;
   PinnedBuf<char> h_text;
@@ -869,6 +871,8 @@ int wsr_decode_all(wsr_index *idx, uint64_t *checksum, float *kernel_ms) {
 namespace {
 bool DeviceFrontEndUsable(const wsr_index *idx, size_t len, int k);
 int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q);
+int PlanQueriesOnDevice(wsr_batch *b, const wsr_query *queries, int n, int k_stride);
+int FinishDevicePlan(wsr_batch *b, uint32_t n, int k_stride);
 }  // namespace
 
 wsr_batch *wsr_batch_create(wsr_index *idx, const wsr_query *queries, int n, int k_stride) {
@@ -1115,8 +1119,15 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
   }
   wsr_batch *b = AcquirePooled(idx);
   if (!b) return Fail(WSR_ERR_CUDA, "cannot create batch");
-  int rc = PlanBatch(b, queries, n, k_stride);
-  if (rc == WSR_OK) rc = UploadBatch(b);
+  // large batches without collect-class queries are planned on the GPU, the rest by host threads
+  static const bool host_planner = getenv("WSR_HOST_FRONTEND") && atoi(getenv("WSR_HOST_FRONTEND")) != 0;
+  int rc;
+  if (!host_planner && n >= 8192 && k_stride <= kMaxFastK) {
+    rc = PlanQueriesOnDevice(b, queries, n, k_stride);
+  } else {
+    rc = PlanBatch(b, queries, n, k_stride);
+    if (rc == WSR_OK) rc = UploadBatch(b);
+  }
   if (rc == WSR_OK) rc = EnqueueRun(b);
   if (rc == WSR_OK) rc = wsr_batch_fetch(b, hits, n_hits);
   ReleasePooled(idx, b);
@@ -1174,6 +1185,12 @@ int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q
                  b->d_nl.p, b->d_fe_small.p, b->d_tmp.p, b->d_item.p, b->d_excl.p, b->d_queries.p,
                  b->d_multi.p, b->d_totals.p, b->d_fe_small.p + 1, b->d_fe_cub.p, cub_bytes, b->stream);
   CU(cudaGetLastError());
+  return FinishDevicePlan(b, n, k);
+}
+
+// Second half of both device planners: reads the 36 bytes of totals back, turns them into the
+// class layout, sizes the batch's buffers and enqueues the unit -> query map.
+int FinishDevicePlan(wsr_batch *b, uint32_t n, int k_stride) {
   CU(cudaMemcpyAsync(b->h_totals.p, b->d_totals.p, 32, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaMemcpyAsync(b->h_totals.p + 8, b->d_fe_small.p + 1, 4, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
@@ -1181,8 +1198,9 @@ int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q
   if (tot[8] & 1u) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
   if (tot[8] & 2u)
     return Fail(WSR_ERR_UNSUPPORTED, "phrase query on an index opened without WSR_OPEN_POSITIONS");
+  if (tot[8] & 4u) return Fail(WSR_ERR_ARG, "query k exceeds k_stride, or term id out of range");
   b->n = (int)n;
-  b->k_stride = k;
+  b->k_stride = k_stride;
   b->planned.clear();
   b->multi.clear();
   uint32_t pos = 0;
@@ -1197,12 +1215,44 @@ int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q
   b->n_multi = tot[7];
   b->n_cand_units = tot[6];
   b->n_seg_entries = b->n_collect = 0;
-  b->listed_postings = b->listed_bytes = 0;   // not tallied by the device planner
+  b->listed_postings = b->listed_bytes = 0;   // not tallied by the device planners
   const int rc = PrepareBatch(b, /*plan_on_host=*/false);
   if (rc) return rc;
   LaunchUnitMap(b->view, b->d_unit_query.p, b->np, b->stream);
   CU(cudaGetLastError());
   return WSR_OK;
+}
+
+// wsr_search_batch for large batches with k_stride <= kMaxFastK: the wsr_query array goes to the
+// GPU as it is and is planned there (frontend.cu PlanQueriesKernel + scan + placement) instead of
+// by host threads.
+int PlanQueriesOnDevice(wsr_batch *b, const wsr_query *queries, int n_in, int k_stride) {
+  wsr_index *idx = b->idx;
+  const uint32_t n = (uint32_t)n_in;
+  CU(b->d_wq.Ensure(n));
+  const wsr_query *src = queries;
+  if (!IsPinned(queries)) {
+    CU(b->h_wq.Ensure(n));
+    memcpy(b->h_wq.p, queries, (size_t)n * sizeof(wsr_query));
+    src = b->h_wq.p;
+  }
+  CU(cudaMemcpyAsync(b->d_wq.p, src, (size_t)n * sizeof(wsr_query), cudaMemcpyHostToDevice, b->stream));
+  CU(b->d_fe_small.Ensure(2));
+  CU(b->d_tmp.Ensure(n));
+  CU(b->d_item.Ensure(n));
+  CU(b->d_excl.Ensure(n));
+  CU(b->d_totals.Ensure(1));
+  CU(b->d_queries.Ensure((size_t)n + 1));
+  CU(b->d_multi.Ensure((size_t)n + 1));
+  CU(b->h_totals.Ensure(9));
+  const size_t cub_bytes = FrontEndTempBytes(16, n);
+  CU(b->d_fe_cub.Ensure(cub_bytes));
+  CU(cudaMemsetAsync(b->d_fe_small.p, 0, 8, b->stream));
+  LaunchPlanQueries(b->d_wq.p, n, (uint32_t)k_stride, idx->view, b->d_tmp.p, b->d_item.p, b->d_excl.p,
+                    b->d_queries.p, b->d_multi.p, b->d_totals.p, b->d_fe_small.p + 1, b->d_fe_cub.p, cub_bytes,
+                    b->stream);
+  CU(cudaGetLastError());
+  return FinishDevicePlan(b, n, k_stride);
 }
 
 bool DeviceFrontEndUsable(const wsr_index *idx, size_t len, int k) {
