@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=100000, help="queries in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-sample", type=int, default=200)
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads of the N=1 line")
     ap.add_argument("--dir", default=os.environ.get("WSR_BENCH_DIR", "/tmp/wsr_bench"))
     ap.add_argument("--query-filter", default="", choices=["", "dense_partner", "no_dense_partner"],
                     help="analysis only: keep the queries whose longest list has df >= docs/16, or the others")
@@ -269,32 +270,45 @@ def cpu_baseline(a, corpus_dir, qlog, reps=1):
 
 
 def reference_arm(a, rank, world):
+    """The reference's own CPU implementation of the path (oracle/_ref/ref_tool = the unmodified
+    VacuumEngine::Search, all host threads on one shared engine) on the SAME configuration as
+    our arm: at N GPUs every one of the N partitions is replayed with the same log (one after
+    the other, the host has one set of cores); value = listed postings of all partitions / the
+    summed time, exactly what our arm lists."""
     if rank != 0:
         return
-    corpus_dir, cinfo = ensure_corpus(a, 0, 1)
-    qlog = ensure_query_log(a, corpus_dir)
+    parts = [ensure_corpus(a, p, world) for p in range(world)]
+    qlog = ensure_query_log(a, parts[0][0])
     reps = a.warmup + a.steps
     # keep the whole run within a few minutes: bound the sample by a quick probe
     sample = a.cpu_sample
     kind, threads, probe = cpu_baseline(argparse.Namespace(**{**vars(a), "cpu_sample": min(2000, sample)}),
-                                        corpus_dir, qlog, 1)
+                                        parts[0][0], qlog, 1)
     per_query = probe["seconds"] / max(1, probe["queries"])
     budget_s = 150.0
-    sample = int(max(500, min(sample, budget_s / max(per_query, 1e-9) / reps)))
+    sample = int(max(500, min(sample, budget_s / max(per_query, 1e-9) / reps / world)))
     a2 = argparse.Namespace(**{**vars(a), "cpu_sample": sample})
-    kind, threads, r = cpu_baseline(a2, corpus_dir, qlog, reps)
-    timed = r["rep_seconds"][a.warmup:]
+    per_step = [0.0] * reps
+    listed = queries = 0
+    for d, _ in parts:
+        kind, threads, r = cpu_baseline(a2, d, qlog, reps)
+        for i, t in enumerate(r["rep_seconds"]):
+            per_step[i] += t
+        listed += r["listed_postings"]
+        queries = r["queries"]
+    timed = per_step[a.warmup:]
     ms = 1000.0 * sum(timed) / len(timed)
-    value = r["listed_postings"] / (ms / 1000.0)
+    value = listed / (ms / 1000.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64 scores / u32 doc ids", "data": "synthetic",
-        "config": workload_config(a, cinfo, sample_queries=sample),
-        "queries_per_s": r["queries"] / (ms / 1000.0),
+        "config": workload_config(a, parts[0][1], sample_queries=sample, n_gpus=world),
+        "queries_per_s": queries / (ms / 1000.0),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
-                         "sample": f"first {r['queries']} queries of the {a.workload} log per step, "
-                                   f"{threads} threads on one shared engine, index page-cache resident"},
+                         "sample": f"first {queries} queries of the {a.workload} log per step against each of the "
+                                   f"{world} partition(s) in turn, {threads} threads on one shared engine, "
+                                   f"index page-cache resident"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -311,6 +325,144 @@ def workload_config(a, cinfo, sample_queries=None, n_gpus=1):
         "k": a.k, "partitioning": (f"document-partitioned x{n_gpus}, top-k exchange: all-to-all of query slices + slice merge + all-gather" if n_gpus > 1 else "single index"),
         "l2": "inputs larger than L2: one step streams GBs of distinct posting blocks (126 MB L2)",
     }
+
+
+KERNEL_NAMES = ["search_one_term", "search_two_term", "search_many_term", "search_collect", "merge_units"]
+
+
+def source_hash():
+    """Hash of the sources that define the kernels and the HBM layout: ncu traffic figures are
+    only quoted for the build they were captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("kernels.cu", "kernels.cuh", "host_index.cc", "host_index.h"):
+        h.update(open(os.path.join(ROOT, "wiser_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def committed_traffic(workload, docs, queries, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this exact
+    workload AND this exact build (profiles/r2_traffic.json); None, with the reason, otherwise."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+    except Exception:
+        return None, "no capture committed"
+    e = tj.get(f"{workload}:{docs}:{queries}:{kernel}")
+    if not e:
+        return None, "no capture of this workload"
+    if e.get("source_hash") != source_hash():
+        return None, f"capture is of another build (source hash {e.get('source_hash')}, now {source_hash()})"
+    return e.get("dram_bytes_per_launch"), "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum"
+
+
+def profile_batch(batch, passes=5):
+    """Per-class kernel times (CUDA events around every launch group of the UNCOUNTED kernels,
+    averaged) and the work counters of one extra pass through the counting instantiations."""
+    profs = [batch.profile() for _ in range(passes)]
+    prof = [sum(p[i] for p in profs) / len(profs) for i in range(6)]
+    batch.count_work()
+    return prof, batch.stats()
+
+
+def roofline_of(prof, st, peak, peak_src):
+    """B_touched of the step / CUDA-event time of the search kernels that read it. On a
+    single-class log that is the dominant kernel; on a mixed log the classes' times are summed,
+    because the byte counter is not kept per class."""
+    dom = max(range(4), key=lambda i: prof[i])
+    search_ms = sum(prof[:4])
+    achieved = st.touched_bytes / (search_ms / 1000.0) / 1e9 if search_ms > 0 else 0.0
+    listed_gbs = st.listed_bytes / (search_ms / 1000.0) / 1e9 if search_ms > 0 else 0.0
+    return dom, {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "kernel": KERNEL_NAMES[dom], "kernel_ms": prof[dom], "search_kernels_ms": search_ms,
+        "step_kernel_ms": prof, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": int(st.touched_bytes),
+        "accounting": ("B_touched (SURVEY 8d): per block decoded in full 16*doc_bits (+16*tf_bits where its tfs "
+                       "are read with it) + 16 B metadata, per probed partner block (once per work unit) "
+                       "16*doc_bits + 16 B, 1 norm byte per intersection hit, 4 B per block-max entry scanned, "
+                       "4 B per position read; widths are the REFERENCE's pack widths of that block"),
+        "decoded_postings_per_launch": int(st.decoded_postings),
+        "decoded_postings_per_s": st.decoded_postings / (search_ms / 1000.0) if search_ms > 0 else 0.0,
+        "probe_blocks_per_launch": int(st.probe_blocks), "matches_per_launch": int(st.matches),
+        "listed_bytes_per_launch": int(st.listed_bytes),
+        "listed_achieved": listed_gbs, "listed_frac": listed_gbs / peak,
+    }
+
+
+def secondary_workloads(a, eng, corpus_dir, peak, peak_src, log_fn):
+    """Device-timed and end-to-end numbers of the other BASELINE.json configurations on the same
+    C2 corpus, after the headline: single-term (config 2), 3-5-term skewed AND (config 3), two-term
+    phrases with position verification (config 4, its own corpus with the position column), and the
+    high-high two-term log (both lists long). 5 timed steps each after 2 warm-up steps."""
+    import numpy as np
+    from wiser_b200 import Batch, GpuVacuumEngine
+    from wiser_b200.capi import HIT_DTYPE, PinnedArray
+    out = {}
+    specs = [("single_high", a.queries), ("multi_term", a.queries), ("two_term_hh", a.queries // 4),
+             ("phrase2", a.queries // 5)]
+    for wl, nq in specs:
+        t_start = time.time()
+        a2 = argparse.Namespace(**{**vars(a), "workload": wl, "queries": nq, "query_filter": ""})
+        e2, cdir, own = eng, corpus_dir, False
+        try:
+            if wl.startswith("phrase"):
+                cdir, _ = ensure_corpus(a2, 0, 1)
+                e2, own = GpuVacuumEngine(cdir, device=eng.device, positions=True).Load(), True
+            text = open(ensure_query_log(a2, cdir), "rb").read()
+            qarr = e2.parse_query_log(text, a.k)
+            n = len(qarr)
+            b = Batch(e2, qarr, a.k)
+            for _ in range(2):
+                b.run()
+            b.sync()
+            steps = 5
+            dev_ms = b.time(steps)
+            prof, st = profile_batch(b, 3)
+            _, roof = roofline_of(prof, st, peak, peak_src)
+            hits_p = PinnedArray((n + 2, a.k), HIT_DTYPE)
+            nh_p = PinnedArray((n + 2,), np.int32)
+            text_p = PinnedArray((len(text),), np.uint8)
+            text_p.array[:] = np.frombuffer(text, np.uint8)
+            for _ in range(2):
+                e2.search_log(text_p.array, a.k, hits_p.array, nh_p.array)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2.search_log(text_p.array, a.k, hits_p.array, nh_p.array)
+            e2e_ms = (time.perf_counter() - t0) / steps * 1000.0
+            out[wl] = {"queries_per_step": n, "steps": steps, "device_ms_per_step": dev_ms,
+                       "e2e_ms_per_step": e2e_ms, "queries_per_s": n / (dev_ms / 1000.0),
+                       "e2e_queries_per_s": n / (e2e_ms / 1000.0),
+                       "listed_postings_per_s": int(st.listed_postings) / (dev_ms / 1000.0),
+                       "roofline_frac": roof["frac"], "listed_frac": roof["listed_frac"],
+                       "touched_bytes": int(st.touched_bytes), "decoded_postings": int(st.decoded_postings),
+                       "matches": int(st.matches), "kernel": roof["kernel"], "step_kernel_ms": prof,
+                       "positions_index": wl.startswith("phrase")}
+            b.close()
+            del hits_p, nh_p, text_p
+        except Exception as e:  # a secondary line must never take the headline down
+            out[wl] = {"error": str(e)[:300]}
+        finally:
+            if own:
+                e2.close()
+        log_fn(f"secondary workload {wl}: {out[wl]} ({time.time() - t_start:.1f}s)")
+    return out
+
+
+def partition_oracles(a, world, sample_terms):
+    """Rank 0's checker at N > 1: one CPU oracle per partition directory in partition mode
+    (collection-wide N, average length and df of the sampled terms), merged on the host."""
+    from oracle_py import OracleIndex
+    from wiser_b200.dist import combine_partition_stats
+    oras = [OracleIndex(ensure_corpus(a, p, world)[0]) for p in range(world)]
+    total, bases, avg = combine_partition_stats([o.num_docs for o in oras], [o.avg_doc_len for o in oras])
+    gdf = {}
+    for t in sample_terms:
+        gdf[t] = sum(max(0, o.df(t)) for o in oras)
+    for o in oras:
+        o.set_global_stats(total, avg)
+        for t, d in gdf.items():
+            o.set_global_df(t, d)
+    return oras, bases
 
 
 # ---------------------------------------------------------------------------------------------
@@ -391,13 +543,7 @@ def ours(a, rank, world, local_rank):
         dev_ms = float(t.item())
     ms_per_step = dev_ms / a.steps
 
-    # per-kernel durations: CUDA events around every launch group of the SAME (uncounted) kernels,
-    # averaged over a few passes; algorithmic bytes: one extra pass through the counting
-    # instantiations of the same kernels (identical work, bookkeeping on)
-    profs = [batch.profile() for _ in range(5)]
-    prof = [sum(p[i] for p in profs) / len(profs) for i in range(6)]
-    batch.count_work()
-    st = batch.stats()
+    prof, st = profile_batch(batch)
     listed = int(st.listed_postings)
     if world > 1:
         t = torch.tensor([listed, int(st.touched_bytes), int(st.decoded_postings)], device="cuda", dtype=torch.int64)
@@ -408,44 +554,23 @@ def ours(a, rank, world, local_rank):
     value = listed_all / (ms_per_step / 1000.0)
 
     # ---- roofline of the dominant kernel (this rank)
-    names = ["search_one_term", "search_two_term", "search_many_term", "search_collect", "merge_units"]
-    dom = max(range(4), key=lambda i: prof[i])
     peak, peak_src = measured_peak_gbs()
-    achieved = st.touched_bytes / (prof[dom] / 1000.0) / 1e9 if prof[dom] > 0 else 0.0
-    listed_gbs = st.listed_bytes / (prof[dom] / 1000.0) / 1e9 if prof[dom] > 0 else 0.0
-    # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of
-    # this exact workload (profiles/r1_traffic.json), null when no capture matches
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        key = f"{a.workload}:{a.docs}:{a.queries}:{names[dom]}"
-        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    # K1 (block decode) on the whole index, timed alone
-    k1 = None
+    dom, roofline = roofline_of(prof, st, peak, peak_src)
+    traffic, traffic_src = committed_traffic(a.workload, a.docs, a.queries, KERNEL_NAMES[dom])
+    roofline["traffic"], roofline["traffic_source"] = traffic, traffic_src
+    roofline["source_hash"] = source_hash()
+    # K1 (block decode) on the whole index, timed alone: algorithmic bytes = every block's reference
+    # doc-id and tf packs + 16 B (listed_bytes of a log naming every list once)
     try:
         eng.decode_all()
         _, k1_ms = eng.decode_all()
-        k1_alg = info.n_postings_global  # placeholder, replaced below
+        roofline["k1_decode_all"] = {"ms": k1_ms, "postings_per_s": info.n_postings / (k1_ms / 1000.0),
+                                     "payload_gbs": info.payload_bytes / (k1_ms / 1000.0) / 1e9}
     except Exception:
-        k1_ms = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": names[dom], "kernel_ms": prof[dom], "step_kernel_ms": prof,
-                "listed_achieved": listed_gbs, "listed_frac": listed_gbs / peak,
-                "note": ("achieved = reference-format (algorithmic) bytes of the blocks the kernel actually read "
-                         "(B_touched, SURVEY 8d) / CUDA-event time; listed_* = same with every block of every "
-                         "listed posting list (exhaustive bound B(q))"),
-                "algorithmic_bytes_per_launch": int(st.touched_bytes), "peak_source": peak_src,
-                "listed_bytes_per_launch": int(st.listed_bytes),
-                "decoded_postings_per_s": st.decoded_postings / (prof[dom] / 1000.0) if prof[dom] > 0 else 0.0,
-                "bytes_per_decoded_posting": st.touched_bytes / max(1, st.decoded_postings),
-                "k1_decode_all": ({"ms": k1_ms, "postings_per_s": info.n_postings / (k1_ms / 1000.0),
-                                   "payload_gbs": info.payload_bytes / (k1_ms / 1000.0) / 1e9}
-                                  if k1_ms else None)}
+        roofline["k1_decode_all"] = None
 
     # ---- e2e through the host-buffer C ABI (term lookup + H2D + kernels + D2H every step)
-    e2e_steps = max(1, min(a.steps, 5))
+    e2e_steps = max(1, min(a.steps, 20))
     t_parse = t_search = 0.0
     if world == 1:
         hits_p = PinnedArray((n + 2, a.k), HIT_DTYPE)
@@ -479,7 +604,7 @@ def ours(a, rank, world, local_rank):
                 batch2.sync()
             t_parse += t1 - t0
             t_search += time.perf_counter() - t1
-    for _ in range(2):
+    for _ in range(3):
         e2e_step()
     if world > 1:
         dist.barrier()
@@ -492,6 +617,7 @@ def ours(a, rank, world, local_rank):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    merged_hits = merged_n = None
     if world > 1:
         # cross-check of the exchange (outside every timed region): the scatter exchange used in
         # the timed steps must give, on every rank, what a plain all-gather + full merge gives
@@ -509,6 +635,7 @@ def ours(a, rank, world, local_rank):
         m = np.arange(a.k)[None, :] < n_ag[:, None]
         assert np.array_equal(h_sc["doc_id"][m], h_ag["doc_id"][m])
         assert np.array_equal(h_sc["score"][m].view(np.uint64), h_ag["score"][m].view(np.uint64))
+        merged_hits, merged_n = h_sc, n_sc
         # ... and the e2e path (device front end; read back on rank 0) the same
         if rank == 0:
             he = hits_t.numpy().view(HIT_DTYPE).reshape(n, a.k)
@@ -530,7 +657,7 @@ def ours(a, rank, world, local_rank):
             d2h_bytes = int(n * 4 + 4 + total_hits * 16)
     e2e = {"value": listed_all / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(len(text)),
-           "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1000.0,
+           "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1000.0, "steps": e2e_steps,
            "queries_per_s": n / e2e_s,
            "parse_lookup_ms": 1000.0 * t_parse / e2e_steps, "search_ms": 1000.0 * t_search / e2e_steps,
            "path": ("wsr_search_log: pinned query-log text -> H2D -> parse + term lookup + planning kernels "
@@ -538,21 +665,37 @@ def ours(a, rank, world, local_rank):
                     "pinned query-log text -> wsr_batch_reset_log (H2D + parse/lookup/plan kernels) -> search "
                     "kernels -> NCCL all-to-all + merge kernel + all-gather -> D2H of the merged top-k on rank 0")}
 
-    # ---- parity spot check against the CPU oracle (outside every timed region)
+    # ---- parity spot check against the CPU oracle (outside every timed region). N = 1: the oracle
+    # on the same directory. N > 1: rank 0 checks the MERGED result against one oracle per partition
+    # in partition mode (collection statistics), merged on the host.
     parity = None
-    if a.parity_sample > 0 and world == 1:
-        from oracle_py import OracleIndex, parse_query_line
+    if a.parity_sample > 0 and rank == 0:
+        from oracle_py import OracleIndex, parse_query_line, partitioned_search
         from parity import check_topk
-        ora = OracleIndex(corpus_dir)
-        hits, nh = batch.fetch()
         lines = text.decode().split("\n")
         idxs = list(range(0, n, max(1, n // a.parity_sample)))[:a.parity_sample]
-        for i in idxs:
-            terms, is_phrase = parse_query_line(lines[i])
-            rd, rs, _ = ora.search(terms, a.k, is_phrase=is_phrase)
-            fd, fs, _ = ora.search(terms, 1 << 30, is_phrase=is_phrase)
-            check_topk(rd, rs, hits["doc_id"][i, :nh[i]], hits["score"][i, :nh[i]], fd, fs, what=lines[i])
-        parity = {"queries_checked": len(idxs), "against": "CPU oracle (bit-exact scores, tie-aware docs)"}
+        if world == 1:
+            ora = OracleIndex(corpus_dir)
+            hits, nh = batch.fetch()
+            for i in idxs:
+                terms, is_phrase = parse_query_line(lines[i])
+                rd, rs, _ = ora.search(terms, a.k, is_phrase=is_phrase)
+                fd, fs, _ = ora.search(terms, 1 << 30, is_phrase=is_phrase)
+                check_topk(rd, rs, hits["doc_id"][i, :nh[i]], hits["score"][i, :nh[i]], fd, fs, what=lines[i])
+            parity = {"queries_checked": len(idxs), "against": "CPU oracle (bit-exact scores, tie-aware docs)"}
+        else:
+            sample_terms = sorted({t for i in idxs for t in parse_query_line(lines[i])[0]})
+            oras, bases = partition_oracles(a, world, sample_terms)
+            for i in idxs:
+                terms, is_phrase = parse_query_line(lines[i])
+                fd, fs, _ = partitioned_search(oras, bases, terms, 1 << 30, is_phrase)
+                check_topk(fd[:a.k], fs[:a.k], merged_hits["doc_id"][i, :merged_n[i]],
+                           merged_hits["score"][i, :merged_n[i]], fd, fs, what=lines[i])
+            parity = {"queries_checked": len(idxs),
+                      "against": f"{world} CPU oracles, one per partition directory, in partition mode (collection "
+                                 f"N / average length / df), merged on the host; bit-exact scores, tie-aware docs"}
+            for o in oras:
+                o.close()
 
     cpu = None
     if rank == 0 and not a.no_cpu_baseline and world == 1:
@@ -562,8 +705,21 @@ def ours(a, rank, world, local_rank):
                    "queries_per_s": r["qps"], "seconds": r["seconds"],
                    "sample": f"first {r['queries']} queries of the same log, {threads} threads on one shared "
                              f"engine, same index directory (page-cache resident), k={a.k}"}
+            # T = 1 (SURVEY 8d asks for both): a fifth of the sample on one thread
+            one = argparse.Namespace(**{**vars(a), "cpu_sample": max(500, a.cpu_sample // 5)})
+            if kind == "reference":
+                r1 = run_reference_tool(corpus_dir, qlog, a.k, 1, 1, one.cpu_sample)
+            else:
+                r1 = run_oracle_port(corpus_dir, qlog, a.k, 1, 1, one.cpu_sample)
+            cpu["single_thread"] = {"value": r1["listed_postings_per_s"], "unit": UNIT, "cores": 1,
+                                    "queries_per_s": r1["qps"], "seconds": r1["seconds"],
+                                    "sample": f"first {r1['queries']} queries of the same log, 1 thread"}
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+
+    workloads = None
+    if rank == 0 and world == 1 and not a.no_secondary:
+        workloads = secondary_workloads(a, eng, corpus_dir, peak, peak_src, log)
 
     if rank == 0:
         line = {
@@ -575,16 +731,14 @@ def ours(a, rank, world, local_rank):
             "wall_ms_per_step": wall_ms / a.steps,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(st.kernel_launches) * a.steps + (a.steps if world > 1 else 0),
-            "parity": parity,
+            "parity": parity, "workloads": workloads,
             "index": {"load_s": load_s, "hbm_bytes": int(info.hbm_bytes), "payload_bytes": int(info.payload_bytes),
                       "blocks": int(info.n_blocks), "corpus_build_s": cinfo.get("wall_s")},
             "matches_per_step": int(st.matches), "work_units_per_step": int(st.work_units),
         }
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    # orderly teardown: torch buffers that lived on the batch streams go first, then the batches
-    # (their streams), then the index; the process leaves through os._exit so that interpreter
-    # shutdown cannot run CUDA destructors in an arbitrary order across the two CUDA runtimes
-    # (torch's and libwsr's statically linked one).
+    # orderly teardown, then a normal return: torch buffers that lived on the batch streams go
+    # first, then the batches (their streams), then the index, then the process group
     if shard is not None:
         shard._bufs.clear()
     torch.cuda.synchronize()
@@ -595,9 +749,10 @@ def ours(a, rank, world, local_rank):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 def main():

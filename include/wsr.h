@@ -204,12 +204,19 @@ int wsr_batch_count_work(wsr_batch *b);
  * touched_bytes and matches are 0 unless that run was wsr_batch_count_work. */
 typedef struct {
   uint64_t listed_postings;   /* sum over valid queries of sum_i df_i (shard-local lists) */
-  uint64_t decoded_postings;  /* 128 x doc-id blocks actually decoded */
-  uint64_t touched_bytes;     /* algorithmic bytes of the blocks actually read (+16 B meta each) */
+  uint64_t decoded_postings;  /* postings of the blocks decoded IN FULL: driver blocks, the partner
+                               * blocks of the merge path, the blocks a single-term query scores */
+  uint64_t touched_bytes;     /* B_touched: per block decoded in full its doc-id pack
+                               * (+ its tf pack where tfs are read with it) + 16 B metadata, per
+                               * probed partner block (once per work unit) its doc-id pack + 16 B,
+                               * + 1 norm byte per intersection hit, + 4 B per block-max entry scanned
+                               * (+ 4 B per position read by phrase queries) */
   uint64_t listed_bytes;      /* algorithmic bytes of every block of every listed list */
   uint64_t matches;           /* intersection hits scored */
   uint64_t work_units;        /* warp work units scheduled */
   uint32_t kernel_launches;   /* launches per run */
+  uint32_t reserved;
+  uint64_t probe_blocks;      /* partner blocks of which single records were read (probe path) */
 } wsr_batch_stats;
 int wsr_batch_get_stats(wsr_batch *b, wsr_batch_stats *s);
 

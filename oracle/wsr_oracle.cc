@@ -275,6 +275,19 @@ struct Index {
   int doc_count = 0;
   double avg_len = 0;
   double cache[256];               // Bm25Similarity::cache_
+  // Partition mode (document-partitioned deployments): a partition directory scored
+  // with the COLLECTION's statistics — global N, average length and per-term df — so that its
+  // top-k lists merge into what one big reference index would return.
+  std::unordered_map<uint64_t, int32_t> global_df;   // list offset -> collection-wide df
+
+  void BuildCache() {
+    // Bm25Similarity::BuildCache, scoring.h:85-90: k1*(1 - b + b*len/avg), left to right.
+    const double k1 = 1.2, b = 0.75;
+    for (int i = 0; i < 256; i++) {
+      uint32_t field_length = Char4ToUint(i & 0xff);
+      cache[i] = k1 * (1 - b + b * field_length / avg_len);
+    }
+  }
 
   bool Load(const std::string &dir, std::string *err) {
     if (!vacuum.Open(dir + "/my.vacuum") || vacuum.n < 100 || vacuum.p[0] != kVacuumMagic) {
@@ -311,12 +324,7 @@ struct Index {
       norms[id] = c;
       doc_count++;
     }
-    // Bm25Similarity::BuildCache, scoring.h:85-90: k1*(1 - b + b*len/avg), left to right.
-    const double k1 = 1.2, b = 0.75;
-    for (int i = 0; i < 256; i++) {
-      uint32_t field_length = Char4ToUint(i & 0xff);
-      cache[i] = k1 * (1 - b + b * field_length / avg_len);
-    }
+    BuildCache();
     return true;
   }
 };
@@ -341,8 +349,9 @@ struct Processor {
   MinHeap heap;
 
   // ProcessorBase ctor, query_processing.h:530-548
-  Processor(const Index &ix_, std::vector<ListCursor> &its_, int k_) : ix(ix_), its(its_), k(k_) {
-    for (auto &it : its) idfs.push_back(EsIdf(ix.doc_count, (int)it.Size()));
+  Processor(const Index &ix_, std::vector<ListCursor> &its_, int k_, const std::vector<int32_t> &dfs)
+      : ix(ix_), its(its_), k(k_) {
+    for (size_t i = 0; i < its.size(); i++) idfs.push_back(EsIdf(ix.doc_count, dfs[i]));
   }
 
   // CalcDocScoreLossy, scoring.h:124-145, with TfNormLossy (:65-69). The reference indexes
@@ -508,10 +517,12 @@ int Search(const Index &ix, const char *const *terms, const size_t *lens, int n_
     if (f == ix.term_to_off.end()) continue;
     its.emplace_back();
     if (!its.back().Reset(ix.vacuum.p, f->second)) return -2;
+    // :217-219 — the posting-list size; in partition mode the collection-wide df of the term
+    auto g = ix.global_df.find(f->second);
+    dfs->push_back(g == ix.global_df.end() ? (int32_t)its.back().Size() : g->second);
   }
-  if (its.empty() || (int)its.size() < n_terms) return 0;  // :213-215
-  for (auto &it : its) dfs->push_back((int32_t)it.Size()); // :217-219
-  Processor p(ix, its, k);
+  if (its.empty() || (int)its.size() < n_terms) { dfs->clear(); return 0; }  // :213-215
+  Processor p(ix, its, k, *dfs);
   p.is_phrase = is_phrase;
   // qq_search::ProcessQueryDelta, query_processing.h:956-979
   if (its.size() == 1) p.One();
@@ -540,6 +551,19 @@ wsr_oracle_index *wsr_oracle_open(const char *dir, char *err, size_t errlen) {
 void wsr_oracle_close(wsr_oracle_index *h) { delete h; }
 int wsr_oracle_num_docs(const wsr_oracle_index *h) { return h->ix.doc_count; }
 double wsr_oracle_avg_doc_len(const wsr_oracle_index *h) { return h->ix.avg_len; }
+int wsr_oracle_set_global_stats(wsr_oracle_index *h, int n_docs_global, double avg_len_global) {
+  if (n_docs_global <= 0 || !(avg_len_global > 0)) return -1;
+  h->ix.doc_count = n_docs_global;
+  h->ix.avg_len = avg_len_global;
+  h->ix.BuildCache();
+  return 0;
+}
+int wsr_oracle_set_global_df(wsr_oracle_index *h, const char *term, size_t len, int32_t df_global) {
+  auto f = h->ix.term_to_off.find(std::string(term, len));
+  if (f == h->ix.term_to_off.end()) return 1;
+  h->ix.global_df[f->second] = df_global;
+  return 0;
+}
 int wsr_oracle_term_count(const wsr_oracle_index *h) { return (int)h->ix.term_to_off.size(); }
 int wsr_oracle_term_at(const wsr_oracle_index *h, int i, char *buf, int cap) {
   if (i < 0 || (size_t)i >= h->ix.term_order.size()) return -1;

@@ -35,6 +35,8 @@ def lib():
         L.wsr_oracle_avg_doc_len.argtypes = [C.c_void_p]
         L.wsr_oracle_avg_doc_len.restype = C.c_double
         L.wsr_oracle_term_count.argtypes = [C.c_void_p]
+        L.wsr_oracle_set_global_stats.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.wsr_oracle_set_global_df.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int32]
         L.wsr_oracle_term_at.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.wsr_oracle_term_df.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.wsr_oracle_term_df.restype = C.c_int64
@@ -93,6 +95,15 @@ class OracleIndex:
             out.append(buf.raw[:n].decode())
         return out
 
+    def set_global_stats(self, n_docs_global, avg_len_global):
+        """Partition mode: score with the collection's N and average length."""
+        if lib().wsr_oracle_set_global_stats(self._h, int(n_docs_global), float(avg_len_global)) != 0:
+            raise ValueError("bad global statistics")
+
+    def set_global_df(self, term, df_global):
+        t = term.encode()
+        return lib().wsr_oracle_set_global_df(self._h, t, len(t), int(df_global)) == 0
+
     def df(self, term):
         t = term.encode()
         return lib().wsr_oracle_term_df(self._h, t, len(t))
@@ -129,6 +140,23 @@ class OracleIndex:
         if rc != 0:
             raise RuntimeError(f"oracle search rc={rc}")
         return docs[:nh.value].copy(), scores[:nh.value].copy(), dfs[:ndf.value].tolist()
+
+
+def partitioned_search(oracles, doc_bases, terms, k, is_phrase=False):
+    """One query against document partitions (OracleIndex objects in partition mode, local doc
+    ids): every partition's top-k and FULL match list with global doc ids, concatenated. The
+    caller picks the global top-k with the tie-aware checker (tests/parity.py)."""
+    docs, scores, dfs = [], [], None
+    for ora, base in zip(oracles, doc_bases):
+        d, s, f = ora.search(terms, k, is_phrase=is_phrase)
+        docs.append(d.astype(np.int64) + base)
+        scores.append(s)
+        if f:
+            dfs = f
+    docs = np.concatenate(docs) if docs else np.zeros(0, np.int64)
+    scores = np.concatenate(scores) if scores else np.zeros(0)
+    order = np.lexsort((docs, -scores))
+    return docs[order].astype(np.int32), scores[order], dfs or []
 
 
 def parse_query_line(line):

@@ -109,3 +109,35 @@ def test_char4_norm_examples(golden_dir):
     for doc in range(0, ix.num_docs, 97):
         b = ix.norm_byte(doc)
         assert 0 <= b < 128
+
+
+def test_partition_mode_reproduces_the_whole_index(golden_dir):
+    """SURVEY §8e oracle: the two partition directories of zipf2k (indexed separately, local doc
+    ids), scored in partition mode with the collection's N, average length and per-term df, merge
+    into exactly what the whole index — and hence the unmodified reference — returns."""
+    from oracle_py import partitioned_search
+    from parity import check_topk
+    d = os.path.join(golden_dir, "zipf2k")
+    whole = OracleIndex(d)
+    gdf = dict((l.split()[0], int(l.split()[1])) for l in open(os.path.join(d, "terms.txt")))
+    parts = [OracleIndex(os.path.join(golden_dir, f"zipf2k_p{s}")) for s in range(2)]
+    for p in parts:
+        p.set_global_stats(whole.num_docs, whole.avg_doc_len)
+        for t in p.terms():
+            assert p.set_global_df(t, gdf[t])
+    bases = [0, parts[0].num_docs]   # num_docs is global now: take the split from the fixture
+    bases = [0, 1000]
+    lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
+    checked = 0
+    for line in lines[::5]:
+        terms, is_phrase = parse_query_line(line)
+        if is_phrase:
+            continue           # the partition fixtures were written without positions
+        rd, rs, rdf = whole.search(terms, 10)
+        fd, fs, _ = whole.search(terms, 1 << 30)
+        gd, gs, gdfs = partitioned_search(parts, bases, terms, 10)
+        check_topk(rd, rs, gd[:10], gs[:10], fd, fs, what=line)
+        if len(rd):
+            assert gdfs == rdf, line
+        checked += 1
+    assert checked > 500

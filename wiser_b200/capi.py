@@ -32,7 +32,8 @@ class BatchStats(C.Structure):
     _fields_ = [("listed_postings", C.c_uint64), ("decoded_postings", C.c_uint64),
                 ("touched_bytes", C.c_uint64), ("listed_bytes", C.c_uint64),
                 ("matches", C.c_uint64), ("work_units", C.c_uint64),
-                ("kernel_launches", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
+                ("probe_blocks", C.c_uint64)]
 
 
 EXPORTS = [

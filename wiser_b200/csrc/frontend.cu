@@ -82,6 +82,8 @@ __device__ __forceinline__ void PlanOne(const DevIndexView &ix, DevQuery &q, uin
     q.driver = best;
     q.out_slot = i;
     cls = n_terms == 1 ? kClassOne : n_terms == 2 ? kClassTwo : kClassMany;
+    if (UseMergePath(n_terms, q.flags & kQueryPhrase, drv_blocks, probe_blocks, ix.merge_ratio_x4))
+      q.flags |= kQueryMerge;
     q.n_units = cls == kClassOne ? 1u : (drv_blocks + (uint32_t)ub - 1u) / (uint32_t)ub;
     it.v[cls] = 1;
     it.v[3 + cls] = q.n_units;

@@ -197,7 +197,8 @@ __device__ __forceinline__ double TopKKth(const TopK &t, int k) {
 template <bool ON>
 struct UnitStatsT {
   static constexpr bool kOn = ON;
-  unsigned long long decoded, bytes, matches;
+  unsigned long long decoded, bytes, matches, probe_blocks;
+  uint32_t last_probe;   // last partner block counted by the current unit (a block counts once per unit)
 };
 #define WSR_STAT(...) do { if constexpr (ST::kOn) { __VA_ARGS__ } } while (0)
 
@@ -223,6 +224,26 @@ struct __align__(16) ProbeScratch {
   HitRec hits[kHitCap];          // intersection hits awaiting scoring
 };
 struct __align__(16) NoScratch { uint32_t unused; };
+
+// Merge-mode scratch of the two-term kernel (balanced lists, ProcessTwoMerge): the driver list's
+// current blocks are a SET in shared memory that the partner list's decoded postings are tested
+// against — a byte map hashed by the low doc-id bits (byte stores of the same value race
+// benignly, so no shared-memory atomics), backed by a ring of the set blocks' doc ids and tfs
+// that settles false positives and yields the driver posting's tf.
+constexpr int kMapBytes = 4096;        // doc & (kMapBytes - 1)
+constexpr int kRingBlocks = 4;         // driver blocks whose docs/tfs stay addressable
+constexpr int kRingMask = kRingBlocks * 128 - 1;
+constexpr int kSurvCap = 64;           // 31 queued + up to 32 of one slot pass
+struct __align__(16) MergeScratch {
+  uint8_t map[kMapBytes];
+  uint32_t rdoc[kRingBlocks * 128];    // doc ids of driver blocks ja-4 .. ja-1, slot = posting index & kRingMask
+  uint8_t rtf[kRingBlocks * 128];      // min(tf, 255); 255 = read the exact tf from the payload
+  uint2 surv[kSurvCap];                // partner postings whose map byte was set: {doc, tf}
+};
+union __align__(16) TwoScratch {
+  ProbeScratch p;
+  MergeScratch m;
+};
 
 // Emits one unit's result: straight to the caller's hit array when the query has one unit,
 // else to the unit's candidate slot for the merge pass. doc ids leave as GLOBAL ids.
@@ -557,12 +578,17 @@ __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, u
     *hit = slot >= 0;
     *pos = ((p.first + j) << 7) | (4u * rec + (uint32_t)max(slot, 0));
   }
-  // accounting: each distinct probe block touched counts once (candidates are doc-ascending)
+  // accounting (B_touched): a partner block of which a record was read counts once per
+  // unit with its doc-id pack + 16 B of metadata. Candidates ascend across lanes and batches, so a
+  // block is new when it differs from the previous lane's and lies past the last one counted.
   if constexpr (ST::kOn) {
-    const uint32_t prev = __shfl_up_sync(kFull, has ? j : kNoDoc, 1);
-    const bool fresh = has && (lane == 0 || j != prev);
-    WSR_STAT(st.decoded += __reduce_add_sync(kFull, fresh ? ShN(info.z) : 0u););
-    WSR_STAT(st.bytes += __reduce_add_sync(kFull, fresh ? AlgBytes(info.z, false) : 0u););
+    const uint32_t gj = has ? p.first + j : kNoDoc;
+    const uint32_t prev = __shfl_up_sync(kFull, gj, 1);
+    const bool fresh = has && (lane == 0 || gj != prev) && (st.last_probe == kNoDoc || gj > st.last_probe);
+    st.probe_blocks += __popc(__ballot_sync(kFull, fresh));
+    st.bytes += __reduce_add_sync(kFull, fresh ? AlgBytes(info.z, false) : 0u);
+    const uint32_t mxj = __reduce_max_sync(kFull, has ? gj + 1u : 0u);
+    if (mxj && (st.last_probe == kNoDoc || mxj - 1u > st.last_probe)) st.last_probe = mxj - 1u;
   }
   return true;
 }
@@ -665,7 +691,7 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
     else OfferToTopK(bv, qi, multi, (int)q.k, has, s, doc, top, published, lane);
   }
   WSR_STAT(st.matches += nq;);
-  WSR_STAT(st.bytes += 17ull * nq;);   // per hit: 2 x 8 B of tf record words + 1 norm byte
+  WSR_STAT(st.bytes += nq;);   // one norm byte per intersection hit
   __syncwarp();
 }
 
@@ -819,6 +845,234 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
 }
 
+// ---- two-term units, merge mode: lists of similar length ---------------------------------------
+// TwoTermNonPhraseQueryProcessor::Process (query_processing.h:656-677) advances both iterators in
+// lock step when neither list is much longer than the other. The probe path above spends a filter
+// word, a skip-metadata lookup and three dependent loads per survivor on such queries, although
+// the partner's blocks under a driver block are no more bytes than its filter words. Here both
+// lists are streamed once, coalesced: driver blocks are decoded into a set in shared memory (byte
+// map hashed by the low doc-id bits + a ring of their doc ids and tfs), every partner block that
+// overlaps them is decoded and its postings tested against the map; the few that pass are queued
+// with their tf and, 32 at a time, located in the ring by binary search (which settles hash
+// aliases and yields the driver posting's tf), scored and offered to the top-k. No filter words,
+// no record search, no tf gathers: the only random access left is the norm byte of a hit.
+__device__ __forceinline__ uint2 LoadRec2(const DevIndexView &ix, const uint4 info, int lane) {
+  // the lane's doc record in the 32/64-bit formats; zeros past the block's records and for
+  // 128-bit records (those are decoded on demand)
+  const uint32_t bits = info.z, rc = ShRcode(bits), nl = (ShN(bits) + 3u) >> 2;
+  uint2 r = make_uint2(0u, 0u);
+  if ((uint32_t)lane < nl) {
+    const uint4 *src = ix.payload + info.y;
+    if (rc == 0u) r.x = __ldg(reinterpret_cast<const uint32_t *>(src) + lane);
+    else if (rc == 1u) r = __ldg(reinterpret_cast<const uint2 *>(src) + lane);
+  }
+  return r;
+}
+__device__ __forceinline__ uint32_t LoadTfWord(const DevIndexView &ix, const uint4 info, int lane) {
+  // the lane's tf record in the 4/8-bit formats (32-bit tfs are read on demand)
+  const uint32_t bits = info.z, tc = ShTcode(bits), nl = (ShN(bits) + 3u) >> 2;
+  uint32_t v = 0u;
+  if ((uint32_t)lane < nl) {
+    const uint4 *src = ix.payload + info.y + DocGranules(bits);
+    if (tc == 0u) v = __ldg(reinterpret_cast<const unsigned short *>(src) + lane);
+    else if (tc == 1u) v = __ldg(reinterpret_cast<const uint32_t *>(src) + lane);
+  }
+  return v;
+}
+
+// Settles the queued partner postings against the ring (driver blocks [max(b0, ja-4), ja)), scores
+// the real matches and offers them to the top-k.
+template <class ST>
+__device__ __forceinline__ void MergeFlush(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
+                                           uint32_t qi, const CtaShared *sh, MergeScratch *ms, int nq,
+                                           uint32_t ja, uint32_t b0, uint32_t first_a, int drv, double idf0,
+                                           double idf1, TopK &top, double &published, bool multi, int lane,
+                                           ST &st) {
+  __syncwarp();
+  const uint32_t lo_blk = ja >= b0 + (uint32_t)kRingBlocks ? ja - (uint32_t)kRingBlocks : b0;
+  const uint32_t glo = lo_blk << 7, ghi = ja << 7;   // posting indices of the driver list held by the ring
+  for (int base = 0; base < nq; base += 32) {
+    bool has = base + lane < nq;
+    uint32_t x = 0u, tfb = 0u, g = glo;
+    if (has) {
+      const uint2 sv = ms->surv[base + lane];
+      x = sv.x;
+      tfb = sv.y;
+    }
+#pragma unroll
+    for (uint32_t s = (uint32_t)kRingBlocks * 64u; s; s >>= 1) {   // lower bound of x in the ring
+      const uint32_t t = g + s;
+      if (t <= ghi && ms->rdoc[(t - 1u) & (uint32_t)kRingMask] < x) g = t;
+    }
+    has = has && g < ghi && ms->rdoc[g & (uint32_t)kRingMask] == x;
+    double s = 0.0;
+    if (has) {
+      uint32_t tfa = ms->rtf[g & (uint32_t)kRingMask];
+      if (tfa == 255u) tfa = TfAt(ix, ((first_a + (g >> 7)) << 7) | (g & 127u));
+      const double cn = sh->cache[__ldg(ix.norms + x)];
+      // query order: term 0 first (scoring.h:124-145)
+      s = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? tfa : tfb, cn));
+      s = __dadd_rn(s, TermScore(idf1, drv == 0 ? tfb : tfa, cn));
+    }
+    WSR_STAT(const unsigned hm = __ballot_sync(kFull, has); st.matches += __popc(hm); st.bytes += __popc(hm););
+    OfferToTopK(bv, qi, multi, (int)q.k, has, s, (int)x, top, published, lane);
+  }
+  __syncwarp();
+}
+
+template <class ST>
+__device__ void ProcessTwoMerge(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
+                                uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
+                                const CtaShared *sh, MergeScratch *ms, int lane, ST &st) {
+  const int drv = (int)q.driver, oth = 1 - drv;
+  const uint4 la = __ldg(&ix.lists[q.term[drv]]);
+  const uint4 lb = __ldg(&ix.lists[q.term[oth]]);
+  const double idf0 = __ldg(&ix.idf[q.term[0]]), idf1 = __ldg(&ix.idf[q.term[1]]);
+  const uint32_t first_a = la.x, first_b = lb.x, nb = lb.y;
+  const bool multi = q.n_units > 1;
+  constexpr uint32_t kMapMask = (uint32_t)kMapBytes - 1u;
+  TopK top;
+  TopKInit(top);
+  double published = 0.0;
+  // the scratch is shared with the probe path: start from a clean map
+  {
+    uint4 *m4 = reinterpret_cast<uint4 *>(ms->map);
+    for (int i = lane; i < kMapBytes / 16; i += 32) m4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  uint4 infoA = __ldg(&ix.blk_info[first_a + b0]);
+  // the partner's first block that reaches the unit's doc range (docs of block b0 are >= its base)
+  uint32_t jb;
+  {
+    ProbeList pb;
+    ProbeInit(pb, ix, lb, lane);
+    jb = ProbeFind(pb, infoA.x, lane);
+  }
+  if (jb == kNoDoc) {
+    EmitTopK(bv, q, local, top, lane);
+    return;
+  }
+  // software pipelines over both lists: a block's info arrives two blocks ahead of its use, the
+  // lane's records one block ahead
+  uint4 infoA_nxt = b0 + 1u < b1 ? __ldg(&ix.blk_info[first_a + b0 + 1u]) : infoA;
+  uint2 rawA = LoadRec2(ix, infoA, lane);
+  uint32_t tfwA = LoadTfWord(ix, infoA, lane);
+  uint4 infoB = __ldg(&ix.blk_info[first_b + jb]);
+  uint4 infoB_nxt = jb + 1u < nb ? __ldg(&ix.blk_info[first_b + jb + 1u]) : infoB;
+  uint2 rawB = LoadRec2(ix, infoB, lane);
+  uint32_t tfwB = LoadTfWord(ix, infoB, lane);
+  uint32_t ja = b0, jr = b0;   // driver blocks [jr, ja) are in the map; [max(b0, ja-4), ja) in the ring
+  uint32_t q_lo = b0;          // oldest driver block a queued partner posting may match
+  int nq = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  __syncwarp();
+  for (; jb < nb; jb++) {
+    // ---- partner block jb: request block jb+1's records and block jb+2's info, then decode
+    uint2 rawB_nxt = make_uint2(0u, 0u);
+    uint32_t tfwB_nxt = 0u;
+    uint4 infoB_nxt2 = infoB_nxt;
+    if (jb + 1u < nb) {
+      rawB_nxt = LoadRec2(ix, infoB_nxt, lane);
+      tfwB_nxt = LoadTfWord(ix, infoB_nxt, lane);
+      if (jb + 2u < nb) infoB_nxt2 = __ldg(&ix.blk_info[first_b + jb + 2u]);
+    }
+    const uint32_t nB = ShN(infoB.z), nlB = (nB + 3u) >> 2;
+    uint32_t dB[4];
+    if (ShRcode(infoB.z) == 2u) DecodeDocs(ix, infoB, lane, dB);
+    else DecodeRaw(infoB, make_uint4(rawB.x, rawB.y, 0u, 0u), dB);
+    const uint32_t lastB = __shfl_sync(kFull, dB[3], (int)nlB - 1);
+    WSR_STAT(st.decoded += nB; st.bytes += AlgBytes(infoB.z, true););
+    for (;;) {
+      // ---- driver blocks that reach into this partner block join the set
+      while (ja < b1 && (infoA.x < lastB || ja == 0u) && ja - jr < (uint32_t)kRingBlocks) {
+        if (nq && q_lo + (uint32_t)kRingBlocks <= ja) {   // the ring slot reused below may hold a queued posting's match
+          MergeFlush(ix, bv, q, qi, sh, ms, nq, ja, b0, first_a, drv, idf0, idf1, top, published, multi, lane, st);
+          nq = 0;
+        }
+        const uint32_t nA = ShN(infoA.z), nlA = (nA + 3u) >> 2, tcA = ShTcode(infoA.z);
+        uint32_t dA[4];
+        if (ShRcode(infoA.z) == 2u) DecodeDocs(ix, infoA, lane, dA);
+        else DecodeRaw(infoA, make_uint4(rawA.x, rawA.y, 0u, 0u), dA);
+        const uint32_t lastA = __shfl_sync(kFull, dA[3], (int)nlA - 1);
+        if ((uint32_t)lane >= nlA) dA[0] = dA[1] = dA[2] = dA[3] = lastA;   // keeps the ring sorted
+        uint32_t tfp;   // the record's four tfs, one byte each, 255 = look the exact value up
+        if (tcA == 0u) tfp = (tfwA & 0xfu) | ((tfwA & 0xf0u) << 4) | ((tfwA & 0xf00u) << 8) | ((tfwA & 0xf000u) << 12);
+        else if (tcA == 1u) tfp = tfwA;
+        else tfp = 0xffffffffu;
+        WSR_STAT(st.decoded += nA; st.bytes += AlgBytes(infoA.z, true););
+        const uint32_t slot = (ja & (uint32_t)(kRingBlocks - 1)) << 5;
+        reinterpret_cast<uint4 *>(ms->rdoc)[slot + lane] = make_uint4(dA[0], dA[1], dA[2], dA[3]);
+        reinterpret_cast<uint32_t *>(ms->rtf)[slot + lane] = tfp;
+#pragma unroll
+        for (int i = 0; i < 4; i++) ms->map[dA[i] & kMapMask] = 1;
+        ja++;
+        infoA = infoA_nxt;
+        if (ja < b1) {
+          rawA = LoadRec2(ix, infoA, lane);
+          tfwA = LoadTfWord(ix, infoA, lane);
+          if (ja + 1u < b1) infoA_nxt = __ldg(&ix.blk_info[first_a + ja + 1u]);
+        }
+      }
+      __syncwarp();
+      // ---- the partner block's postings against the map
+      bool sv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) sv[i] = 4u * lane + i < nB && ms->map[dB[i] & kMapMask] != 0;
+      if (__any_sync(kFull, sv[0] || sv[1] || sv[2] || sv[3])) {
+        const uint32_t tcB = ShTcode(infoB.z);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const unsigned bm = __ballot_sync(kFull, sv[i]);
+          if (bm) {
+            if (nq == 0) q_lo = jr;
+            if (sv[i]) {
+              const uint32_t tf = tcB == 0u ? (tfwB >> (4 * i)) & 15u
+                                  : tcB == 1u ? (tfwB >> (8 * i)) & 255u
+                                              : TfAt(ix, ((first_b + jb) << 7) | (4u * lane + i));
+              ms->surv[nq + __popc(bm & lt)] = make_uint2(dB[i], tf);
+            }
+            nq += __popc(bm);
+            if (nq >= 32) {
+              MergeFlush(ix, bv, q, qi, sh, ms, nq, ja, b0, first_a, drv, idf0, idf1, top, published, multi, lane, st);
+              nq = 0;
+            }
+          }
+        }
+      }
+      // a full ring with more driver blocks reaching into this partner block: everything in the
+      // set lies below the next driver block, retire it all and go round again
+      const bool again = ja < b1 && infoA.x < lastB;
+      // ---- driver blocks that end at or before this partner block's last doc leave the set
+      uint32_t nr = jr;
+      while (nr < ja && ms->rdoc[((nr & (uint32_t)(kRingBlocks - 1)) << 7) + 127u] <= lastB) nr++;
+      if (nr != jr) {
+        // bytes may be shared with postings that stay (hash aliases): clear the leavers', then set
+        // the stayers' again
+        for (uint32_t t = jr; t < nr; t++) {
+          const uint4 d4 = reinterpret_cast<const uint4 *>(ms->rdoc)[((t & (uint32_t)(kRingBlocks - 1)) << 5) + lane];
+          ms->map[d4.x & kMapMask] = 0; ms->map[d4.y & kMapMask] = 0;
+          ms->map[d4.z & kMapMask] = 0; ms->map[d4.w & kMapMask] = 0;
+        }
+        __syncwarp();
+        for (uint32_t t = nr; t < ja; t++) {
+          const uint4 d4 = reinterpret_cast<const uint4 *>(ms->rdoc)[((t & (uint32_t)(kRingBlocks - 1)) << 5) + lane];
+          ms->map[d4.x & kMapMask] = 1; ms->map[d4.y & kMapMask] = 1;
+          ms->map[d4.z & kMapMask] = 1; ms->map[d4.w & kMapMask] = 1;
+        }
+        jr = nr;
+        __syncwarp();
+      }
+      if (!again) break;
+    }
+    if (ja == b1 && jr == ja) break;   // the unit's driver blocks are done
+    infoB = infoB_nxt;
+    infoB_nxt = infoB_nxt2;
+    rawB = rawB_nxt;
+    tfwB = tfwB_nxt;
+  }
+  if (nq) MergeFlush(ix, bv, q, qi, sh, ms, nq, ja, b0, first_a, drv, idf0, idf1, top, published, multi, lane, st);
+  EmitTopK(bv, q, local, top, lane);
+}
+
 // ---- 3..8-term units: QueryProcessor::ProcessMultipleTerms, query_processing.h:710-728 -------
 // The shortest list drives. A driver posting survives when it passes the Bloom filters of ALL
 // other lists; survivors are compacted in doc order and, 32 at a time (one per lane), probed
@@ -928,7 +1182,7 @@ __device__ bool MultiBatch(const DevIndexView &ix, const BatchView &bv, const De
   const unsigned hm = __ballot_sync(kFull, has);
   if (hm) {
     WSR_STAT(st.matches += __popc(hm););
-    WSR_STAT(st.bytes += (8ull * m + 1ull) * __popc(hm););
+    WSR_STAT(st.bytes += __popc(hm););   // one norm byte per hit
     if (COLLECT) CollectAppend(bv, q, qi, has, (int)c.doc, s, lane);
     else OfferToTopK(bv, qi, multi, (int)q.k, has, s, (int)c.doc, top, published, lane);
   }
@@ -1046,14 +1300,19 @@ __device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const 
 
 template <int CLASS> struct ScratchOf { typedef MultiScratch type; };
 template <> struct ScratchOf<kClassOne> { typedef NoScratch type; };
-template <> struct ScratchOf<kClassTwo> { typedef ProbeScratch type; };
+template <> struct ScratchOf<kClassTwo> { typedef TwoScratch type; };
 
 // Persistent search kernel of one query class: warps drain the class's unit queue.
+// The per-warp scratch is dynamic shared memory (the two-term class needs more than the 48 KB a
+// kernel may declare statically).
+extern __shared__ __align__(16) unsigned char g_dyn_smem[];
+
 template <int CLASS, bool STATS>
-__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? 4 : CLASS == kClassMany ? 3 : CLASS == kClassOne ? 8 : 1)
+__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? 3 : CLASS == kClassMany ? 3 : CLASS == kClassOne ? 8 : 1)
 SearchKernel(const DevIndexView ix, const BatchView bv) {
   __shared__ CtaShared sh;
-  __shared__ typename ScratchOf<CLASS>::type scratch[kWarpsPerCta];
+  typedef typename ScratchOf<CLASS>::type Scratch;
+  Scratch *scratch = reinterpret_cast<Scratch *>(g_dyn_smem);
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     const double c = ix.cache[i];
     sh.cache[i] = c;
@@ -1064,7 +1323,7 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
   auto *ws = &scratch[threadIdx.x >> 5];
   (void)ws;
   const uint32_t n_units = bv.class_units[CLASS];
-  UnitStatsT<STATS> st = {0ull, 0ull, 0ull};
+  UnitStatsT<STATS> st = {0ull, 0ull, 0ull, 0ull, kNoDoc};
   unsigned long long units = 0;
   for (;;) {
     uint32_t u = 0;
@@ -1073,6 +1332,7 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
     if (u >= n_units) break;
     const uint32_t qi = __ldg(&bv.unit_query[bv.class_unit_base[CLASS] + u]);
     const DevQuery q = bv.queries[qi];
+    st.last_probe = kNoDoc;
     const uint32_t local = u - q.unit_begin;
     // driver list block range of this unit
     const uint4 li = __ldg(&ix.lists[q.term[q.driver]]);
@@ -1082,7 +1342,8 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
     if constexpr (CLASS == kClassOne) {
       ProcessOneTerm<false>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
     } else if constexpr (CLASS == kClassTwo) {
-      ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
+      if (q.flags & kQueryMerge) ProcessTwoMerge(ix, bv, q, qi, local, b0, b1, &sh, &ws->m, lane, st);
+      else ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, &ws->p, lane, st);
     } else if constexpr (CLASS == kClassMany) {
       ProcessMulti<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     } else {
@@ -1097,6 +1358,7 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
       atomicAdd(&bv.counters->decoded_postings, st.decoded);
       atomicAdd(&bv.counters->touched_bytes, st.bytes);
       atomicAdd(&bv.counters->matches, st.matches);
+      atomicAdd(&bv.counters->probe_blocks, st.probe_blocks);
     }
     atomicAdd(&bv.counters->units, units);
   }
@@ -1332,15 +1594,17 @@ void LaunchClass(const DevIndexView &ix, const BatchView &b, int sm_count, cudaS
   const uint32_t nu = b.class_units[CLASS];
   if (!nu) return;
   // persistent grid = resident CTAs per SM (occupancy query, cached) x SM count
+  constexpr size_t kDyn = sizeof(typename ScratchOf<CLASS>::type) * kWarpsPerCta;
   static int occ = 0;
   if (!occ) {
     int o = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, SearchKernel<CLASS, STATS>, kThreadsPerCta, 0);
+    cudaFuncSetAttribute(SearchKernel<CLASS, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, SearchKernel<CLASS, STATS>, kThreadsPerCta, kDyn);
     occ = o > 0 ? o : 1;
   }
   const uint32_t want = (nu + kWarpsPerCta - 1) / kWarpsPerCta;
   const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sm_count * occ));
-  SearchKernel<CLASS, STATS><<<grid, kThreadsPerCta, 0, s>>>(ix, b);
+  SearchKernel<CLASS, STATS><<<grid, kThreadsPerCta, kDyn, s>>>(ix, b);
 }
 
 }  // namespace

@@ -39,13 +39,14 @@ struct DevIndexView {
   uint32_t n_docs;
   uint32_t doc_lo;            // first doc id held by this shard (filter origin)
   uint32_t n_filter_words;    // length of filters[] (bound for look-ahead prefetches)
+  uint32_t merge_ratio_x4;    // planner rule for the two-term merge path (UseMergePath)
 };
 
 // One planned query. unit_begin = index of its first work unit in its class queue.
 struct DevQuery {
   uint32_t term[WSR_MAX_TERMS];  // query order
   uint8_t n_terms;
-  uint8_t flags;                 // bit 0: phrase query (terms must occur at consecutive positions)
+  uint8_t flags;                 // kQueryPhrase | kQueryMerge
   uint16_t unit_blocks;          // driver-list blocks per work unit of this query
   uint32_t k;
   uint32_t unit_begin;
@@ -56,12 +57,22 @@ struct DevQuery {
   uint32_t cand_begin;           // multi-unit queries: first candidate slot (in units)
 };
 static_assert(sizeof(DevQuery) == 64, "DevQuery is 64 bytes");
+constexpr uint8_t kQueryPhrase = 1;   // terms must occur at consecutive positions, in query order
+constexpr uint8_t kQueryMerge = 2;    // two-term query whose lists are of similar length: merge path
+// Merge path when partner blocks <= kMergeRatioX4/4 x driver blocks (DevIndexView::merge_ratio_x4;
+// WSR_MERGE_RATIO_X4 overrides at wsr_index_open, 0 switches the path off).
+constexpr uint32_t kMergeRatioX4 = 16;
+__host__ __device__ inline bool UseMergePath(uint32_t n_terms, bool phrase, unsigned long long drv_blocks,
+                                             unsigned long long probe_blocks, uint32_t ratio_x4) {
+  return n_terms == 2 && !phrase && ratio_x4 != 0 && probe_blocks * 4ull <= drv_blocks * (unsigned long long)ratio_x4;
+}
 
 struct DevCounters {
   unsigned long long decoded_postings;
   unsigned long long touched_bytes;
   unsigned long long matches;
   unsigned long long units;
+  unsigned long long probe_blocks;
   unsigned int next_unit[4];      // one dynamic queue per query class
 };
 

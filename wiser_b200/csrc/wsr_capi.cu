@@ -329,6 +329,9 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
       dq.n_units = (drv.n_blocks + ub - 1) / ub;
       const int c = q.k > (uint32_t)kMaxFastK ? kClassCollect
                     : q.n_terms == 1 ? kClassOne : q.n_terms == 2 ? kClassTwo : kClassMany;
+      if (c == kClassTwo && UseMergePath(q.n_terms, dq.flags & kQueryPhrase, drv.n_blocks, probe_blocks,
+                                         ix->view.merge_ratio_x4))
+        dq.flags |= kQueryMerge;
       if (c == kClassOne) dq.n_units = 1;   // block-max prepass + selective decode, one warp
       b->tmp[i] = dq;
       b->tmp_cls[i] = (uint8_t)c;
@@ -658,6 +661,8 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
   v.n_docs = (uint32_t)h.n_docs;
   v.doc_lo = (uint32_t)h.doc_lo;
   v.n_filter_words = (uint32_t)h.filters.size();
+  v.merge_ratio_x4 = kMergeRatioX4;
+  if (const char *mr = getenv("WSR_MERGE_RATIO_X4")) v.merge_ratio_x4 = (uint32_t)std::max(0, atoi(mr));
   v.positions = nullptr;
   v.blk_pos = nullptr;
   v.rec_pos = nullptr;
@@ -1095,6 +1100,8 @@ int wsr_batch_get_stats(wsr_batch *b, wsr_batch_stats *s) {
   s->matches = c.matches;
   s->work_units = c.units;
   s->kernel_launches = b->launches;
+  s->reserved = 0;
+  s->probe_blocks = c.probe_blocks;
   return WSR_OK;
 }
 
