@@ -65,6 +65,10 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-sample", type=int, default=200)
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads of the N=1 line")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): --docs documents per GPU; strong: a fixed corpus of --total-parts "
+                         "partitions of --docs documents (config 5: 8 x 5M = 40M docs) regrouped over the N GPUs")
+    ap.add_argument("--total-parts", type=int, default=8)
     ap.add_argument("--dir", default=os.environ.get("WSR_BENCH_DIR", "/tmp/wsr_bench"))
     ap.add_argument("--query-filter", default="", choices=["", "dense_partner", "no_dense_partner"],
                     help="analysis only: keep the queries whose longest list has df >= docs/16, or the others")
@@ -277,7 +281,8 @@ def reference_arm(a, rank, world):
     summed time, exactly what our arm lists."""
     if rank != 0:
         return
-    parts = [ensure_corpus(a, p, world) for p in range(world)]
+    n_parts = a.total_parts if a.scaling == "strong" else world
+    parts = [ensure_corpus(a, p, n_parts) for p in range(n_parts)]
     qlog = ensure_query_log(a, parts[0][0])
     reps = a.warmup + a.steps
     # keep the whole run within a few minutes: bound the sample by a quick probe
@@ -286,7 +291,7 @@ def reference_arm(a, rank, world):
                                         parts[0][0], qlog, 1)
     per_query = probe["seconds"] / max(1, probe["queries"])
     budget_s = 150.0
-    sample = int(max(500, min(sample, budget_s / max(per_query, 1e-9) / reps / world)))
+    sample = int(max(500, min(sample, budget_s / max(per_query, 1e-9) / reps / n_parts)))
     a2 = argparse.Namespace(**{**vars(a), "cpu_sample": sample})
     per_step = [0.0] * reps
     listed = queries = 0
@@ -302,12 +307,12 @@ def reference_arm(a, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64 scores / u32 doc ids", "data": "synthetic",
+        "scaling": a.scaling, "vs_baseline": None, "dtype": "f64 scores / u32 doc ids", "data": "synthetic",
         "config": workload_config(a, parts[0][1], sample_queries=sample, n_gpus=world),
         "queries_per_s": queries / (ms / 1000.0),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": f"first {queries} queries of the {a.workload} log per step against each of the "
-                                   f"{world} partition(s) in turn, {threads} threads on one shared engine, "
+                                   f"{n_parts} partition(s) in turn, {threads} threads on one shared engine, "
                                    f"index page-cache resident"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -316,6 +321,20 @@ def reference_arm(a, rank, world):
 
 
 def workload_config(a, cinfo, sample_queries=None, n_gpus=1):
+    if a.scaling == "strong":
+        return {
+            "workload": (f"C5 document-partitioned synthetic Zipf corpus: {a.total_parts} partitions x {a.docs} docs "
+                         f"= {a.total_parts * a.docs} docs over {n_gpus} GPU(s), {cinfo['postings']} postings/partition, "
+                         f"vocab {a.vocab}; {a.workload} query log ({sample_queries or a.queries} queries/step, "
+                         f"gen_synthetic_log.py-style, high df >= {a.high_df}); BM25 AND top-{a.k}"),
+            "docs_total": a.total_parts * a.docs, "partitions": a.total_parts,
+            "partitions_per_gpu": a.total_parts // max(1, n_gpus), "postings_per_partition": cinfo["postings"],
+            "queries_per_step": sample_queries or a.queries, "k": a.k,
+            "partitioning": (f"{a.total_parts} document partitions, {a.total_parts // max(1, n_gpus)} per GPU: on-device "
+                             f"merge of a GPU's partitions, then all-to-all of query slices + slice merge + all-gather "
+                             f"across GPUs (NCCL called from the C library)"),
+            "l2": "inputs larger than L2: one step streams GBs of distinct posting blocks (126 MB L2)",
+        }
     return {
         "workload": (f"C2 Wikipedia-scale synthetic Zipf corpus: {a.docs} docs x {n_gpus} GPU(s), "
                      f"{cinfo['postings']} postings/partition, vocab {a.vocab}; "
@@ -463,6 +482,209 @@ def partition_oracles(a, world, sample_terms):
         for t, d in gdf.items():
             o.set_global_df(t, d)
     return oras, bases
+
+
+# ---------------------------------------------------------------------------------------------
+def ours_group(a, rank, world, local_rank):
+    """N > 1 (one process per GPU) and the strong-scaling configuration: every rank drives its
+    partitions through the C-ABI group (wsr_group_*): search kernels of each local partition,
+    on-device merge of the local partitions, NCCL exchange called from the library."""
+    import numpy as np
+    import torch
+    from wiser_b200 import Batch
+    from wiser_b200.capi import HIT_DTYPE, WSR_MAX_TERMS, PinnedArray
+    from wiser_b200.dist import ShardGroup
+
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_parts = a.total_parts if a.scaling == "strong" else world
+    if n_parts % world:
+        raise SystemExit(f"--total-parts {n_parts} is not a multiple of {world} GPUs")
+    per_rank = n_parts // world
+    mine = list(range(rank * per_rank, (rank + 1) * per_rank))
+    corp = [ensure_corpus(a, p, n_parts) for p in mine]
+    cinfo = corp[0][1]
+    if world > 1:
+        objs = [None]
+        if rank == 0:
+            objs = [open(ensure_query_log(a, corp[0][0]), "rb").read()]
+        dist.broadcast_object_list(objs, src=0)
+        text = objs[0]
+    else:
+        text = open(ensure_query_log(a, corp[0][0]), "rb").read()
+
+    t0 = time.time()
+    group = ShardGroup([c[0] for c in corp], [local_rank], rank if world > 1 else None, world if world > 1 else None,
+                       positions=a.workload.startswith("phrase"))
+    load_s = time.time() - t0
+    gstats = group.stats()
+    n = group.load_log(text, a.k)
+    log(f"rank {rank}: {per_rank} partition(s) loaded in {load_s:.1f}s, {gstats['n_postings']} postings, "
+        f"{gstats['hbm_bytes'] / 1e9:.2f} GB HBM, {n} queries")
+
+    def sync_all():
+        group.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(a.warmup):
+        group.run()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stream = torch.cuda.ExternalStream(group.stream())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    t_wall = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(a.steps):
+        group.run()
+    ev1.record(stream)
+    sync_all()
+    wall_ms = (time.perf_counter() - t_wall) * 1000.0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    ms_per_step = dev_ms / a.steps
+    merged_hits, merged_n = group.fetch()
+    merged_hits, merged_n = merged_hits.copy(), merged_n.copy()
+
+    # listed postings of this rank's partitions, roofline of its first partition (a Batch on the
+    # group's own index, outside every timed region)
+    peak, peak_src = measured_peak_gbs()
+    listed = 0
+    roofline = None
+    for i in range(per_rank):
+        e = group.part(i)
+        b = Batch(e, e.parse_query_log(text, a.k), a.k)
+        if i == 0:
+            for _ in range(2):
+                b.run()
+            b.sync()
+            prof, st = profile_batch(b)
+            dom, roofline = roofline_of(prof, st, peak, peak_src)
+            roofline["traffic"], roofline["traffic_source"] = None, "not captured at N > 1 (ncu profiles one GPU)"
+            roofline["note"] = "rank 0, its first partition"
+            launches = int(st.kernel_launches)
+            listed += int(st.listed_postings)
+        else:
+            listed += int(b.stats().listed_postings)
+        b.close()
+    if world > 1:
+        t = torch.tensor([listed], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        listed_all = int(t.item())
+    else:
+        listed_all = listed
+    value = listed_all / (ms_per_step / 1000.0)
+
+    # ---- e2e through the host-buffer C ABI: wsr_group_search_log on the pinned log text, every
+    # step; the client-facing rank reads top-k and doc_freqs back into pinned host buffers
+    e2e_steps = max(1, min(a.steps, 20))
+    text_p = PinnedArray((len(text),), np.uint8)
+    text_p.array[:] = np.frombuffer(text, np.uint8)
+    if rank == 0:
+        hits_p = PinnedArray((n + 2, a.k), HIT_DTYPE)
+        nh_p = PinnedArray((n + 2,), np.int32)
+        df_p = PinnedArray((n + 2, WSR_MAX_TERMS), np.uint32)
+        ndf_p = PinnedArray((n + 2,), np.int32)
+
+    def e2e_step():
+        if rank == 0:
+            assert group.search_log(text_p.array, a.k, hits_p.array, nh_p.array, df_p.array, ndf_p.array) == n
+        else:
+            assert group.search_log(text_p.array, a.k, fetch=False) == n
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    # cross-checks outside the timed regions: the all-gather exchange and the e2e path must give
+    # exactly what the scatter exchange of the timed steps gave
+    group.load_log(text, a.k)
+    group.run("allgather")
+    h_ag, n_ag = group.fetch()
+    assert np.array_equal(merged_n, n_ag), "scatter and all-gather exchanges disagree on hit counts"
+    m = np.arange(a.k)[None, :] < n_ag[:, None]
+    assert np.array_equal(merged_hits["doc_id"][m], h_ag["doc_id"][m])
+    assert np.array_equal(merged_hits["score"][m].view(np.uint64), h_ag["score"][m].view(np.uint64))
+    if rank == 0:
+        assert np.array_equal(nh_p.array[:n], n_ag)
+        assert np.array_equal(hits_p.array[:n]["doc_id"][m], h_ag["doc_id"][m])
+        assert np.array_equal(hits_p.array[:n]["score"][m].view(np.uint64), h_ag["score"][m].view(np.uint64))
+    e2e = {"value": listed_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(len(text)),
+           "d2h_bytes_per_step": int(n * a.k * 16 + n * 4 + n * WSR_MAX_TERMS * 4 + n * 4),
+           "ms_per_step": e2e_s * 1000.0, "steps": e2e_steps, "queries_per_s": n / e2e_s,
+           "path": ("wsr_group_search_log on every rank: pinned query-log text -> H2D -> parse + term lookup + "
+                    "planning kernels per partition -> search kernels -> on-device merge of the rank's partitions "
+                    "-> NCCL send/recv of query slices + slice merge + all-gather (called from the library) -> D2H "
+                    "of the merged top-k and doc_freqs into pinned host buffers on rank 0")}
+
+    # ---- parity: rank 0 checks the MERGED result against one CPU oracle per partition directory
+    # in partition mode (collection statistics), merged on the host
+    parity = None
+    if a.parity_sample > 0 and rank == 0:
+        from oracle_py import parse_query_line, partitioned_search
+        from parity import check_topk
+        lines = text.decode().split("\n")
+        idxs = list(range(0, n, max(1, n // a.parity_sample)))[:a.parity_sample]
+        sample_terms = sorted({t for i in idxs for t in parse_query_line(lines[i])[0]})
+        oras, bases = partition_oracles(a, n_parts, sample_terms)
+        for i in idxs:
+            terms, is_phrase = parse_query_line(lines[i])
+            fd, fs, dfs = partitioned_search(oras, bases, terms, 1 << 30, is_phrase)
+            check_topk(fd[:a.k], fs[:a.k], merged_hits["doc_id"][i, :merged_n[i]],
+                       merged_hits["score"][i, :merged_n[i]], fd, fs, what=lines[i])
+            if dfs:
+                assert list(df_p.array[i, :ndf_p.array[i]]) == dfs, f"doc_freqs of {lines[i]!r}"
+        parity = {"queries_checked": len(idxs),
+                  "against": f"{n_parts} CPU oracles, one per partition directory, in partition mode (collection "
+                             f"N / average length / df), merged on the host; bit-exact scores, tie-aware docs, doc_freqs"}
+        for o in oras:
+            o.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": a.scaling,
+            "vs_baseline": None, "dtype": "f64 scores / u32 doc ids", "data": "synthetic",
+            "config": workload_config(a, cinfo, n_gpus=world),
+            "queries_per_s": n / (ms_per_step / 1000.0),
+            "wall_ms_per_step": wall_ms / a.steps,
+            "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "clocks": clocks,
+            # per step and rank: the search kernels of every local partition, the local merge
+            # (more than one partition), 2 NCCL launches + the slice merge (more than one rank)
+            "gpu_launches": a.steps * (launches * per_rank + (1 if per_rank > 1 else 0) + (3 if world > 1 else 0)),
+            "parity": parity, "workloads": None,
+            "index": {"load_s": load_s, "hbm_bytes": int(gstats["hbm_bytes"]), "partitions_on_this_gpu": per_rank,
+                      "corpus_build_s": cinfo.get("wall_s")},
+        }
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    group.close()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
+    sys.stdout.flush()
+    sys.stderr.flush()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -766,7 +988,10 @@ def main():
         return
     if world == 1 and a.gpus > 1:
         log("--gpus > 1 expects a torchrun launch; running the single-GPU configuration")
-    ours(a, rank, world, local_rank)
+    if world > 1 or a.scaling == "strong":
+        ours_group(a, rank, world, local_rank)
+    else:
+        ours(a, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -168,6 +168,13 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
  * hits[] by host threads. A line with more than WSR_MAX_TERMS terms fails the call. */
 int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
                    int32_t *n_hits, int cap_q, int *n_queries);
+/* Same with SearchResult::doc_freqs (vacuum_engine.h:217-219): doc_freqs[i*WSR_MAX_TERMS + t] =
+ * collection-wide df of term t of line i, n_doc_freqs[i] = its number of terms, 0 where the
+ * reference returns early (n_results == 0, no terms, a term missing from the dictionary). Both
+ * arrays hold cap_q rows; pass NULL for both to skip them. */
+int wsr_search_log_ex(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
+                      int32_t *n_hits, uint32_t *doc_freqs, int32_t *n_doc_freqs, int cap_q,
+                      int *n_queries);
 
 /* ---- device-resident batches (replay driver, multi-GPU merge, benchmarking) --------------
  * wsr_batch_create uploads and plans a batch once; wsr_batch_run launches the kernels on the
@@ -226,6 +233,65 @@ int wsr_batch_get_stats(wsr_batch *b, wsr_batch_stats *s);
 int wsr_merge_topk_device(const void *d_gathered_hits, const void *d_gathered_n_hits,
                           int n_shards, int n_queries, int k_stride, void *d_out_hits,
                           void *d_out_n_hits, void *stream);
+
+/* ---- multi-GPU: the shard exchange and document-partitioned groups ----------
+ * The reference has one engine per process (SearchEngineServiceNew, engine_services.h:14-27); a
+ * document-partitioned deployment of it would run one engine per partition and merge their top-k.
+ * Here that lives behind the C ABI: NCCL is called directly from the library (loaded with dlopen
+ * on first use: libnccl.so.2, or the path in WSR_NCCL_LIB), on the batch's own stream. */
+typedef struct wsr_comm wsr_comm;   /* one rank of the exchange: an NCCL communicator + buffers */
+#define WSR_COMM_ID_BYTES 128
+/* ncclGetUniqueId: rank 0 creates the id, the host program hands it to the other ranks. */
+int wsr_comm_unique_id(char id[WSR_COMM_ID_BYTES]);
+wsr_comm *wsr_comm_init_rank(const char id[WSR_COMM_ID_BYTES], int rank, int world, int device);
+void wsr_comm_destroy(wsr_comm *c);
+/* Enqueued on the batch's stream right behind its search kernels; every rank ends with the merged
+ * top-k of all shards (score desc, doc id asc; every query of the batch must use k == k_stride).
+ * mode 0, scatter: a grouped send/recv gives rank r every shard's lists of ITS slice of the
+ * queries (hits and counts in one NCCL launch), rank r merges that slice, a grouped all-gather
+ * distributes the merged slices — (2 - 2/N) n k 16 B per rank and 1/N of the merge work.
+ * mode 1, all-gather: every rank receives every shard's lists and merges all queries. */
+int wsr_batch_exchange(wsr_batch *b, wsr_comm *c, int mode);
+int wsr_batch_exchanged_results(wsr_batch *b, wsr_comm *c, void **d_hits, void **d_n_hits);
+int wsr_batch_fetch_exchanged(wsr_batch *b, wsr_comm *c, wsr_hit *hits, int32_t *n_hits); /* D2H + sync */
+
+/* A group = a document-partitioned collection: n_dirs partition directories (standalone vacuum
+ * indexes with local doc ids, partition i holding global docs [base_i, base_i + n_i)), spread
+ * evenly over n_dev devices of this process (partition i on devices[i / (n_dirs / n_dev)]).
+ * Single process (dist == NULL): the library exchanges the collection statistics between the
+ * partitions itself (N, average length, per-term df; wsr_index_set_global_stats) and creates one
+ * exchange rank per device. Multi-process (one device per process): dist names this process's
+ * rank, the world size and the communicator id; the caller then sets the collection statistics on
+ * each wsr_group_part() with wsr_index_set_global_stats, because only it can reach the other ranks. */
+typedef struct wsr_group wsr_group;
+typedef struct {
+  int rank, world;
+  char comm_id[WSR_COMM_ID_BYTES];
+} wsr_group_dist;
+wsr_group *wsr_group_open(const char *const *dirs, int n_dirs, const int *devices, int n_dev,
+                          int loader_threads, unsigned flags, const wsr_group_dist *dist, char *err,
+                          size_t errlen);
+void wsr_group_close(wsr_group *g);
+int wsr_group_n_parts(const wsr_group *g);
+wsr_index *wsr_group_part(wsr_group *g, int i);   /* borrowed; partition i of this process */
+/* The replay driver's inner loop over a group (wsr_search_log_ex for one index): every partition
+ * parses, looks up and plans the log text on its GPU, searches, and the per-partition top-k are
+ * merged (on the device for partitions sharing one, through the exchange across devices). hits,
+ * n_hits, doc_freqs, n_doc_freqs as wsr_search_log_ex. In a multi-process job every rank makes
+ * the call; ranks that do not face the client pass hits = n_hits = NULL and only search + exchange. */
+int wsr_group_search_log(wsr_group *g, const char *text, size_t len, int k, wsr_hit *hits,
+                         int32_t *n_hits, uint32_t *doc_freqs, int32_t *n_doc_freqs, int cap_q,
+                         int *n_queries);
+/* Device-resident form (benchmarks): plan once, run many times. wsr_group_run enqueues search
+ * kernels + merges + exchange on every device (asynchronous); wsr_group_stream is the first
+ * device's leading stream (cudaStream_t) for CUDA-event timing. */
+int wsr_group_load_log(wsr_group *g, const char *text, size_t len, int k, int *n_queries);
+int wsr_group_run(wsr_group *g, int mode);
+int wsr_group_sync(wsr_group *g);
+int wsr_group_stream(wsr_group *g, void **stream);
+int wsr_group_fetch(wsr_group *g, wsr_hit *hits, int32_t *n_hits);
+int wsr_group_stats(wsr_group *g, uint64_t *listed_postings, uint64_t *n_postings, uint64_t *hbm_bytes,
+                    int64_t *n_docs);
 
 #ifdef __cplusplus
 }

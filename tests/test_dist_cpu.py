@@ -168,3 +168,15 @@ def test_slice_bounds_cover_every_query_once():
             assert all(0 <= x <= s for x in sizes) and sum(sizes) == n
             # slice r starts at r*s: the all-gather of s-padded slices is the result in query order
             assert all(lo[r] == min(n, r * s) for r in range(world))
+
+
+def test_sharded_search_refuses_doc_range_shards():
+    """A doc-range shard of ONE directory (wsr_index_open(dir, dev, shard, n_shards)) already scores
+    with the collection's statistics and emits global doc ids: the partition exchange would count N
+    world times and offset ids twice, so ShardedSearch refuses such an engine."""
+    sys.path.insert(0, ROOT)
+    from wiser_b200.dist import ShardedSearch
+    eng = FakeEngine(1000, 80.0, np.array([0], np.uint32), np.array([1], np.uint32))
+    eng.n_shards = 2
+    with pytest.raises(ValueError, match="OWN partition directory"):
+        ShardedSearch(eng, 0, 2, device=torch.device("cpu"))

@@ -207,7 +207,8 @@ def test_partition_directories_with_global_stats(golden_dir):
         assert np.array_equal(got["score"][i, :k].view(np.uint64), ref_hits["score"][i, :k].view(np.uint64))
 
 
-def test_generated_corpus_vs_oracle(tmp_path):
+@pytest.mark.parametrize("merge_ratio_x4", [None, 1 << 30])
+def test_generated_corpus_vs_oracle(tmp_path, monkeypatch, merge_ratio_x4):
     """A 200k-doc corpus from the native generator (multi-thousand-posting lists, skewed AND,
     3-5 term queries, phrases; doc ids beyond 2^16, so sparse lists have blocks spanning more than
     65536 docs: 32-bit record heads, 16-byte records, the probe's wide-block path): GPU top-10 vs
@@ -229,6 +230,8 @@ def test_generated_corpus_vs_oracle(tmp_path):
              gen_query_log.generate("two_term_lh", groups, 200, 9) +
              gen_query_log.generate("phrase2", groups, 200, 6) +
              gen_query_log.generate("phrase3", groups, 80, 7))
+    if merge_ratio_x4 is not None:     # every non-phrase two-term query down the merge path
+        monkeypatch.setenv("WSR_MERGE_RATIO_X4", str(merge_ratio_x4))
     eng = GpuVacuumEngine(d).Load()
     ora = OracleIndex(d)
     qs = [SearchQuery(*parse_query_line(l), n_results=10) for l in lines]
@@ -371,3 +374,100 @@ def test_counting_pass_equals_plain_run(golden_dir):
     mask = np.arange(10)[None, :] < n1[:, None]
     assert np.array_equal(h1["doc_id"][mask], h2["doc_id"][mask])
     assert np.array_equal(h1["score"][mask].view(np.uint64), h2["score"][mask].view(np.uint64))
+
+
+@pytest.mark.parametrize("name", ["wiki4", "zipf2k"])
+@pytest.mark.parametrize("ratio_x4", [0, 4, 1 << 30])
+def test_two_term_merge_and_probe_paths_vs_reference(golden_dir, name, ratio_x4, monkeypatch):
+    """Both two-term paths against the reference files: WSR_MERGE_RATIO_X4 = 0 sends every two-term
+    query down the probe path (filter + galloping), 2^30 sends every one down the merge path (both
+    lists streamed once), 4 only exactly balanced lists. Small units (k = 3 and 10) and the
+    per-unit threshold exchange of multi-unit queries are covered by the long lists of zipf2k."""
+    from wiser_b200 import GpuVacuumEngine, SearchQuery
+    monkeypatch.setenv("WSR_MERGE_RATIO_X4", str(ratio_x4))
+    d = os.path.join(golden_dir, name)
+    eng = GpuVacuumEngine(d).Load()
+    full = read_ref_results(os.path.join(d, "ref_full.txt.gz"))
+    lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
+    for k, fn in [(10, "ref_top10.txt.gz"), (3, "ref_top3.txt.gz")]:
+        ref = read_ref_results(os.path.join(d, fn))
+        qs, keep = [], []
+        for i, l in enumerate(lines):
+            terms, is_phrase = parse_query_line(l)
+            if len(terms) == 2:
+                qs.append(SearchQuery(terms, is_phrase, n_results=k))
+                keep.append(i)
+        assert len(qs) > 50
+        res = eng.SearchBatch(qs)
+        for q, r, i in zip(qs, res, keep):
+            rd, rs, rdf = ref[i]
+            fd, fs, _ = full[i]
+            assert r.doc_freqs == rdf, q.terms
+            check_topk(rd, rs, [e.doc_id for e in r.entries], [e.doc_score for e in r.entries], fd, fs,
+                       what=f"ratio_x4={ratio_x4} k={k} " + " ".join(q.terms))
+    eng.close()
+
+
+def test_group_of_partitions_on_one_device(golden_dir):
+    """wsr_group_* with two partition directories on ONE device (no NCCL involved): the library
+    exchanges the collection statistics between the partitions itself, every partition parses and
+    searches the log on the GPU, the per-partition top-k are merged on the device — and the result,
+    doc_freqs included, equals the whole index's (and through it the reference's)."""
+    from wiser_b200 import GpuVacuumEngine, SearchQuery
+    from wiser_b200.capi import HIT_DTYPE, WSR_MAX_TERMS
+    from wiser_b200.dist import ShardGroup
+    d = os.path.join(golden_dir, "zipf2k")
+    lines = [l for l in open(os.path.join(d, "queries.txt")).read().split("\n")[:-1] if not l.startswith('"')]
+    text = ("\n".join(lines) + "\n").encode()
+    n = len(lines)
+    whole = GpuVacuumEngine(d).Load()
+    ref_hits, ref_n = whole.search_log(text, 10)
+    qs = [SearchQuery(*parse_query_line(l), n_results=10) for l in lines]
+    ref_res = whole.SearchBatch(qs)
+    group = ShardGroup([os.path.join(golden_dir, "zipf2k_p0"), os.path.join(golden_dir, "zipf2k_p1")], [0])
+    hits = np.zeros((n + 1, 10), HIT_DTYPE)
+    nh = np.zeros(n + 1, np.int32)
+    dfs = np.zeros((n + 1, WSR_MAX_TERMS), np.uint32)
+    ndf = np.zeros(n + 1, np.int32)
+    assert group.search_log(text, 10, hits, nh, dfs, ndf) == n
+    assert np.array_equal(nh[:n], ref_n)
+    ora = OracleIndex(d)
+    for i in range(n):
+        k = ref_n[i]
+        # the stored average length of the whole index is a running mean, the group's a weighted
+        # mean of the partitions': scores agree to the last ulps, not bit for bit (DESIGN §6)
+        assert np.array_equal(hits["doc_id"][i, :k], ref_hits["doc_id"][i, :k]), lines[i]
+        assert np.allclose(hits["score"][i, :k], ref_hits["score"][i, :k], rtol=1e-12, atol=0), lines[i]
+        if ref_res[i].doc_freqs:
+            assert list(dfs[i, :ndf[i]]) == ref_res[i].doc_freqs, lines[i]
+    # device-resident form: plan once, run, fetch
+    assert group.load_log(text, 10) == n
+    group.run()
+    h2, n2 = group.fetch()
+    assert np.array_equal(n2, nh[:n])
+    m = np.arange(10)[None, :] < n2[:, None]
+    assert np.array_equal(h2["doc_id"][m], hits[:n]["doc_id"][m])
+    assert np.array_equal(h2["score"][m].view(np.uint64), hits[:n]["score"][m].view(np.uint64))
+    group.close()
+    whole.close()
+
+
+def test_search_log_doc_freqs(engines):
+    """wsr_search_log_ex: the log path returns SearchResult::doc_freqs like Search() does."""
+    from wiser_b200 import SearchQuery
+    from wiser_b200.capi import HIT_DTYPE, WSR_MAX_TERMS
+    eng, _, d = engines["zipf2k"]
+    lines = open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]
+    lines += ["nosuchterm t1", "", "t1 t1"]
+    text = ("\n".join(lines) + "\n").encode()
+    n = len(lines)
+    hits = np.zeros((n + 1, 10), HIT_DTYPE)
+    nh = np.zeros(n + 1, np.int32)
+    dfs = np.zeros((n + 1, WSR_MAX_TERMS), np.uint32)
+    ndf = np.zeros(n + 1, np.int32)
+    h, c = eng.search_log(text, 10, hits, nh, dfs, ndf)
+    assert len(c) == n
+    res = eng.SearchBatch([SearchQuery(*parse_query_line(l), n_results=10) for l in lines])
+    for i, r in enumerate(res):
+        assert list(dfs[i, :ndf[i]]) == r.doc_freqs, lines[i]
+        assert int(nh[i]) == len(r.entries)

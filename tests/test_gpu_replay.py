@@ -46,3 +46,33 @@ def test_replay_batchlog_timing_passes_use_the_device_front_end(golden_dir, tmp_
     assert js["queries"] == 3 * len(got)
     assert js["result_entries"] == 3 * one_pass
     assert js["listed_postings"] == 3 * sum(sum(g[2]) for g in got)
+
+
+def test_replay_driver_over_a_partitioned_group(golden_dir, tmp_path):
+    """wsr_replay -dirs=<p0>,<p1>: the two partition directories of zipf2k served as one group on
+    one GPU (wsr_group_search_log). Doc ids, doc_freqs and result counts equal the reference's on
+    the whole index; scores agree to the last ulps (the group's average document length is the
+    weighted mean of the partitions', the whole index stores a running mean)."""
+    import numpy as np
+    d = os.path.join(golden_dir, "zipf2k")
+    lines = [l for l in open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]]
+    keep = [i for i, l in enumerate(lines) if not l.startswith('"')]   # partitions were written without positions
+    qpath = str(tmp_path / "q.txt")
+    with open(qpath, "w") as f:
+        f.write("\n".join(lines[i] for i in keep) + "\n")
+    out = str(tmp_path / "dump.txt")
+    dirs = ",".join(os.path.join(golden_dir, f"zipf2k_p{s}") for s in range(2))
+    log = subprocess.check_output([REPLAY, f"-dirs={dirs}", "-devices=0", f"-query_path={qpath}", "-n_results=10",
+                                   "-batch_size=900", f"-dump={out}"]).decode()
+    assert "WSR_REPLAY_JSON" in log and '"mode": "group"' in log
+    got = read_ref_results(out)
+    ref = read_ref_results(os.path.join(d, "ref_top10.txt.gz"))
+    assert len(got) == len(keep)
+    for (gd, gs, gdf), i in zip(got, keep):
+        rd, rs, rdf = ref[i]
+        assert len(gd) == len(rd), lines[i]
+        if len(rd):
+            assert gdf == rdf, lines[i]
+        assert np.allclose(gs, rs, rtol=1e-12, atol=0), lines[i]
+        # ties (equal reference scores) may come in either order
+        assert sorted(gd.tolist()) == sorted(rd.tolist()) or len(set(rs.tolist())) < len(rs), lines[i]

@@ -1,0 +1,13 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2b_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/r2b_tests.log
+tail -5 gpurun_out/r2b_tests.log
+for r in 16 0 4 8 32; do
+  WSR_MERGE_RATIO_X4=$r timeout 600 python bench.py --steps 20 --warmup 3 --no-secondary --no-cpu-baseline --parity-sample 50 > gpurun_out/r2b_bench_mr$r.json 2> gpurun_out/r2b_bench_mr$r.err; echo "rc=$?" >> gpurun_out/r2b_bench_mr$r.err
+done
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-secondary --parity-sample 0"
+timeout 600 $CMD > gpurun_out/r2b_plain.log 2>&1 && \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2b_launches.csv $CMD > gpurun_out/r2b_ncu_l.log 2>&1
+timeout 600 $CMD > gpurun_out/r2b_plain2.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:SearchKernel -s 8 -c 2 -o gpurun_out/r2b_two $CMD > gpurun_out/r2b_ncu_f.log 2>&1
+ls -la gpurun_out | tail -12

@@ -43,7 +43,18 @@ EXPORTS = [
     "wsr_batch_run", "wsr_batch_sync", "wsr_batch_fetch", "wsr_batch_device_results",
     "wsr_batch_time", "wsr_batch_get_stats", "wsr_merge_topk_device", "wsr_batch_profile", "wsr_batch_count_work", "wsr_batch_reset_log",
     "wsr_parse_query_log", "wsr_index_set_global_stats", "wsr_index_local_stats", "wsr_batch_reset", "wsr_search_log",
+    "wsr_search_log_ex", "wsr_comm_unique_id", "wsr_comm_init_rank", "wsr_comm_destroy", "wsr_batch_exchange",
+    "wsr_batch_exchanged_results", "wsr_batch_fetch_exchanged", "wsr_group_open", "wsr_group_close",
+    "wsr_group_n_parts", "wsr_group_part", "wsr_group_search_log", "wsr_group_load_log", "wsr_group_run",
+    "wsr_group_sync", "wsr_group_stream", "wsr_group_fetch", "wsr_group_stats",
 ]
+
+WSR_COMM_ID_BYTES = 128
+
+
+class GroupDist(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("comm_id", C.c_char * WSR_COMM_ID_BYTES)]
+
 
 _lib = None
 
@@ -93,6 +104,29 @@ def lib():
     L.wsr_batch_reset.argtypes = [vp, vp, C.c_int, C.c_int]
     L.wsr_search_log.argtypes = [vp, vp, sz, C.c_int, vp, vp, C.c_int, C.POINTER(C.c_int)]
     L.wsr_merge_topk_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.wsr_search_log_ex.argtypes = [vp, vp, sz, C.c_int, vp, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.wsr_comm_unique_id.argtypes = [vp]
+    L.wsr_comm_init_rank.restype = vp
+    L.wsr_comm_init_rank.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.wsr_comm_destroy.argtypes = [vp]
+    L.wsr_batch_exchange.argtypes = [vp, vp, C.c_int]
+    L.wsr_batch_exchanged_results.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.wsr_batch_fetch_exchanged.argtypes = [vp, vp, vp, vp]
+    L.wsr_group_open.restype = vp
+    L.wsr_group_open.argtypes = [C.POINTER(cp), C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_uint,
+                                 C.POINTER(GroupDist), cp, sz]
+    L.wsr_group_close.argtypes = [vp]
+    L.wsr_group_n_parts.argtypes = [vp]
+    L.wsr_group_part.restype = vp
+    L.wsr_group_part.argtypes = [vp, C.c_int]
+    L.wsr_group_search_log.argtypes = [vp, vp, sz, C.c_int, vp, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
+    L.wsr_group_load_log.argtypes = [vp, vp, sz, C.c_int, C.POINTER(C.c_int)]
+    L.wsr_group_run.argtypes = [vp, C.c_int]
+    L.wsr_group_sync.argtypes = [vp]
+    L.wsr_group_stream.argtypes = [vp, C.POINTER(vp)]
+    L.wsr_group_fetch.argtypes = [vp, vp, vp]
+    L.wsr_group_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                  C.POINTER(C.c_int64)]
     _lib = L
     return L
 

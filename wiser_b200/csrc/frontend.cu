@@ -54,7 +54,7 @@ __device__ __forceinline__ void PlanOne(const DevIndexView &ix, DevQuery &q, uin
                                         PlanItem *__restrict__ item, uint32_t *__restrict__ err) {
   PlanItem it;
 #pragma unroll
-  for (int j = 0; j < 8; j++) it.v[j] = 0;
+  for (int j = 0; j < kPlanWords; j++) it.v[j] = 0;
   uint32_t cls = 255;
   bool ok = resolvable && k > 0 && n_terms > 0;             // vacuum_engine.h:206-215
   uint32_t best = 0, best_df = 0xffffffffu;
@@ -88,10 +88,27 @@ __device__ __forceinline__ void PlanOne(const DevIndexView &ix, DevQuery &q, uin
     it.v[cls] = 1;
     it.v[3 + cls] = q.n_units;
     if (q.n_units > 1) { it.v[6] = q.n_units; it.v[7] = 1; }
+    if (q.flags & kQueryMerge) it.v[8] = q.n_units;
   }
   q.cand_begin = cls;
+  // VacuumEngine::Search fills doc_freqs unless it returned early (n_results == 0, no terms, a
+  // term missing from the dictionary: vacuum_engine.h:206-219); kept for DocFreqsKernel
+  q.seg_begin = (resolvable && k > 0 && n_terms > 0) ? n_terms : 0u;
   tmp[i] = q;
   item[i] = it;
+}
+
+// doc_freqs of a planned log (SearchResult::doc_freqs, vacuum_engine.h:217-219): per input query
+// the collection-wide df of its terms in query order, and how many there are (0 on the early-out
+// paths). Reads the unplaced queries the planner left in tmp[].
+__global__ void DocFreqsKernel(const DevQuery *__restrict__ tmp, uint32_t n, const DevIndexView ix,
+                               uint32_t *__restrict__ doc_freqs, int32_t *__restrict__ n_doc_freqs) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = t / WSR_MAX_TERMS, j = t % WSR_MAX_TERMS;
+  if (i >= n) return;
+  const uint32_t m = tmp[i].seg_begin;
+  if (j == 0) n_doc_freqs[i] = (int32_t)m;
+  doc_freqs[t] = j < m ? __ldg(&ix.lists[tmp[i].term[j]]).w : 0u;
 }
 
 // Same planning from term ids the host already resolved (wsr_search_batch): one thread per
@@ -160,7 +177,7 @@ struct PlanAdd {
   __device__ __forceinline__ PlanItem operator()(const PlanItem &x, const PlanItem &y) const {
     PlanItem r;
 #pragma unroll
-    for (int j = 0; j < 8; j++) r.v[j] = x.v[j] + y.v[j];
+    for (int j = 0; j < kPlanWords; j++) r.v[j] = x.v[j] + y.v[j];
     return r;
   }
 };
@@ -230,6 +247,13 @@ void LaunchPlanQueries(const wsr_query *d_in, uint32_t n, uint32_t k_stride, con
   size_t bytes = cub_bytes;
   cub::DeviceScan::ExclusiveScan(d_cub, bytes, d_item, d_excl, PlanAdd(), PlanItem(), (int)n, s);
   PlaceKernel<<<grid, 128, 0, s>>>(d_tmp, d_item, d_excl, n, d_planned, d_multi, d_totals);
+}
+
+void LaunchDocFreqs(const DevQuery *d_tmp, uint32_t n, const DevIndexView &ix, uint32_t *d_doc_freqs,
+                    int32_t *d_n_doc_freqs, cudaStream_t s) {
+  if (!n) return;
+  const unsigned long long threads = (unsigned long long)n * WSR_MAX_TERMS;
+  DocFreqsKernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d_tmp, n, ix, d_doc_freqs, d_n_doc_freqs);
 }
 
 size_t PackTempBytes(uint32_t n) {

@@ -23,6 +23,7 @@
 //                     device order is (score desc, doc id asc) — the reference's order among
 //                     equal scores is implementation-defined (SURVEY §7 "Ties").
 #include "kernels.cuh"
+#include "host_index.h"
 
 #include <algorithm>
 #include <cub/device/device_segmented_sort.cuh>
@@ -205,6 +206,7 @@ struct UnitStatsT {
 struct CtaShared {
   double cache[256];
   float cache32[256];
+  uint32_t fpat[kFilterPatterns];   // host_index.h FilterPattern
 };
 
 struct HitRec {
@@ -233,16 +235,16 @@ struct __align__(16) NoScratch { uint32_t unused; };
 constexpr int kMapBytes = 4096;        // doc & (kMapBytes - 1)
 constexpr int kRingBlocks = 4;         // driver blocks whose docs/tfs stay addressable
 constexpr int kRingMask = kRingBlocks * 128 - 1;
-constexpr int kSurvCap = 64;           // 31 queued + up to 32 of one slot pass
+constexpr int kSurvCap = 160;          // 31 queued + up to 128 of one partner block
+constexpr int kMergeHitCap = 64;       // 31 queued + up to 32 of one verification pass
 struct __align__(16) MergeScratch {
   uint8_t map[kMapBytes];
   uint32_t rdoc[kRingBlocks * 128];    // doc ids of driver blocks ja-4 .. ja-1, slot = posting index & kRingMask
   uint8_t rtf[kRingBlocks * 128];      // min(tf, 255); 255 = read the exact tf from the payload
   uint2 surv[kSurvCap];                // partner postings whose map byte was set: {doc, tf}
-};
-union __align__(16) TwoScratch {
-  ProbeScratch p;
-  MergeScratch m;
+  uint32_t hdoc[kMergeHitCap];         // verified matches awaiting scoring
+  uint32_t htfa[kMergeHitCap];         // tf in the driver list
+  uint32_t htfb[kMergeHitCap];         // tf in the partner list
 };
 
 // Emits one unit's result: straight to the caller's hit array when the query has one unit,
@@ -454,15 +456,14 @@ __device__ __forceinline__ ListFilter FilterOf(const DevIndexView &ix, uint32_t 
   lf.shift = f.y & 31u;
   return lf;
 }
-__device__ __forceinline__ bool FilterTest(uint32_t w, uint32_t doc) {
-  const uint32_t h = doc * 0x9E3779B1u;   // host_index.h FilterBits
-  const uint32_t need = (1u << (h >> 27)) | (1u << ((h >> 22) & 31u)) | (1u << ((h >> 17) & 31u));
+__device__ __forceinline__ bool FilterTest(const CtaShared *sh, uint32_t w, uint32_t doc) {
+  const uint32_t need = sh->fpat[FilterIndex(doc)];   // host_index.h FilterBits
   return (w & need) == need;
 }
-// Filter word of a candidate (all ones = "may be present" when the list has no filter).
-__device__ __forceinline__ uint32_t FilterWord(const DevIndexView &ix, const ListFilter &lf, uint32_t doc,
-                                               bool valid) {
-  if (lf.words == nullptr || !valid) return 0xffffffffu;
+// Filter word of a candidate (all ones = "may be present" when the list has no filter). Slots past
+// a block's postings decode to docs inside the shard's range, so their word may be read as well.
+__device__ __forceinline__ uint32_t FilterWord(const DevIndexView &ix, const ListFilter &lf, uint32_t doc) {
+  if (lf.words == nullptr) return 0xffffffffu;
   return __ldg(lf.words + ((doc - ix.doc_lo) >> lf.shift));
 }
 
@@ -750,7 +751,7 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
     if ((uint32_t)lane < ((ShN(info_cur.z) + 3u) >> 2)) raw = LoadRecord(ix, info_cur, (uint32_t)lane);
     DecodeRaw(info_cur, raw, d);
 #pragma unroll
-    for (int i = 0; i < 4; i++) fw[i] = FilterWord(ix, flt, d[i], 4u * lane + i < ShN(info_cur.z));
+    for (int i = 0; i < 4; i++) fw[i] = FilterWord(ix, flt, d[i]);
   }
   uint4 raw_nxt = make_uint4(0u, 0u, 0u, 0u);
   if (b0 + 1 < b1 && (uint32_t)lane < ((ShN(info_nxt.z) + 3u) >> 2))
@@ -765,7 +766,7 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
     if (ja + 1 < b1) {
       DecodeRaw(info_nxt, raw_nxt, dn);
 #pragma unroll
-      for (int i = 0; i < 4; i++) fwn[i] = FilterWord(ix, flt, dn[i], 4u * lane + i < ShN(info_nxt.z));
+      for (int i = 0; i < 4; i++) fwn[i] = FilterWord(ix, flt, dn[i]);
       if (ja + 2 < b1) {
         info_nxt2 = __ldg(&ix.blk_info[first_a + ja + 2]);
       }
@@ -773,11 +774,11 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
       // The driver walks the doc-id space upwards, so the filter words it will need are the ones
       // just above the words of block ja+1: pull the next two blocks' worth (estimated from this
       // block's span) into L2, one 128-byte line per lane, when that is at most 32 lines.
-      if (flt.words != nullptr && ja + 3 < b1) {
+      if (flt.words != nullptr && ja + 3 < b1 && ((ja - b0) & 1u) == 0u) {   // every other block, twice the reach
         const uint32_t nl1 = (ShN(info_nxt.z) + 3u) >> 2;
         const uint32_t w_lo = (__shfl_sync(kFull, dn[0], 0) - ix.doc_lo) >> flt.shift;
         const uint32_t w_hi = (__shfl_sync(kFull, dn[3], (int)nl1 - 1) - ix.doc_lo) >> flt.shift;
-        const uint32_t span = WSR_PF_MULT * (w_hi - w_lo + 1u);
+        const uint32_t span = 2u * WSR_PF_MULT * (w_hi - w_lo + 1u);
         const uint32_t w = w_hi + 1u + 32u * (uint32_t)lane;
         if (span <= 1024u && 32u * (uint32_t)lane < span &&
             (size_t)(flt.words - ix.filters) + w < ix.n_filter_words)
@@ -789,10 +790,13 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
     bool pass[4];
     unsigned bm[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      pass[i] = 4u * lane + i < na && FilterTest(fw[i], d[i]);   // padded slots repeat the last doc
-      bm[i] = __ballot_sync(kFull, pass[i]);
+    for (int i = 0; i < 4; i++) pass[i] = FilterTest(sh, fw[i], d[i]);
+    if (na != 128u) {   // a list's last block: padded slots repeat the last doc
+#pragma unroll
+      for (int i = 0; i < 4; i++) pass[i] = pass[i] && 4u * lane + i < na;
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++) bm[i] = __ballot_sync(kFull, pass[i]);
     const unsigned lt = (1u << lane) - 1u;
     int at = nc + __popc(bm[0] & lt) + __popc(bm[1] & lt) + __popc(bm[2] & lt) + __popc(bm[3] & lt);
     const uint32_t ga = (first_a + ja) << 7;
@@ -856,6 +860,31 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
 // with their tf and, 32 at a time, located in the ring by binary search (which settles hash
 // aliases and yields the driver posting's tf), scored and offered to the top-k. No filter words,
 // no record search, no tf gathers: the only random access left is the norm byte of a hit.
+// 128-bit records (blocks spanning >= 2^16 docs or with wide deltas) are rare: out of line, so
+// that the merge loop's instruction footprint stays small (the loops of this kernel live or die
+// by the 32 KB instruction cache).
+__device__ __noinline__ void DecodeDocsWide(const DevIndexView &ix, const uint4 info, int lane, uint32_t d[4]) {
+  DecodeDocs(ix, info, lane, d);
+}
+// rcode <= 1 only: [f:w0][d1:b][d2:b][d3:b] in 64 bits
+__device__ __forceinline__ void DecodeRaw64(const uint4 info, const uint2 raw, uint32_t d[4]) {
+  const uint32_t bits = info.z;
+  const uint32_t w0 = ShW0(bits), b = ShB(bits);
+  const uint32_t m0 = w0 >= 32u ? 0xffffffffu : ((1u << w0) - 1u);
+  const uint32_t mb = b >= 32u ? 0xffffffffu : ((1u << b) - 1u);
+  unsigned long long x = ((unsigned long long)raw.y << 32) | raw.x;
+  const uint32_t f = (uint32_t)x & m0;
+  x >>= w0;
+  const uint32_t d1 = (uint32_t)x & mb;
+  x >>= b;
+  const uint32_t d2 = (uint32_t)x & mb;
+  x >>= b;
+  const uint32_t d3 = (uint32_t)x & mb;
+  d[0] = info.x + f;
+  d[1] = d[0] + d1;
+  d[2] = d[1] + d2;
+  d[3] = d[2] + d3;
+}
 __device__ __forceinline__ uint2 LoadRec2(const DevIndexView &ix, const uint4 info, int lane) {
   // the lane's doc record in the 32/64-bit formats; zeros past the block's records and for
   // 128-bit records (those are decoded on demand)
@@ -880,46 +909,6 @@ __device__ __forceinline__ uint32_t LoadTfWord(const DevIndexView &ix, const uin
   return v;
 }
 
-// Settles the queued partner postings against the ring (driver blocks [max(b0, ja-4), ja)), scores
-// the real matches and offers them to the top-k.
-template <class ST>
-__device__ __forceinline__ void MergeFlush(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
-                                           uint32_t qi, const CtaShared *sh, MergeScratch *ms, int nq,
-                                           uint32_t ja, uint32_t b0, uint32_t first_a, int drv, double idf0,
-                                           double idf1, TopK &top, double &published, bool multi, int lane,
-                                           ST &st) {
-  __syncwarp();
-  const uint32_t lo_blk = ja >= b0 + (uint32_t)kRingBlocks ? ja - (uint32_t)kRingBlocks : b0;
-  const uint32_t glo = lo_blk << 7, ghi = ja << 7;   // posting indices of the driver list held by the ring
-  for (int base = 0; base < nq; base += 32) {
-    bool has = base + lane < nq;
-    uint32_t x = 0u, tfb = 0u, g = glo;
-    if (has) {
-      const uint2 sv = ms->surv[base + lane];
-      x = sv.x;
-      tfb = sv.y;
-    }
-#pragma unroll
-    for (uint32_t s = (uint32_t)kRingBlocks * 64u; s; s >>= 1) {   // lower bound of x in the ring
-      const uint32_t t = g + s;
-      if (t <= ghi && ms->rdoc[(t - 1u) & (uint32_t)kRingMask] < x) g = t;
-    }
-    has = has && g < ghi && ms->rdoc[g & (uint32_t)kRingMask] == x;
-    double s = 0.0;
-    if (has) {
-      uint32_t tfa = ms->rtf[g & (uint32_t)kRingMask];
-      if (tfa == 255u) tfa = TfAt(ix, ((first_a + (g >> 7)) << 7) | (g & 127u));
-      const double cn = sh->cache[__ldg(ix.norms + x)];
-      // query order: term 0 first (scoring.h:124-145)
-      s = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? tfa : tfb, cn));
-      s = __dadd_rn(s, TermScore(idf1, drv == 0 ? tfb : tfa, cn));
-    }
-    WSR_STAT(const unsigned hm = __ballot_sync(kFull, has); st.matches += __popc(hm); st.bytes += __popc(hm););
-    OfferToTopK(bv, qi, multi, (int)q.k, has, s, (int)x, top, published, lane);
-  }
-  __syncwarp();
-}
-
 template <class ST>
 __device__ void ProcessTwoMerge(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
                                 uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
@@ -931,14 +920,11 @@ __device__ void ProcessTwoMerge(const DevIndexView &ix, const BatchView &bv, con
   const uint32_t first_a = la.x, first_b = lb.x, nb = lb.y;
   const bool multi = q.n_units > 1;
   constexpr uint32_t kMapMask = (uint32_t)kMapBytes - 1u;
+  constexpr uint32_t kSlotMask = (uint32_t)kRingBlocks - 1u;
   TopK top;
   TopKInit(top);
   double published = 0.0;
-  // the scratch is shared with the probe path: start from a clean map
-  {
-    uint4 *m4 = reinterpret_cast<uint4 *>(ms->map);
-    for (int i = lane; i < kMapBytes / 16; i += 32) m4[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
+  // the map starts clean and every unit leaves it clean (see the end of this function)
   uint4 infoA = __ldg(&ix.blk_info[first_a + b0]);
   // the partner's first block that reaches the unit's doc range (docs of block b0 are >= its base)
   uint32_t jb;
@@ -962,114 +948,181 @@ __device__ void ProcessTwoMerge(const DevIndexView &ix, const BatchView &bv, con
   uint32_t tfwB = LoadTfWord(ix, infoB, lane);
   uint32_t ja = b0, jr = b0;   // driver blocks [jr, ja) are in the map; [max(b0, ja-4), ja) in the ring
   uint32_t q_lo = b0;          // oldest driver block a queued partner posting may match
-  int nq = 0;
+  int nq = 0, nh = 0;          // queued partner postings / verified matches
   const unsigned lt = (1u << lane) - 1u;
   __syncwarp();
-  for (; jb < nb; jb++) {
-    // ---- partner block jb: request block jb+1's records and block jb+2's info, then decode
-    uint2 rawB_nxt = make_uint2(0u, 0u);
-    uint32_t tfwB_nxt = 0u;
-    uint4 infoB_nxt2 = infoB_nxt;
-    if (jb + 1u < nb) {
-      rawB_nxt = LoadRec2(ix, infoB_nxt, lane);
-      tfwB_nxt = LoadTfWord(ix, infoB_nxt, lane);
-      if (jb + 2u < nb) infoB_nxt2 = __ldg(&ix.blk_info[first_b + jb + 2u]);
-    }
-    const uint32_t nB = ShN(infoB.z), nlB = (nB + 3u) >> 2;
+  bool redo = false;           // the partner block in hand reaches past a full ring: go round again
+  uint2 rawB_nxt = make_uint2(0u, 0u);
+  uint32_t tfwB_nxt = 0u;
+  uint4 infoB_nxt2 = infoB_nxt;
+  for (;;) {
     uint32_t dB[4];
-    if (ShRcode(infoB.z) == 2u) DecodeDocs(ix, infoB, lane, dB);
-    else DecodeRaw(infoB, make_uint4(rawB.x, rawB.y, 0u, 0u), dB);
-    const uint32_t lastB = __shfl_sync(kFull, dB[3], (int)nlB - 1);
-    WSR_STAT(st.decoded += nB; st.bytes += AlgBytes(infoB.z, true););
-    for (;;) {
-      // ---- driver blocks that reach into this partner block join the set
-      while (ja < b1 && (infoA.x < lastB || ja == 0u) && ja - jr < (uint32_t)kRingBlocks) {
-        if (nq && q_lo + (uint32_t)kRingBlocks <= ja) {   // the ring slot reused below may hold a queued posting's match
-          MergeFlush(ix, bv, q, qi, sh, ms, nq, ja, b0, first_a, drv, idf0, idf1, top, published, multi, lane, st);
-          nq = 0;
-        }
-        const uint32_t nA = ShN(infoA.z), nlA = (nA + 3u) >> 2, tcA = ShTcode(infoA.z);
-        uint32_t dA[4];
-        if (ShRcode(infoA.z) == 2u) DecodeDocs(ix, infoA, lane, dA);
-        else DecodeRaw(infoA, make_uint4(rawA.x, rawA.y, 0u, 0u), dA);
-        const uint32_t lastA = __shfl_sync(kFull, dA[3], (int)nlA - 1);
-        if ((uint32_t)lane >= nlA) dA[0] = dA[1] = dA[2] = dA[3] = lastA;   // keeps the ring sorted
-        uint32_t tfp;   // the record's four tfs, one byte each, 255 = look the exact value up
-        if (tcA == 0u) tfp = (tfwA & 0xfu) | ((tfwA & 0xf0u) << 4) | ((tfwA & 0xf00u) << 8) | ((tfwA & 0xf000u) << 12);
-        else if (tcA == 1u) tfp = tfwA;
-        else tfp = 0xffffffffu;
-        WSR_STAT(st.decoded += nA; st.bytes += AlgBytes(infoA.z, true););
-        const uint32_t slot = (ja & (uint32_t)(kRingBlocks - 1)) << 5;
-        reinterpret_cast<uint4 *>(ms->rdoc)[slot + lane] = make_uint4(dA[0], dA[1], dA[2], dA[3]);
-        reinterpret_cast<uint32_t *>(ms->rtf)[slot + lane] = tfp;
-#pragma unroll
-        for (int i = 0; i < 4; i++) ms->map[dA[i] & kMapMask] = 1;
-        ja++;
-        infoA = infoA_nxt;
-        if (ja < b1) {
-          rawA = LoadRec2(ix, infoA, lane);
-          tfwA = LoadTfWord(ix, infoA, lane);
-          if (ja + 1u < b1) infoA_nxt = __ldg(&ix.blk_info[first_a + ja + 1u]);
-        }
+    const uint32_t nB = ShN(infoB.z);
+    if (!redo) {
+      // request block jb+1's records and block jb+2's info before working on block jb
+      if (jb + 1u < nb) {
+        rawB_nxt = LoadRec2(ix, infoB_nxt, lane);
+        tfwB_nxt = LoadTfWord(ix, infoB_nxt, lane);
+        if (jb + 2u < nb) infoB_nxt2 = __ldg(&ix.blk_info[first_b + jb + 2u]);
       }
-      __syncwarp();
-      // ---- the partner block's postings against the map
+      WSR_STAT(st.decoded += nB; st.bytes += AlgBytes(infoB.z, true););
+    }
+    if (ShRcode(infoB.z) == 2u) DecodeDocsWide(ix, infoB, lane, dB);
+    else DecodeRaw64(infoB, rawB, dB);
+    const uint32_t lastB = __shfl_sync(kFull, dB[3], (int)((nB + 3u) >> 2) - 1);
+    // ---- driver blocks that reach into this partner block join the set. Ring slots reused here
+    // held blocks below jr - (those were retired) and no queued posting can match them: the
+    // queue is settled at the end of every round in which a block it may match retired.
+#pragma unroll 1
+    while (ja < b1 && (infoA.x < lastB || ja == 0u) && ja - jr < (uint32_t)kRingBlocks) {
+      const uint32_t nA = ShN(infoA.z), nlA = (nA + 3u) >> 2, tcA = ShTcode(infoA.z);
+      uint32_t dA[4];
+      if (ShRcode(infoA.z) == 2u) DecodeDocsWide(ix, infoA, lane, dA);
+      else DecodeRaw64(infoA, rawA, dA);
+      const uint32_t lastA = __shfl_sync(kFull, dA[3], (int)nlA - 1);
+      if ((uint32_t)lane >= nlA) dA[0] = dA[1] = dA[2] = dA[3] = lastA;   // keeps the ring sorted
+      uint32_t tfp;   // the record's four tfs, one byte each, 255 = look the exact value up
+      if (tcA == 0u) tfp = (tfwA & 0xfu) | ((tfwA & 0xf0u) << 4) | ((tfwA & 0xf00u) << 8) | ((tfwA & 0xf000u) << 12);
+      else if (tcA == 1u) tfp = tfwA;
+      else tfp = 0xffffffffu;
+      WSR_STAT(st.decoded += nA; st.bytes += AlgBytes(infoA.z, true););
+      const uint32_t slot = (ja & kSlotMask) << 5;
+      reinterpret_cast<uint4 *>(ms->rdoc)[slot + lane] = make_uint4(dA[0], dA[1], dA[2], dA[3]);
+      reinterpret_cast<uint32_t *>(ms->rtf)[slot + lane] = tfp;
+#pragma unroll
+      for (int i = 0; i < 4; i++) ms->map[dA[i] & kMapMask] = 1;
+      ja++;
+      infoA = infoA_nxt;
+      if (ja < b1) {
+        rawA = LoadRec2(ix, infoA, lane);
+        tfwA = LoadTfWord(ix, infoA, lane);
+        if (ja + 1u < b1) infoA_nxt = __ldg(&ix.blk_info[first_a + ja + 1u]);
+      }
+    }
+    __syncwarp();
+    // ---- the partner block's postings against the map
+    {
       bool sv[4];
 #pragma unroll
       for (int i = 0; i < 4; i++) sv[i] = 4u * lane + i < nB && ms->map[dB[i] & kMapMask] != 0;
       if (__any_sync(kFull, sv[0] || sv[1] || sv[2] || sv[3])) {
+        if (nq == 0) q_lo = jr;
         const uint32_t tcB = ShTcode(infoB.z);
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const unsigned bm = __ballot_sync(kFull, sv[i]);
-          if (bm) {
-            if (nq == 0) q_lo = jr;
-            if (sv[i]) {
-              const uint32_t tf = tcB == 0u ? (tfwB >> (4 * i)) & 15u
-                                  : tcB == 1u ? (tfwB >> (8 * i)) & 255u
-                                              : TfAt(ix, ((first_b + jb) << 7) | (4u * lane + i));
-              ms->surv[nq + __popc(bm & lt)] = make_uint2(dB[i], tf);
-            }
-            nq += __popc(bm);
-            if (nq >= 32) {
-              MergeFlush(ix, bv, q, qi, sh, ms, nq, ja, b0, first_a, drv, idf0, idf1, top, published, multi, lane, st);
-              nq = 0;
-            }
+          if (sv[i]) {
+            const uint32_t tf = tcB == 0u ? (tfwB >> (4 * i)) & 15u
+                                : tcB == 1u ? (tfwB >> (8 * i)) & 255u
+                                            : TfAt(ix, ((first_b + jb) << 7) | (4u * lane + i));
+            ms->surv[nq + __popc(bm & lt)] = make_uint2(dB[i], tf);
           }
+          nq += __popc(bm);
         }
       }
-      // a full ring with more driver blocks reaching into this partner block: everything in the
-      // set lies below the next driver block, retire it all and go round again
-      const bool again = ja < b1 && infoA.x < lastB;
-      // ---- driver blocks that end at or before this partner block's last doc leave the set
-      uint32_t nr = jr;
-      while (nr < ja && ms->rdoc[((nr & (uint32_t)(kRingBlocks - 1)) << 7) + 127u] <= lastB) nr++;
-      if (nr != jr) {
-        // bytes may be shared with postings that stay (hash aliases): clear the leavers', then set
-        // the stayers' again
-        for (uint32_t t = jr; t < nr; t++) {
-          const uint4 d4 = reinterpret_cast<const uint4 *>(ms->rdoc)[((t & (uint32_t)(kRingBlocks - 1)) << 5) + lane];
-          ms->map[d4.x & kMapMask] = 0; ms->map[d4.y & kMapMask] = 0;
-          ms->map[d4.z & kMapMask] = 0; ms->map[d4.w & kMapMask] = 0;
-        }
-        __syncwarp();
-        for (uint32_t t = nr; t < ja; t++) {
-          const uint4 d4 = reinterpret_cast<const uint4 *>(ms->rdoc)[((t & (uint32_t)(kRingBlocks - 1)) << 5) + lane];
-          ms->map[d4.x & kMapMask] = 1; ms->map[d4.y & kMapMask] = 1;
-          ms->map[d4.z & kMapMask] = 1; ms->map[d4.w & kMapMask] = 1;
-        }
-        jr = nr;
-        __syncwarp();
-      }
-      if (!again) break;
     }
-    if (ja == b1 && jr == ja) break;   // the unit's driver blocks are done
+    // a full ring with more driver blocks reaching into this partner block: everything in the
+    // set lies below the next driver block, it all retires and the block goes round again
+    redo = ja < b1 && infoA.x < lastB;
+    // ---- driver blocks that end at or before this partner block's last doc leave the set
+    uint32_t nr = jr;
+#pragma unroll 1
+    while (nr < ja && ms->rdoc[((nr & kSlotMask) << 7) + 127u] <= lastB) nr++;
+    const bool last = !redo && ((ja == b1 && nr == ja) || jb + 1u >= nb);   // the unit's last round
+    if (nr != jr || last) {
+      // bytes may be shared with postings that stay (hash aliases): clear the leavers', then set
+      // the stayers' again. The last round clears everything: the next unit finds a clean map.
+      const uint32_t clr_end = last ? ja : nr;
+#pragma unroll 1
+      for (uint32_t t = jr; t < clr_end; t++) {
+        const uint4 d4 = reinterpret_cast<const uint4 *>(ms->rdoc)[((t & kSlotMask) << 5) + lane];
+        ms->map[d4.x & kMapMask] = 0; ms->map[d4.y & kMapMask] = 0;
+        ms->map[d4.z & kMapMask] = 0; ms->map[d4.w & kMapMask] = 0;
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (uint32_t t = clr_end; t < ja; t++) {
+        const uint4 d4 = reinterpret_cast<const uint4 *>(ms->rdoc)[((t & kSlotMask) << 5) + lane];
+        ms->map[d4.x & kMapMask] = 1; ms->map[d4.y & kMapMask] = 1;
+        ms->map[d4.z & kMapMask] = 1; ms->map[d4.w & kMapMask] = 1;
+      }
+      jr = nr;
+    }
+    __syncwarp();
+    // ---- settle the queue against the ring when it is long enough, or when a block it may match
+    // has left the set (its ring slot may be reused from the next round on): binary search for the
+    // driver posting, which also drops hash aliases and yields the driver-side tf
+    if (nq >= 32 || (nq && q_lo < jr) || last) {
+      const uint32_t lo_blk = ja >= b0 + (uint32_t)kRingBlocks ? ja - (uint32_t)kRingBlocks : b0;
+      const uint32_t glo = lo_blk << 7, ghi = ja << 7;   // driver posting indices the ring holds
+      int base = 0;
+#pragma unroll 1
+      do {
+        bool has = base + lane < nq;
+        uint32_t x = 0u, tfb = 0u, g = glo;
+        if (has) {
+          const uint2 sv = ms->surv[base + lane];
+          x = sv.x;
+          tfb = sv.y;
+        }
+#pragma unroll
+        for (uint32_t s = (uint32_t)kRingBlocks * 64u; s; s >>= 1) {   // lower bound of x in the ring
+          const uint32_t t = g + s;
+          if (t <= ghi && ms->rdoc[(t - 1u) & (uint32_t)kRingMask] < x) g = t;
+        }
+        has = has && g < ghi && ms->rdoc[g & (uint32_t)kRingMask] == x;
+        const unsigned hm = __ballot_sync(kFull, has);
+        if (has) {
+          uint32_t tfa = ms->rtf[g & (uint32_t)kRingMask];
+          if (tfa == 255u) tfa = TfAt(ix, ((first_a + (g >> 7)) << 7) | (g & 127u));
+          const int at = nh + __popc(hm & lt);
+          ms->hdoc[at] = x;
+          ms->htfa[at] = tfa;
+          ms->htfb[at] = tfb;
+        }
+        nh += __popc(hm);
+        __syncwarp();
+        // ---- score 32 verified matches at a time (the only random access: the norm byte); the
+        // unit's last pass scores whatever is left
+        const bool final_pass = last && base + 32 >= nq;
+#pragma unroll 1
+        while (nh >= 32 || (final_pass && nh > 0)) {
+          const int n_now = min(nh, 32);
+          const bool on = lane < n_now;
+          double sc = 0.0;
+          int doc = 0;
+          if (on) {
+            doc = (int)ms->hdoc[lane];
+            const uint32_t ta = ms->htfa[lane], tb = ms->htfb[lane];
+            const double cn = sh->cache[__ldg(ix.norms + doc)];
+            // query order: term 0 first (scoring.h:124-145)
+            sc = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? ta : tb, cn));
+            sc = __dadd_rn(sc, TermScore(idf1, drv == 0 ? tb : ta, cn));
+          }
+          WSR_STAT(st.matches += n_now; st.bytes += n_now;);   // one norm byte per hit
+          OfferToTopK(bv, qi, multi, (int)q.k, on, sc, doc, top, published, lane);
+          // the (at most 31) matches behind the scored ones move to the front
+          const int rest = nh - n_now;
+          uint32_t m0 = 0, m1 = 0, m2 = 0;
+          if (lane < rest) { m0 = ms->hdoc[32 + lane]; m1 = ms->htfa[32 + lane]; m2 = ms->htfb[32 + lane]; }
+          __syncwarp();
+          if (lane < rest) { ms->hdoc[lane] = m0; ms->htfa[lane] = m1; ms->htfb[lane] = m2; }
+          nh = rest;
+          __syncwarp();
+        }
+        base += 32;
+      } while (base < nq);
+      nq = 0;
+    }
+    if (last) break;
+    if (redo) continue;
+    // ---- next partner block: its records were requested at the start of this round
+    jb++;
     infoB = infoB_nxt;
     infoB_nxt = infoB_nxt2;
     rawB = rawB_nxt;
     tfwB = tfwB_nxt;
   }
-  if (nq) MergeFlush(ix, bv, q, qi, sh, ms, nq, ja, b0, first_a, drv, idf0, idf1, top, published, multi, lane, st);
   EmitTopK(bv, q, local, top, lane);
 }
 
@@ -1258,7 +1311,7 @@ __device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const 
 #pragma unroll
       for (int i = 0; i < 4; i++) w[i] = pass[i] ? __ldg(words + ((d[i] - ix.doc_lo) >> (shift & 31u))) : 0u;
 #pragma unroll
-      for (int i = 0; i < 4; i++) pass[i] = pass[i] && FilterTest(w[i], d[i]);
+      for (int i = 0; i < 4; i++) pass[i] = pass[i] && FilterTest(sh, w[i], d[i]);
     }
     unsigned bm[4];
 #pragma unroll
@@ -1300,37 +1353,67 @@ __device__ void ProcessMulti(const DevIndexView &ix, const BatchView &bv, const 
 
 template <int CLASS> struct ScratchOf { typedef MultiScratch type; };
 template <> struct ScratchOf<kClassOne> { typedef NoScratch type; };
-template <> struct ScratchOf<kClassTwo> { typedef TwoScratch type; };
+template <> struct ScratchOf<kClassTwo> { typedef ProbeScratch type; };
 
 // Persistent search kernel of one query class: warps drain the class's unit queue.
 // The per-warp scratch is dynamic shared memory (the two-term class needs more than the 48 KB a
 // kernel may declare statically).
 extern __shared__ __align__(16) unsigned char g_dyn_smem[];
 
-template <int CLASS, bool STATS>
-__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? 3 : CLASS == kClassMany ? 3 : CLASS == kClassOne ? 8 : 1)
+// MERGE: the two-term class runs as two kernels over the same unit queue, one per path, so that
+// each kernel's loops fit the instruction cache (one kernel holding both paths ran at 20 % issue
+// utilisation, stalled on instruction fetch). The unit -> query map carries the unit's path in its
+// top bit; a kernel skips the other path's units.
+constexpr uint32_t kUnitMergeBit = 0x80000000u;
+template <int CLASS, bool MERGE> struct ScratchOfKernel { typedef typename ScratchOf<CLASS>::type type; };
+template <> struct ScratchOfKernel<kClassTwo, false> { typedef ProbeScratch type; };
+template <> struct ScratchOfKernel<kClassTwo, true> { typedef MergeScratch type; };
+
+template <int CLASS, bool STATS, bool MERGE>
+__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? (MERGE ? 3 : 4) : CLASS == kClassMany ? 3 : CLASS == kClassOne ? 8 : 1)
 SearchKernel(const DevIndexView ix, const BatchView bv) {
   __shared__ CtaShared sh;
-  typedef typename ScratchOf<CLASS>::type Scratch;
-  Scratch *scratch = reinterpret_cast<Scratch *>(g_dyn_smem);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+  typedef typename ScratchOfKernel<CLASS, MERGE>::type Scratch;
+  // static shared memory where it fits (ptxas then addresses it without generic-pointer
+  // conversions); only the merge kernel's scratch needs the dynamic window
+  constexpr bool kDynamic = sizeof(Scratch) * kWarpsPerCta > 40 * 1024;
+  __shared__ Scratch static_scratch[kDynamic ? 1 : kWarpsPerCta];
+  Scratch *scratch = kDynamic ? reinterpret_cast<Scratch *>(g_dyn_smem) : static_scratch;
+  // thread id through a volatile asm: ptxas otherwise re-reads %tid and re-derives the warp's
+  // scratch address in front of every shared-memory access (8-18 % of all issued instructions
+  // in the round-2 profiles of the two-term kernels)
+  uint32_t tid;
+  asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+  for (uint32_t i = tid; i < 256u; i += kThreadsPerCta) {
     const double c = ix.cache[i];
     sh.cache[i] = c;
     sh.cache32[i] = __double2float_rd(c);   // smaller denominator => larger (safe) bound
   }
+  if constexpr (CLASS != kClassOne) {
+    for (uint32_t i = tid; i < (uint32_t)kFilterPatterns; i += kThreadsPerCta) sh.fpat[i] = FilterPattern(i);
+  }
+  if constexpr (MERGE) {   // every merge unit starts from, and leaves behind, an all-zero map
+    uint4 *m4 = reinterpret_cast<uint4 *>(g_dyn_smem);
+    for (uint32_t i = tid; i < sizeof(Scratch) * kWarpsPerCta / 16; i += kThreadsPerCta)
+      m4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  auto *ws = &scratch[threadIdx.x >> 5];
+  const int lane = (int)(tid & 31u);
+  auto *ws = &scratch[tid >> 5];
   (void)ws;
   const uint32_t n_units = bv.class_units[CLASS];
   UnitStatsT<STATS> st = {0ull, 0ull, 0ull, 0ull, kNoDoc};
   unsigned long long units = 0;
   for (;;) {
     uint32_t u = 0;
-    if (lane == 0) u = atomicAdd(&bv.counters->next_unit[CLASS], 1u);
+    if (lane == 0) u = atomicAdd(&bv.counters->next_unit[MERGE ? 4 : CLASS], 1u);
     u = __shfl_sync(kFull, u, 0);
     if (u >= n_units) break;
-    const uint32_t qi = __ldg(&bv.unit_query[bv.class_unit_base[CLASS] + u]);
+    uint32_t qi = __ldg(&bv.unit_query[bv.class_unit_base[CLASS] + u]);
+    if constexpr (CLASS == kClassTwo) {
+      if (((qi & kUnitMergeBit) != 0u) != MERGE) continue;   // the other kernel's unit
+      qi &= ~kUnitMergeBit;
+    }
     const DevQuery q = bv.queries[qi];
     st.last_probe = kNoDoc;
     const uint32_t local = u - q.unit_begin;
@@ -1342,8 +1425,8 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
     if constexpr (CLASS == kClassOne) {
       ProcessOneTerm<false>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
     } else if constexpr (CLASS == kClassTwo) {
-      if (q.flags & kQueryMerge) ProcessTwoMerge(ix, bv, q, qi, local, b0, b1, &sh, &ws->m, lane, st);
-      else ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, &ws->p, lane, st);
+      if constexpr (MERGE) ProcessTwoMerge(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
+      else ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     } else if constexpr (CLASS == kClassMany) {
       ProcessMulti<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     } else {
@@ -1373,7 +1456,8 @@ __global__ void UnitMapKernel(const BatchView bv, uint32_t *__restrict__ unit_qu
   uint32_t c = 0;
   while (c < 3 && i >= bv.class_begin[c + 1]) c++;
   uint32_t *dst = unit_query + bv.class_unit_base[c] + q.unit_begin;
-  for (uint32_t u = 0; u < q.n_units; u++) dst[u] = i;
+  const uint32_t v = i | ((c == kClassTwo && (q.flags & kQueryMerge)) ? kUnitMergeBit : 0u);
+  for (uint32_t u = 0; u < q.n_units; u++) dst[u] = v;
 }
 
 // One warp per multi-unit query: folds the units' candidate lists into the final top-k.
@@ -1589,22 +1673,34 @@ __global__ void SegEndKernel(const BatchView bv, uint32_t q_begin, uint32_t n_co
   seg_end[i] = b + bv.seg_count[q_begin + i];
 }
 
-template <int CLASS, bool STATS>
-void LaunchClass(const DevIndexView &ix, const BatchView &b, int sm_count, cudaStream_t s) {
-  const uint32_t nu = b.class_units[CLASS];
+template <int CLASS, bool STATS, bool MERGE>
+void LaunchClassKernel(const DevIndexView &ix, const BatchView &b, uint32_t nu, int sm_count, cudaStream_t s) {
   if (!nu) return;
   // persistent grid = resident CTAs per SM (occupancy query, cached) x SM count
-  constexpr size_t kDyn = sizeof(typename ScratchOf<CLASS>::type) * kWarpsPerCta;
+  constexpr size_t kScratch = sizeof(typename ScratchOfKernel<CLASS, MERGE>::type) * kWarpsPerCta;
+  constexpr size_t kDyn = kScratch > 40 * 1024 ? kScratch : 0;   // see SearchKernel: small scratch is static
   static int occ = 0;
   if (!occ) {
     int o = 0;
-    cudaFuncSetAttribute(SearchKernel<CLASS, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, SearchKernel<CLASS, STATS>, kThreadsPerCta, kDyn);
+    if (kDyn) cudaFuncSetAttribute(SearchKernel<CLASS, STATS, MERGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDyn);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, SearchKernel<CLASS, STATS, MERGE>, kThreadsPerCta, kDyn);
     occ = o > 0 ? o : 1;
   }
   const uint32_t want = (nu + kWarpsPerCta - 1) / kWarpsPerCta;
   const uint32_t grid = std::min<uint32_t>(want, (uint32_t)(sm_count * occ));
-  SearchKernel<CLASS, STATS><<<grid, kThreadsPerCta, kDyn, s>>>(ix, b);
+  SearchKernel<CLASS, STATS, MERGE><<<grid, kThreadsPerCta, kDyn, s>>>(ix, b);
+}
+
+template <int CLASS, bool STATS>
+void LaunchClass(const DevIndexView &ix, const BatchView &b, int sm_count, cudaStream_t s) {
+  if constexpr (CLASS == kClassTwo) {
+    // both kernels walk the class's whole unit queue and take their own path's units
+    const uint32_t nu = b.class_units[CLASS];
+    if (b.merge_units < nu) LaunchClassKernel<CLASS, STATS, false>(ix, b, nu, sm_count, s);
+    if (b.merge_units) LaunchClassKernel<CLASS, STATS, true>(ix, b, nu, sm_count, s);
+  } else {
+    LaunchClassKernel<CLASS, STATS, false>(ix, b, b.class_units[CLASS], sm_count, s);
+  }
 }
 
 }  // namespace

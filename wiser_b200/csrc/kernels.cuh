@@ -59,9 +59,11 @@ struct DevQuery {
 static_assert(sizeof(DevQuery) == 64, "DevQuery is 64 bytes");
 constexpr uint8_t kQueryPhrase = 1;   // terms must occur at consecutive positions, in query order
 constexpr uint8_t kQueryMerge = 2;    // two-term query whose lists are of similar length: merge path
-// Merge path when partner blocks <= kMergeRatioX4/4 x driver blocks (DevIndexView::merge_ratio_x4;
-// WSR_MERGE_RATIO_X4 overrides at wsr_index_open, 0 switches the path off).
-constexpr uint32_t kMergeRatioX4 = 16;
+// Merge path when partner blocks <= merge_ratio_x4/4 x driver blocks (DevIndexView::merge_ratio_x4,
+// set from WSR_MERGE_RATIO_X4 at wsr_index_open). OFF by default: measured on B200 (C2, two-term
+// log) the merge kernel needs ~460 warp instructions per partner block against ~590 per DRIVER
+// block on the probe path, so it loses even on exactly balanced lists (profiles/r2_notes.md).
+constexpr uint32_t kMergeRatioX4 = 0;
 __host__ __device__ inline bool UseMergePath(uint32_t n_terms, bool phrase, unsigned long long drv_blocks,
                                              unsigned long long probe_blocks, uint32_t ratio_x4) {
   return n_terms == 2 && !phrase && ratio_x4 != 0 && probe_blocks * 4ull <= drv_blocks * (unsigned long long)ratio_x4;
@@ -73,7 +75,8 @@ struct DevCounters {
   unsigned long long matches;
   unsigned long long units;
   unsigned long long probe_blocks;
-  unsigned int next_unit[4];      // one dynamic queue per query class
+  unsigned int next_unit[5];      // one dynamic queue per query class; [4]: the two-term merge kernel
+  unsigned int pad_;
 };
 
 struct BatchView {
@@ -82,6 +85,7 @@ struct BatchView {
   uint32_t class_unit_base[4];
   uint32_t class_begin[5];
   uint32_t class_units[4];
+  uint32_t merge_units;        // units of the two-term class that take the merge path
   wsr_hit *hits;               // n * k_stride
   int32_t *n_hits;             // n
   wsr_hit *cand;               // kMaxFastK entries per unit of every multi-unit query
@@ -133,9 +137,11 @@ struct DevDict {
   const char *arena;
 };
 // Per-query plan contribution / running sums: v[0..2] queries per class (one, two, many),
-// v[3..5] work units per class, v[6] candidate-list units of multi-unit queries, v[7] their number.
+// v[3..5] work units per class, v[6] candidate-list units of multi-unit queries, v[7] their number,
+// v[8] units of two-term queries that take the merge path.
+constexpr int kPlanWords = 9;
 struct PlanItem {
-  uint32_t v[8];
+  uint32_t v[kPlanWords];
 };
 size_t FrontEndTempBytes(uint32_t len, uint32_t n_lines);
 // Enqueues: newline positions -> parse + term lookup + per-query planning -> exclusive scan ->
@@ -154,6 +160,11 @@ void LaunchPlanQueries(const wsr_query *d_in, uint32_t n, uint32_t k_stride, con
                        DevQuery *d_tmp, PlanItem *d_item, PlanItem *d_excl, DevQuery *d_planned,
                        uint32_t *d_multi, PlanItem *d_totals, uint32_t *d_err, void *d_cub, size_t cub_bytes,
                        cudaStream_t s);
+
+// doc_freqs of a batch planned by LaunchFrontEnd / LaunchPlanQueries (reads its d_tmp):
+// d_doc_freqs[n * WSR_MAX_TERMS], d_n_doc_freqs[n].
+void LaunchDocFreqs(const DevQuery *d_tmp, uint32_t n, const DevIndexView &ix, uint32_t *d_doc_freqs,
+                    int32_t *d_n_doc_freqs, cudaStream_t s);
 
 // Dense packing of a batch's results for the D2H copy: offsets = exclusive sum of n_hits over
 // n + 1 slots (d_off[n] = total), then packed[off[q] + j] = hits[q*k + j] for j < n_hits[q].

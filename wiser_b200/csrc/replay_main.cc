@@ -14,6 +14,9 @@
 //                                   locallog: n_threads client threads calling Search()
 //                                             (LocalLogTreatmentExecutor, engine_bench.cc:214-290)
 //   -n_threads=N  -n_results=K  -batch_size=B  -repeat=R  -dump=<file>
+//   -dirs=<p0>,<p1>,..  -devices=0,1,..   instead of -engine: a document-partitioned collection, one
+//                                   vacuum directory per partition, spread over the listed GPUs of
+//                                   this process (wsr_group_*; batchlog only)
 // -dump writes one line per query: <n_entries> <n_doc_freqs> {<doc> <score %a>}* {<df>}*
 #include <atomic>
 #include <chrono>
@@ -72,6 +75,85 @@ SearchQuery ParseLine(std::string line, int n_results) {
   return q;
 }
 
+std::vector<std::string> Split(const std::string &s, char sep) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (char c : s) {
+    if (c == sep) { if (!cur.empty()) out.push_back(cur); cur.clear(); }
+    else cur += c;
+  }
+  if (!cur.empty()) out.push_back(cur);
+  return out;
+}
+
+// -dirs=<p0>,<p1>,... [-devices=0,1,...]: a document-partitioned collection (one vacuum directory
+// per partition, local doc ids) served by one process over one or more GPUs through the group API
+// (wsr_group_search_log: per-partition search, on-device merge, NCCL exchange between devices).
+// The dump has the format of the single-index one, with global doc ids.
+int ReplayGroup(int argc, char **argv, const std::string &dirs_flag, const std::string &text, int n_results,
+                int batch_size, int repeat, const std::string &dump) {
+  const std::vector<std::string> dirs = Split(dirs_flag, ',');
+  std::vector<int> devices;
+  for (const std::string &d : Split(FlagStr(argc, argv, "devices", "0"), ',')) devices.push_back(atoi(d.c_str()));
+  std::vector<const char *> dptr;
+  for (const std::string &d : dirs) dptr.push_back(d.c_str());
+  char err[512] = {0};
+  const auto t_load = std::chrono::steady_clock::now();
+  wsr_group *g = wsr_group_open(dptr.data(), (int)dptr.size(), devices.data(), (int)devices.size(), 0, 0u, nullptr,
+                                err, sizeof(err));
+  if (!g) { fprintf(stderr, "wsr_group_open: %s\n", err); return 1; }
+  const double load_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count();
+  std::vector<size_t> line_at;
+  for (size_t p = 0; p < text.size();) {
+    line_at.push_back(p);
+    const size_t e = text.find('\n', p);
+    p = e == std::string::npos ? text.size() : e + 1;
+  }
+  const int n = (int)line_at.size();
+  line_at.push_back(text.size());
+  const int B = batch_size > 0 ? std::min(batch_size, n) : n;
+  wsr_hit *hits = (wsr_hit *)wsr_host_alloc((size_t)B * n_results * sizeof(wsr_hit));
+  int32_t *n_hits = (int32_t *)wsr_host_alloc((size_t)B * 4);
+  uint32_t *dfs = (uint32_t *)wsr_host_alloc((size_t)B * WSR_MAX_TERMS * 4);
+  int32_t *ndf = (int32_t *)wsr_host_alloc((size_t)B * 4);
+  if (!hits || !n_hits || !dfs || !ndf) { fprintf(stderr, "pinned alloc failed\n"); return 1; }
+  FILE *df = dump.empty() ? nullptr : fopen(dump.c_str(), "w");
+  uint64_t n_queries = 0, listed = 0, entries = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (int rep = 0; rep < repeat; rep++) {
+    for (int lo = 0; lo < n; lo += B) {
+      const int m = std::min(B, n - lo);
+      int got = 0;
+      if (wsr_group_search_log(g, text.data() + line_at[lo], line_at[lo + m] - line_at[lo], n_results, hits, n_hits,
+                               dfs, ndf, B, &got) != 0 || got != m) {
+        fprintf(stderr, "wsr_group_search_log: %s\n", wsr_last_error());
+        return 1;
+      }
+      for (int i = 0; i < m; i++) {
+        entries += n_hits[i];
+        for (int t = 0; t < ndf[i]; t++) listed += dfs[(size_t)i * WSR_MAX_TERMS + t];
+        if (df && rep == 0) {
+          fprintf(df, "%d %d", n_hits[i], ndf[i]);
+          for (int j = 0; j < n_hits[i]; j++)
+            fprintf(df, " %d %a", hits[(size_t)i * n_results + j].doc_id, hits[(size_t)i * n_results + j].score);
+          for (int t = 0; t < ndf[i]; t++) fprintf(df, " %u", dfs[(size_t)i * WSR_MAX_TERMS + t]);
+          fprintf(df, "\n");
+        }
+      }
+      n_queries += m;
+    }
+  }
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  if (df) fclose(df);
+  wsr_host_free(hits); wsr_host_free(n_hits); wsr_host_free(dfs); wsr_host_free(ndf);
+  wsr_group_close(g);
+  printf("WSR_REPLAY_JSON {\"mode\": \"group\", \"partitions\": %zu, \"devices\": %zu, \"queries\": %" PRIu64
+         ", \"seconds\": %.6f, \"qps\": %.3f, \"listed_postings\": %" PRIu64 ", \"listed_postings_per_s\": %.3f, "
+         "\"result_entries\": %" PRIu64 ", \"load_seconds\": %.3f}\n",
+         dirs.size(), devices.size(), n_queries, secs, n_queries / secs, listed, listed / secs, entries, load_s);
+  return 0;
+}
+
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -83,7 +165,7 @@ int main(int argc, char **argv) {
   const int n_results = atoi(FlagStr(argc, argv, "n_results", "5").c_str());
   const int batch_size = atoi(FlagStr(argc, argv, "batch_size", "65536").c_str());
   const int repeat = atoi(FlagStr(argc, argv, "repeat", "1").c_str());
-  if (engine_url.empty() || query_path.empty()) {
+  if ((engine_url.empty() && FlagStr(argc, argv, "dirs", "").empty()) || query_path.empty()) {
     fprintf(stderr, "usage: wsr_replay -engine=gpu:vacuum_dump:<dir> -query_path=<log> "
                     "[-exp_mode=batchlog|locallog] [-n_threads=N] [-n_results=K] "
                     "[-batch_size=B] [-repeat=R] [-dump=<file>]\n");
@@ -94,6 +176,8 @@ int main(int argc, char **argv) {
     fprintf(stderr, "File may not exist: %s\n", query_path.c_str());   // QueryLogReader, query_pool.h:18-23
     return 1;
   }
+  const std::string dirs_flag = FlagStr(argc, argv, "dirs", "");
+  if (!dirs_flag.empty()) return ReplayGroup(argc, argv, dirs_flag, text, n_results, batch_size, repeat, dump);
   std::unique_ptr<SearchEngineServiceNew> engine = wsr::CreateSearchEngine(engine_url);
   const auto t_load = std::chrono::steady_clock::now();
   engine->Load();

@@ -201,6 +201,7 @@ struct wsr_batch {
   uint32_t class_units[4] = {0, 0, 0, 0};
   uint32_t np = 0, n_multi = 0;      // planned queries / multi-unit queries (either planner)
   uint32_t n_cand_units = 0, n_seg_entries = 0, n_collect = 0;
+  uint32_t merge_units = 0;          // units of the two-term class on the merge path
   uint64_t listed_postings = 0, listed_bytes = 0;
   uint32_t launches = 0;
   // device
@@ -238,6 +239,10 @@ struct wsr_batch {
   PinnedBuf<wsr_hit> h_packed;
   PinnedBuf<int32_t> h_n;
   PinnedBuf<uint32_t> h_totals;        // PlanItem (8 words) + error bits
+  DevBuf<uint32_t> d_df;               // doc_freqs of a log planned on the device
+  DevBuf<int32_t> d_ndf;
+  PinnedBuf<uint32_t> h_df;
+  PinnedBuf<int32_t> h_ndf;
   // pinned staging for the host-buffer API
   PinnedBuf<DevQuery> h_queries;
   PinnedBuf<uint8_t> h_out;            // same layout as d_out (hits | n_hits)
@@ -260,7 +265,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
   const int T = HostThreads((size_t)n, 1024);
   struct Part {
     uint32_t count[4] = {0, 0, 0, 0}, units[4] = {0, 0, 0, 0};
-    uint32_t cand = 0, multi = 0;
+    uint32_t cand = 0, multi = 0, merge_units = 0;
     uint64_t seg = 0, listed = 0, listed_bytes = 0;
     int err = 0;
   };
@@ -332,6 +337,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
       if (c == kClassTwo && UseMergePath(q.n_terms, dq.flags & kQueryPhrase, drv.n_blocks, probe_blocks,
                                          ix->view.merge_ratio_x4))
         dq.flags |= kQueryMerge;
+      if (dq.flags & kQueryMerge) p.merge_units += dq.n_units;
       if (c == kClassOne) dq.n_units = 1;   // block-max prepass + selective decode, one warp
       b->tmp[i] = dq;
       b->tmp_cls[i] = (uint8_t)c;
@@ -354,6 +360,8 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
   uint32_t pos = 0, cand = 0, multi = 0;
   uint64_t seg = 0;
   b->listed_postings = b->listed_bytes = 0;
+  b->merge_units = 0;
+  for (const Part &p : part) b->merge_units += p.merge_units;
   for (int c = 0; c < 4; c++) {
     b->class_begin[c] = pos;
     uint32_t units = 0;
@@ -376,7 +384,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
     b->listed_postings += part[t].listed;
     b->listed_bytes += part[t].listed_bytes;
   }
-  if (seg > 0xfffffff0ull) return Fail(WSR_ERR_UNSUPPORTED, "collect-mode batch too large");
+  if (seg > 0x7fffffffull) return Fail(WSR_ERR_UNSUPPORTED, "collect-mode batch too large (cub counts in int)");
   b->planned.resize(pos);
   b->multi.resize(multi);
   auto place = [&](int t, int TT) {
@@ -447,6 +455,7 @@ int PrepareBatch(wsr_batch *b, bool plan_on_host) {
   }
   for (int c = 0; c < 5; c++) v.class_begin[c] = b->class_begin[c];
   for (int c = 0; c < 4; c++) v.class_units[c] = b->class_units[c];
+  v.merge_units = b->merge_units;
   v.hits = b->out_hits;
   v.n_hits = b->out_n;
   v.cand = b->d_cand.p;
@@ -495,6 +504,7 @@ int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr, bool count_work = false)
     LaunchSearchClass(b->idx->view, b->view, c, b->idx->sm_count, b->stream, count_work);
     if (ev) CU(cudaEventRecord(ev[1 + c], b->stream));
     launches += b->class_units[c] ? 1 : 0;
+    if (c == kClassTwo && b->merge_units && b->merge_units < b->class_units[c]) launches++;   // both paths' kernels
   }
   if (b->n_multi) {
     LaunchMerge(b->view, b->d_multi.p, b->n_multi, b->stream);
@@ -510,6 +520,15 @@ int EnqueueRun(wsr_batch *b, cudaEvent_t *ev = nullptr, bool count_work = false)
   b->launches = launches;
   CU(cudaGetLastError());
   return WSR_OK;
+}
+
+// A batch whose (re)planning failed must not be runnable: its device plan may be half written.
+void InvalidateBatch(wsr_batch *b) {
+  b->n = 0;
+  b->np = b->n_multi = b->n_cand_units = b->n_seg_entries = b->n_collect = 0;
+  b->merge_units = b->view.merge_units = 0;
+  for (int c = 0; c < 4; c++) b->class_units[c] = b->view.class_units[c] = 0;
+  for (int c = 0; c < 5; c++) b->class_begin[c] = b->view.class_begin[c] = 0;
 }
 
 wsr_batch *NewBatch(wsr_index *idx) {
@@ -545,6 +564,22 @@ void ReleasePooled(wsr_index *idx, wsr_batch *b) {
   std::lock_guard<std::mutex> g(idx->pool_mu);
   idx->pool.push_back(b);
 }
+
+// Returns a pooled batch when it goes out of scope, after its stream has drained (no copy may
+// still target the caller's buffers, and the next user must not race the previous one's work).
+struct PooledBatch {
+  wsr_index *idx;
+  wsr_batch *b;
+  PooledBatch(wsr_index *i) : idx(i), b(AcquirePooled(i)) {}
+  ~PooledBatch() {
+    if (!b) return;
+    cudaStreamSynchronize(b->stream);
+    ReleasePooled(idx, b);
+  }
+  PooledBatch(const PooledBatch &) = delete;
+  PooledBatch &operator=(const PooledBatch &) = delete;
+};
+
 
 }  // namespace
 
@@ -898,17 +933,22 @@ wsr_batch *wsr_batch_create(wsr_index *idx, const wsr_query *queries, int n, int
 int wsr_batch_reset(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
   if (!b || (!queries && n > 0) || n < 0 || k_stride < 1) return Fail(WSR_ERR_ARG, "bad argument");
   CU(cudaSetDevice(b->idx->device));
+  // the previous plan's H2D copies read the pinned staging this call is about to overwrite
+  CU(cudaStreamSynchronize(b->stream));
   int rc = PlanBatch(b, queries, n, k_stride);
   if (rc == WSR_OK) rc = UploadBatch(b);
+  if (rc != WSR_OK) InvalidateBatch(b);
   return rc;
 }
 
 int wsr_batch_reset_log(wsr_batch *b, const char *text, size_t len, int k, int *n_queries) {
   if (!b || (!text && len) || k < 1 || !n_queries) return Fail(WSR_ERR_ARG, "bad argument");
   CU(cudaSetDevice(b->idx->device));
+  CU(cudaStreamSynchronize(b->stream));   // see wsr_batch_reset
   if (DeviceFrontEndUsable(b->idx, len, k)) {
     const int rc = PlanLogOnDevice(b, text, len, k, 0x7fffffff);
     if (rc == WSR_OK) *n_queries = b->n;
+    else InvalidateBatch(b);
     return rc;
   }
   size_t lines = 1;
@@ -919,6 +959,7 @@ int wsr_batch_reset_log(wsr_batch *b, const char *text, size_t len, int k, int *
   if (rc == WSR_OK) rc = PlanBatch(b, qs.data(), n, k);
   if (rc == WSR_OK) rc = UploadBatch(b);
   if (rc == WSR_OK) *n_queries = n;
+  else InvalidateBatch(b);
   return rc;
 }
 
@@ -986,14 +1027,17 @@ int wsr_batch_time(wsr_batch *b, int iters, float *ms_per_iter) {
 int wsr_batch_profile(wsr_batch *b, float ms[6]) {
   if (!b || !ms) return Fail(WSR_ERR_ARG, "null argument");
   CU(cudaSetDevice(b->idx->device));
-  cudaEvent_t ev[6];
+  struct Events {
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~Events() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
+  } evs;
+  cudaEvent_t *ev = evs.ev;
   for (int i = 0; i < 6; i++) CU(cudaEventCreate(&ev[i]));
   int rc = EnqueueRun(b, ev);
   if (rc) return rc;
   CU(cudaStreamSynchronize(b->stream));
   for (int i = 0; i < 5; i++) CU(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
   CU(cudaEventElapsedTime(&ms[5], ev[0], ev[5]));
-  for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
   return WSR_OK;
 }
 
@@ -1124,7 +1168,8 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
           doc_freqs[(size_t)i * WSR_MAX_TERMS + t] = idx->host.lists[q.term_ids[t]].df_global;
     }
   }
-  wsr_batch *b = AcquirePooled(idx);
+  PooledBatch pooled(idx);
+  wsr_batch *b = pooled.b;
   if (!b) return Fail(WSR_ERR_CUDA, "cannot create batch");
   // large batches without collect-class queries are planned on the GPU, the rest by host threads
   static const bool host_planner = getenv("WSR_HOST_FRONTEND") && atoi(getenv("WSR_HOST_FRONTEND")) != 0;
@@ -1137,7 +1182,6 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
   }
   if (rc == WSR_OK) rc = EnqueueRun(b);
   if (rc == WSR_OK) rc = wsr_batch_fetch(b, hits, n_hits);
-  ReleasePooled(idx, b);
   return rc;
 }
 
@@ -1184,7 +1228,7 @@ int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q
   CU(b->d_totals.Ensure(1));
   CU(b->d_queries.Ensure((size_t)n + 1));
   CU(b->d_multi.Ensure((size_t)n + 1));
-  CU(b->h_totals.Ensure(9));
+  CU(b->h_totals.Ensure(kPlanWords + 1));
   const size_t cub_bytes = FrontEndTempBytes((uint32_t)len, n);
   CU(b->d_fe_cub.Ensure(cub_bytes));
   CU(cudaMemsetAsync(b->d_fe_small.p, 0, 8, b->stream));
@@ -1198,14 +1242,16 @@ int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q
 // Second half of both device planners: reads the 36 bytes of totals back, turns them into the
 // class layout, sizes the batch's buffers and enqueues the unit -> query map.
 int FinishDevicePlan(wsr_batch *b, uint32_t n, int k_stride) {
-  CU(cudaMemcpyAsync(b->h_totals.p, b->d_totals.p, 32, cudaMemcpyDeviceToHost, b->stream));
-  CU(cudaMemcpyAsync(b->h_totals.p + 8, b->d_fe_small.p + 1, 4, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaMemcpyAsync(b->h_totals.p, b->d_totals.p, kPlanWords * 4, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaMemcpyAsync(b->h_totals.p + kPlanWords, b->d_fe_small.p + 1, 4, cudaMemcpyDeviceToHost, b->stream));
   CU(cudaStreamSynchronize(b->stream));
   const uint32_t *tot = b->h_totals.p;
-  if (tot[8] & 1u) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
-  if (tot[8] & 2u)
+  const uint32_t errs = tot[kPlanWords];
+  if (errs & 7u) InvalidateBatch(b);   // the plan in d_queries is not usable
+  if (errs & 1u) return Fail(WSR_ERR_UNSUPPORTED, "more than WSR_MAX_TERMS terms");
+  if (errs & 2u)
     return Fail(WSR_ERR_UNSUPPORTED, "phrase query on an index opened without WSR_OPEN_POSITIONS");
-  if (tot[8] & 4u) return Fail(WSR_ERR_ARG, "query k exceeds k_stride, or term id out of range");
+  if (errs & 4u) return Fail(WSR_ERR_ARG, "query k exceeds k_stride, or term id out of range");
   b->n = (int)n;
   b->k_stride = k_stride;
   b->planned.clear();
@@ -1221,6 +1267,7 @@ int FinishDevicePlan(wsr_batch *b, uint32_t n, int k_stride) {
   b->np = pos;
   b->n_multi = tot[7];
   b->n_cand_units = tot[6];
+  b->merge_units = tot[8];
   b->n_seg_entries = b->n_collect = 0;
   b->listed_postings = b->listed_bytes = 0;   // not tallied by the device planners
   const int rc = PrepareBatch(b, /*plan_on_host=*/false);
@@ -1251,7 +1298,7 @@ int PlanQueriesOnDevice(wsr_batch *b, const wsr_query *queries, int n_in, int k_
   CU(b->d_totals.Ensure(1));
   CU(b->d_queries.Ensure((size_t)n + 1));
   CU(b->d_multi.Ensure((size_t)n + 1));
-  CU(b->h_totals.Ensure(9));
+  CU(b->h_totals.Ensure(kPlanWords + 1));
   const size_t cub_bytes = FrontEndTempBytes(16, n);
   CU(b->d_fe_cub.Ensure(cub_bytes));
   CU(cudaMemsetAsync(b->d_fe_small.p, 0, 8, b->stream));
@@ -1267,18 +1314,45 @@ bool DeviceFrontEndUsable(const wsr_index *idx, size_t len, int k) {
   return !host_frontend && idx->dict_on_device && k <= kMaxFastK && len > 0 && len < 0x7ffffff0ull;   // cub counts in int
 }
 
+// doc_freqs of the log a batch was just planned from on the device: kernel + D2H on the batch
+// stream, into the caller's arrays (through pinned staging unless they are pinned themselves).
+int EnqueueDocFreqs(wsr_batch *b, uint32_t *doc_freqs, int32_t *n_doc_freqs, bool *staged) {
+  const uint32_t n = (uint32_t)b->n;
+  *staged = false;
+  if (!n) return WSR_OK;
+  CU(b->d_df.Ensure((size_t)n * WSR_MAX_TERMS));
+  CU(b->d_ndf.Ensure(n));
+  LaunchDocFreqs(b->d_tmp.p, n, b->idx->view, b->d_df.p, b->d_ndf.p, b->stream);
+  CU(cudaGetLastError());
+  uint32_t *df = doc_freqs;
+  int32_t *ndf = n_doc_freqs;
+  if (!IsPinned(doc_freqs) || !IsPinned(n_doc_freqs)) {
+    CU(b->h_df.Ensure((size_t)n * WSR_MAX_TERMS));
+    CU(b->h_ndf.Ensure(n));
+    df = b->h_df.p;
+    ndf = b->h_ndf.p;
+    *staged = true;
+  }
+  CU(cudaMemcpyAsync(df, b->d_df.p, (size_t)n * WSR_MAX_TERMS * 4, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaMemcpyAsync(ndf, b->d_ndf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
+  return WSR_OK;
+}
+
 int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
-                      int32_t *n_hits, int cap_q, int *n_queries) {
-  wsr_batch *b = AcquirePooled(idx);
+                      int32_t *n_hits, uint32_t *doc_freqs, int32_t *n_doc_freqs, int cap_q,
+                      int *n_queries) {
+  PooledBatch pooled(idx);
+  wsr_batch *b = pooled.b;
   if (!b) return Fail(WSR_ERR_CUDA, "cannot create batch");
-  struct Release {
-    wsr_index *i; wsr_batch *b;
-    ~Release() { cudaStreamSynchronize(b->stream); ReleasePooled(i, b); }
-  } release{idx, b};
   int rc = PlanLogOnDevice(b, text, len, k, cap_q);
   const uint32_t n = (uint32_t)b->n;
   if (rc == WSR_OK) rc = EnqueueRun(b);
   if (rc) return rc;
+  bool df_staged = false;
+  if (doc_freqs && n_doc_freqs) {
+    rc = EnqueueDocFreqs(b, doc_freqs, n_doc_freqs, &df_staged);
+    if (rc) return rc;
+  }
   const size_t nh = (size_t)n * k;
   const bool pinned = IsPinned(hits) && IsPinned(n_hits);
   int32_t *cnt = n_hits;
@@ -1292,13 +1366,14 @@ int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_h
   // less PCIe traffic, but a host round trip between kernel and copy, and the first copy after
   // such a gap was measured ~350 us slower on the B200 boxes (4.7 MB: 444 us vs 93 us back to
   // back). So the packed path is taken only when the index's recent logs were under 10 % full.
-  const bool packed_path = idx->result_fill_ppm.load(std::memory_order_relaxed) < 100000;
+  // (the packed path sums hit counts in int32: n*k must fit)
+  const bool packed_path = idx->result_fill_ppm.load(std::memory_order_relaxed) < 100000 && nh < 0x7fffffffull;
   size_t total = 0;
   if (packed_path) {
     const size_t cub_bytes = PackTempBytes(n);
     CU(b->d_off.Ensure((size_t)n + 2));
     CU(b->d_pack_cub.Ensure(cub_bytes));
-    CU(b->h_totals.Ensure(9));
+    CU(b->h_totals.Ensure(kPlanWords + 1));
     LaunchResultOffsets(b->out_n, b->d_off.p, n, b->d_pack_cub.p, cub_bytes, b->stream);
     CU(cudaMemcpyAsync(cnt, b->out_n, (size_t)n * 4, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaMemcpyAsync(b->h_totals.p, b->d_off.p + n, 4, cudaMemcpyDeviceToHost, b->stream));
@@ -1343,6 +1418,10 @@ int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_h
   }
   if (nh) idx->result_fill_ppm.store((int)(total * 1000000ull / nh), std::memory_order_relaxed);
   if (!pinned) memcpy(n_hits, cnt, (size_t)n * 4);
+  if (df_staged) {   // both result paths ended with a stream synchronize: the staging is complete
+    memcpy(doc_freqs, b->h_df.p, (size_t)n * WSR_MAX_TERMS * 4);
+    memcpy(n_doc_freqs, b->h_ndf.p, (size_t)n * 4);
+  }
   *n_queries = (int)n;
   return WSR_OK;
 }
@@ -1351,13 +1430,20 @@ int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_h
 
 int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
                    int32_t *n_hits, int cap_q, int *n_queries) {
-  if (!idx || (!text && len) || k < 1 || !hits || !n_hits || !n_queries || cap_q < 0)
+  return wsr_search_log_ex(idx, text, len, k, hits, n_hits, nullptr, nullptr, cap_q, n_queries);
+}
+
+int wsr_search_log_ex(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
+                      int32_t *n_hits, uint32_t *doc_freqs, int32_t *n_doc_freqs, int cap_q,
+                      int *n_queries) {
+  if (!idx || (!text && len) || k < 1 || !hits || !n_hits || !n_queries || cap_q < 0 ||
+      (doc_freqs == nullptr) != (n_doc_freqs == nullptr))
     return Fail(WSR_ERR_ARG, "bad argument");
   CU(cudaSetDevice(idx->device));
   // k <= kMaxFastK (no collect class) and a dictionary in HBM: parse and plan on the GPU.
   // WSR_HOST_FRONTEND=1 forces the host parser/planner (the same one wsr_search_batch uses).
   if (DeviceFrontEndUsable(idx, len, k))
-    return SearchLogOnDevice(idx, text, len, k, hits, n_hits, cap_q, n_queries);
+    return SearchLogOnDevice(idx, text, len, k, hits, n_hits, doc_freqs, n_doc_freqs, cap_q, n_queries);
   // chunk boundaries on line starts: up to 4 chunks of at least 128 KiB of text each
   const int n_chunks = (int)std::max<size_t>(1, std::min<size_t>(4, len >> 17));
   std::vector<size_t> cut(n_chunks + 1, len);
@@ -1368,7 +1454,8 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
     cut[c] = p < len ? p + 1 : len;
   }
   const bool pinned = IsPinned(hits) && IsPinned(n_hits);
-  wsr_batch *bt[2] = {AcquirePooled(idx), AcquirePooled(idx)};
+  PooledBatch pool0(idx), pool1(idx);   // released (after their streams drain) on every return path
+  wsr_batch *bt[2] = {pool0.b, pool1.b};
   if (!bt[0] || !bt[1]) return Fail(WSR_ERR_CUDA, "cannot create batch");
   struct Pend { int q0 = 0, n = 0; bool live = false; } pend[2];
   std::vector<wsr_query> qs;
@@ -1399,6 +1486,17 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
     int n = 0;
     rc = wsr_parse_query_log(idx, ct, cl, k, qs.data(), (int)qs.size(), &n);   // overlaps the GPU
     if (rc) break;
+    if (doc_freqs) {   // vacuum_engine.h:206-219, as wsr_search_batch fills them
+      for (int i = 0; i < n; i++) {
+        const wsr_query &q = qs[i];
+        bool ok = q.k > 0 && q.n_terms > 0;
+        for (uint32_t t = 0; ok && t < q.n_terms; t++) ok = q.term_ids[t] != WSR_TERM_ABSENT;
+        n_doc_freqs[done_q + i] = ok ? (int32_t)q.n_terms : 0;
+        for (uint32_t t = 0; t < WSR_MAX_TERMS; t++)
+          doc_freqs[(size_t)(done_q + i) * WSR_MAX_TERMS + t] =
+              ok && t < q.n_terms ? idx->host.lists[q.term_ids[t]].df_global : 0u;
+      }
+    }
     rc = drain(s);                         // this slot's previous chunk must be finished
     if (rc) break;
     wsr_batch *b = bt[s];
@@ -1423,10 +1521,7 @@ int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit 
   for (int s = 0; s < 2; s++) {
     const int r2 = drain(s);
     if (rc == WSR_OK) rc = r2;
-    if (pend[s].live) cudaStreamSynchronize(bt[s]->stream);
   }
-  ReleasePooled(idx, bt[0]);
-  ReleasePooled(idx, bt[1]);
   *n_queries = done_q;
   return rc;
 }
@@ -1473,3 +1568,5 @@ int wsr_merge_topk_device(const void *d_gathered_hits, const void *d_gathered_n_
 }
 
 }  // extern "C"
+
+#include "wsr_group.inl"

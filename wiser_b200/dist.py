@@ -20,6 +20,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from . import capi
 from .capi import HIT_DTYPE, check, lib
 
 
@@ -73,30 +74,55 @@ def exchange_slices(hits_u8, n_hits_i32, n, k, rank, world, recv_hits, recv_n):
     return mine
 
 
-class _DevPtr:
-    """Exposes a raw device pointer to torch through __cuda_array_interface__."""
+def _new_comm_id(rank):
+    """NCCL unique id for the C-ABI exchange: created by rank 0 in the library, handed to the
+    other ranks through torch.distributed (plumbing)."""
+    buf = C.create_string_buffer(capi.WSR_COMM_ID_BYTES)
+    if rank == 0:
+        check(lib().wsr_comm_unique_id(buf))
+    objs = [buf.raw if rank == 0 else None]
+    dist.broadcast_object_list(objs, src=0)
+    return objs[0]
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
-                                         "version": 3}
 
-
-def device_bytes(ptr, nbytes, device):
-    return torch.as_tensor(_DevPtr(ptr, nbytes), device=device)
+def _exchange_df(df_locals, ranks_list, dev):
+    """Collection-wide df of every local term. Synthetic vocabularies (terms named t<rank>): a
+    dense all-reduce over term ranks; general ones: an exchange of (term, df) tables."""
+    vmax = torch.tensor([max([int(r.max()) + 1 if len(r) else 1 for r in ranks_list])], dtype=torch.int64, device=dev)
+    dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
+    dense = torch.zeros(int(vmax.item()), dtype=torch.int64, device=dev)
+    for df, r in zip(df_locals, ranks_list):
+        dense.index_add_(0, torch.from_numpy(r.astype(np.int64)).to(dev), torch.from_numpy(df.astype(np.int64)).to(dev))
+    dist.all_reduce(dense)
+    return [dense[torch.from_numpy(r.astype(np.int64)).to(dev)].cpu().numpy().astype(np.uint32) for r in ranks_list]
 
 
 class ShardedSearch:
-    """One rank of a document-partitioned deployment."""
+    """One rank of a document-partitioned deployment: one engine (one partition directory) per
+    process. The per-batch exchange runs in the library (wsr_batch_exchange: NCCL called from C on
+    the batch's stream); torch.distributed only carries the communicator id and the one-time
+    exchange of collection statistics."""
 
     def __init__(self, engine, rank, world, device=None, term_keys="synthetic_rank", exchange=None):
+        if getattr(engine, "n_shards", 1) != 1:
+            # a doc-range shard of ONE directory already scores with the collection's statistics
+            # and emits global doc ids; feeding it through the partition exchange would count N
+            # world times and offset the ids twice
+            raise ValueError("ShardedSearch expects every rank to open its OWN partition directory "
+                             "(n_shards == 1); doc-range shards of one directory need no statistics exchange")
         self.engine, self.rank, self.world = engine, rank, world
         self.exchange = exchange or os.environ.get("WSR_EXCHANGE", "scatter")
         if self.exchange not in ("scatter", "allgather"):
             raise ValueError("exchange must be 'scatter' or 'allgather'")
         self.device = device if device is not None else torch.device("cuda", engine.device)
         self.term_keys = term_keys
-        self._bufs = {}
+        self._comm = None
         self.exchange_stats()
+        if dist.get_backend() == "nccl":
+            cid = _new_comm_id(rank)
+            self._comm = lib().wsr_comm_init_rank(cid, rank, world, engine.device)
+            if not self._comm:
+                raise capi.WsrError("wsr_comm_init_rank: " + lib().wsr_last_error().decode())
 
     # ---- load-time exchange of collection statistics ---------------------------------------
     def exchange_stats(self):
@@ -110,12 +136,7 @@ class ShardedSearch:
         total, bases, avg = combine_partition_stats(n_docs, avgs)
         df_local, ranks = self.engine.local_stats(want_ranks=(self.term_keys == "synthetic_rank"))
         if self.term_keys == "synthetic_rank":
-            vmax = torch.tensor([int(ranks.max()) + 1 if len(ranks) else 1], dtype=torch.int64, device=dev)
-            dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
-            dense = torch.zeros(int(vmax.item()), dtype=torch.int64, device=dev)
-            dense[torch.from_numpy(ranks.astype(np.int64)).to(dev)] = torch.from_numpy(df_local.astype(np.int64)).to(dev)
-            dist.all_reduce(dense)
-            df_global = dense[torch.from_numpy(ranks.astype(np.int64)).to(dev)].cpu().numpy().astype(np.uint32)
+            df_global = _exchange_df([df_local], [ranks], dev)[0]
         else:
             # generic vocabularies: exchange (term, df) pairs (fine for test-sized corpora)
             terms = [self.engine.term_at(i)[0] for i in range(len(df_local))]
@@ -130,61 +151,135 @@ class ShardedSearch:
         self.engine.set_global_stats(bases[self.rank], total, avg, df_global)
         return total, bases[self.rank], avg
 
-    # ---- per-batch: exchange of the shard top-k + merge kernel -----------------------------
-    def _buffers(self, n, k):
-        key = (n, k)
-        if key not in self._bufs:
-            d = self.device
-            s, _ = slice_bounds(n, self.world)
-            self._bufs = {key: dict(
-                g_hits=torch.empty((self.world, n * k * 16), dtype=torch.uint8, device=d),
-                g_n=torch.empty((self.world, n), dtype=torch.int32, device=d),
-                # scatter exchange: merged slice (padded to s queries) and the gathered slices;
-                # slice r starts at query r*s, so the first n queries of full_* are the result
-                m_hits=torch.zeros(max(1, s) * k * 16, dtype=torch.uint8, device=d),
-                m_n=torch.zeros(max(1, s), dtype=torch.int32, device=d),
-                full_hits=torch.empty(self.world * max(1, s) * k * 16, dtype=torch.uint8, device=d),
-                full_n=torch.empty(self.world * max(1, s), dtype=torch.int32, device=d),
-                out_hits=torch.empty(n * k * 16, dtype=torch.uint8, device=d),
-                out_n=torch.empty(n, dtype=torch.int32, device=d))}
-        return self._bufs[key]
-
+    # ---- per-batch: exchange of the shard top-k + merge kernel, in the library -------------
     def gather_merge(self, batch):
         """Enqueued on the batch's stream, right behind its search kernels."""
-        n, k = batch.n, batch.k_stride
-        b = self._buffers(n, k)
-        d_hits, d_n, stream_ptr = batch.device_results()
-        stream = torch.cuda.ExternalStream(stream_ptr, device=self.device)
-        mine_h = device_bytes(d_hits, n * k * 16, self.device)
-        mine_n = device_bytes(d_n, n * 4, self.device).view(torch.int32)
-        if self.exchange == "allgather":
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(b["g_hits"].view(-1), mine_h)
-                dist.all_gather_into_tensor(b["g_n"].view(-1), mine_n)
-            check(lib().wsr_merge_topk_device(b["g_hits"].data_ptr(), b["g_n"].data_ptr(), self.world, n, k,
-                                              b["out_hits"].data_ptr(), b["out_n"].data_ptr(),
-                                              C.c_void_p(stream_ptr)))
-            b["res_hits"], b["res_n"] = b["out_hits"], b["out_n"]
-            return b["res_hits"], b["res_n"]
-        with torch.cuda.stream(stream):
-            mine = exchange_slices(mine_h, mine_n, n, k, self.rank, self.world,
-                                   b["g_hits"].view(-1), b["g_n"].view(-1))
-        check(lib().wsr_merge_topk_device(b["g_hits"].data_ptr(), b["g_n"].data_ptr(), self.world, mine, k,
-                                          b["m_hits"].data_ptr(), b["m_n"].data_ptr(),
-                                          C.c_void_p(stream_ptr)))
-        with torch.cuda.stream(stream):
-            dist.all_gather_into_tensor(b["full_hits"], b["m_hits"])
-            dist.all_gather_into_tensor(b["full_n"], b["m_n"])
-        b["res_hits"], b["res_n"] = b["full_hits"][:n * k * 16], b["full_n"][:n]
-        return b["res_hits"], b["res_n"]
+        check(lib().wsr_batch_exchange(batch._b, self._comm, 0 if self.exchange == "scatter" else 1))
 
     def fetch_merged(self, batch, hits_host=None, n_host=None):
-        """D2H of the merged result of the last gather_merge (synchronises the batch stream)."""
+        """D2H of the merged result of the last gather_merge (synchronises the batch stream).
+        hits_host / n_host: optional pinned numpy arrays (capi.PinnedArray.array)."""
         n, k = batch.n, batch.k_stride
-        b = self._buffers(n, k)
-        stream = torch.cuda.ExternalStream(batch.device_results()[2], device=self.device)
-        with torch.cuda.stream(stream):
-            h = b["res_hits"].cpu() if hits_host is None else hits_host.copy_(b["res_hits"], non_blocking=True)
-            c = b["res_n"].cpu() if n_host is None else n_host.copy_(b["res_n"], non_blocking=True)
-        stream.synchronize()
-        return h.numpy().view(HIT_DTYPE).reshape(n, k), c.numpy()
+        h = hits_host if hits_host is not None else np.zeros((n, k), HIT_DTYPE)
+        c = n_host if n_host is not None else np.zeros(n, np.int32)
+        check(lib().wsr_batch_fetch_exchanged(batch._b, self._comm, h.ctypes.data, c.ctypes.data))
+        return h.reshape(-1)[:n * k].reshape(n, k), c[:n]
+
+    def close(self):
+        if self._comm:
+            lib().wsr_comm_destroy(self._comm)
+            self._comm = None
+
+
+class ShardGroup:
+    """Binding of wsr_group (include/wsr.h): the partitions this process holds — one or more
+    partition directories on one or more of its GPUs — as one engine. Single process: the library
+    does everything (statistics exchange between partitions, NCCL between devices). One process
+    per GPU (rank / world given): the communicator id and the collection statistics travel through
+    torch.distributed once at load; every batch is search kernels + on-device merge of the local
+    partitions + NCCL exchange called from C."""
+
+    def __init__(self, dirs, devices, rank=None, world=None, positions=False, loader_threads=0):
+        self.dirs, self.devices = list(dirs), list(devices)
+        self.rank, self.world = rank, world
+        multi = world is not None and world > 1
+        arr = (C.c_char_p * len(self.dirs))(*[d.encode() for d in self.dirs])
+        devs = (C.c_int * len(self.devices))(*self.devices)
+        gd = None
+        if multi:
+            gd = capi.GroupDist()
+            gd.rank, gd.world = rank, world
+            gd.comm_id = _new_comm_id(rank)
+        err = C.create_string_buffer(512)
+        self._g = lib().wsr_group_open(arr, len(self.dirs), devs, len(self.devices), loader_threads,
+                                       capi.WSR_OPEN_POSITIONS if positions else 0,
+                                       C.byref(gd) if gd is not None else None, err, 512)
+        if not self._g:
+            raise capi.WsrError("wsr_group_open: " + err.value.decode())
+        self.n = self.k = 0
+        if multi:
+            self._exchange_stats()
+
+    def part(self, i):
+        """Partition i as an engine object over the group's own index (borrowed: closing it is a no-op)."""
+        from .engine import GpuVacuumEngine
+        e = GpuVacuumEngine(self.dirs[i], device=self.devices[i // max(1, len(self.dirs) // len(self.devices))])
+        e._h = lib().wsr_group_part(self._g, i)
+        e._borrowed = True
+        return e
+
+    def _exchange_stats(self):
+        dev = torch.device("cuda", self.devices[0])
+        parts = [self.part(i) for i in range(len(self.dirs))]
+        infos = [p.info() for p in parts]
+        mine = torch.tensor([[float(i.n_docs), float(i.avg_doc_len)] for i in infos], dtype=torch.float64, device=dev)
+        allv = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(allv, mine)
+        n_docs = [int(v[p, 0].item()) for v in allv for p in range(len(parts))]
+        avgs = [float(v[p, 1].item()) for v in allv for p in range(len(parts))]
+        total, bases, avg = combine_partition_stats(n_docs, avgs)
+        stats = [p.local_stats(want_ranks=True) for p in parts]
+        dfg = _exchange_df([s[0] for s in stats], [s[1] for s in stats], dev)
+        for i, p in enumerate(parts):
+            p.set_global_stats(bases[self.rank * len(parts) + i], total, avg, dfg[i])
+        self.n_docs_global, self.avg_len_global = total, avg
+
+    def load_log(self, text, k):
+        ptr, length = _text_ptr(text)
+        n = C.c_int(0)
+        check(lib().wsr_group_load_log(self._g, ptr, length, k, C.byref(n)))
+        self.n, self.k = n.value, k
+        return n.value
+
+    def run(self, mode="scatter"):
+        check(lib().wsr_group_run(self._g, 0 if mode == "scatter" else 1))
+
+    def sync(self):
+        check(lib().wsr_group_sync(self._g))
+
+    def stream(self):
+        s = C.c_void_p(0)
+        check(lib().wsr_group_stream(self._g, C.byref(s)))
+        return s.value
+
+    def fetch(self, hits=None, n_hits=None):
+        h = hits if hits is not None else np.zeros((self.n, self.k), HIT_DTYPE)
+        c = n_hits if n_hits is not None else np.zeros(self.n, np.int32)
+        check(lib().wsr_group_fetch(self._g, h.ctypes.data, c.ctypes.data))
+        return h.reshape(-1)[:self.n * self.k].reshape(self.n, self.k), c[:self.n]
+
+    def search_log(self, text, k, hits=None, n_hits=None, doc_freqs=None, n_doc_freqs=None, fetch=True):
+        """wsr_group_search_log. fetch=False: a rank that does not face the client."""
+        ptr, length = _text_ptr(text)
+        n = C.c_int(0)
+        if not fetch:
+            check(lib().wsr_group_search_log(self._g, ptr, length, k, None, None, None, None, 0, C.byref(n)))
+            return n.value
+        cap = len(n_hits)
+        check(lib().wsr_group_search_log(self._g, ptr, length, k, hits.ctypes.data, n_hits.ctypes.data,
+                                         doc_freqs.ctypes.data if doc_freqs is not None else None,
+                                         n_doc_freqs.ctypes.data if n_doc_freqs is not None else None,
+                                         cap, C.byref(n)))
+        return n.value
+
+    def stats(self):
+        a, b, c, d = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0), C.c_int64(0)
+        check(lib().wsr_group_stats(self._g, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"listed_postings": a.value, "n_postings": b.value, "hbm_bytes": c.value, "n_docs": d.value}
+
+    def close(self):
+        if self._g:
+            lib().wsr_group_close(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _text_ptr(text):
+    if isinstance(text, np.ndarray):
+        return C.c_void_p(text.ctypes.data), int(text.size)
+    return C.cast(C.c_char_p(text), C.c_void_p), len(text)

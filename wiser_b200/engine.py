@@ -187,7 +187,7 @@ class GpuVacuumEngine:
                                      ndfs.ctypes.data if want_doc_freqs else None))
         return hits, n_hits, dfs, ndfs
 
-    def search_log(self, text: bytes, k: int, hits=None, n_hits=None):
+    def search_log(self, text: bytes, k: int, hits=None, n_hits=None, doc_freqs=None, n_doc_freqs=None):
         """wsr_search_log: whole query-log text -> (hits[n,k], n_hits[n]); parse, GPU and copies
         pipelined inside the library."""
         if isinstance(text, np.ndarray):       # e.g. a pinned uint8 buffer holding the log
@@ -201,8 +201,13 @@ class GpuVacuumEngine:
         if n_hits is None:
             n_hits = np.zeros(cap, np.int32)
         n = C.c_int(0)
-        check(lib().wsr_search_log(self._h, ptr, length, k, hits.ctypes.data, n_hits.ctypes.data,
-                                   min(cap, len(n_hits)), C.byref(n)))
+        if doc_freqs is not None:
+            check(lib().wsr_search_log_ex(self._h, ptr, length, k, hits.ctypes.data, n_hits.ctypes.data,
+                                          doc_freqs.ctypes.data, n_doc_freqs.ctypes.data,
+                                          min(cap, len(n_hits)), C.byref(n)))
+        else:
+            check(lib().wsr_search_log(self._h, ptr, length, k, hits.ctypes.data, n_hits.ctypes.data,
+                                       min(cap, len(n_hits)), C.byref(n)))
         return hits[:n.value], n_hits[:n.value]
 
     def SearchBatch(self, queries: Sequence[SearchQuery]) -> List[SearchResult]:
@@ -268,9 +273,9 @@ class GpuVacuumEngine:
         return buf.raw[:n].decode(), df.value
 
     def close(self):
-        if self._h:
+        if self._h and not getattr(self, "_borrowed", False):   # a group's partitions belong to the group
             lib().wsr_index_close(self._h)
-            self._h = None
+        self._h = None
 
     def __del__(self):
         try:
