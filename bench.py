@@ -417,17 +417,25 @@ def secondary_workloads(a, eng, corpus_dir, peak, peak_src, log_fn):
     from wiser_b200 import Batch, GpuVacuumEngine
     from wiser_b200.capi import HIT_DTYPE, PinnedArray
     out = {}
+    # phrase2_plain: the phrase2 log with the quotes stripped, on the same index — what the position
+    # verification adds on top of the plain AND of the same terms
     specs = [("single_high", a.queries), ("multi_term", a.queries), ("two_term_hh", a.queries // 4),
-             ("phrase2", a.queries // 5)]
+             ("phrase2", a.queries // 5), ("phrase2_plain", a.queries // 5)]
+    pos_engine = None
     for wl, nq in specs:
         t_start = time.time()
-        a2 = argparse.Namespace(**{**vars(a), "workload": wl, "queries": nq, "query_filter": ""})
-        e2, cdir, own = eng, corpus_dir, False
+        a2 = argparse.Namespace(**{**vars(a), "workload": "phrase2" if wl == "phrase2_plain" else wl, "queries": nq,
+                                   "query_filter": ""})
+        e2, cdir = eng, corpus_dir
         try:
             if wl.startswith("phrase"):
                 cdir, _ = ensure_corpus(a2, 0, 1)
-                e2, own = GpuVacuumEngine(cdir, device=eng.device, positions=True).Load(), True
+                if pos_engine is None:
+                    pos_engine = GpuVacuumEngine(cdir, device=eng.device, positions=True).Load()
+                e2 = pos_engine
             text = open(ensure_query_log(a2, cdir), "rb").read()
+            if wl == "phrase2_plain":
+                text = text.replace(b'"', b"")
             qarr = e2.parse_query_log(text, a.k)
             n = len(qarr)
             b = Batch(e2, qarr, a.k)
@@ -460,10 +468,9 @@ def secondary_workloads(a, eng, corpus_dir, peak, peak_src, log_fn):
             del hits_p, nh_p, text_p
         except Exception as e:  # a secondary line must never take the headline down
             out[wl] = {"error": str(e)[:300]}
-        finally:
-            if own:
-                e2.close()
         log_fn(f"secondary workload {wl}: {out[wl]} ({time.time() - t_start:.1f}s)")
+    if pos_engine is not None:
+        pos_engine.close()
     return out
 
 
@@ -689,61 +696,34 @@ def ours_group(a, rank, world, local_rank):
 
 # ---------------------------------------------------------------------------------------------
 def ours(a, rank, world, local_rank):
+    """N = 1, BASELINE.json configs[1]: one index on one GPU."""
     import numpy as np
     import torch
     from wiser_b200 import Batch, GpuVacuumEngine
-    from wiser_b200.capi import HIT_DTYPE, PinnedArray
+    from wiser_b200.capi import HIT_DTYPE, WSR_MAX_TERMS, PinnedArray
 
-    # NCCL prints its version banner on fd 1; keep stdout for the ONE JSON line
-    real_stdout = os.dup(1)
+    real_stdout = os.dup(1)     # keep stdout for the ONE JSON line
     os.dup2(2, 1)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-
-    corpus_dir, cinfo = ensure_corpus(a, rank, world)
-    # every rank replays the SAME log (rank 0's), as every query goes to every shard
-    if world > 1:
-        objs = [None]
-        if rank == 0:
-            objs = [open(ensure_query_log(a, corpus_dir), "rb").read()]
-        dist.broadcast_object_list(objs, src=0)
-        text = objs[0]
-        qlog = None
-    else:
-        qlog = ensure_query_log(a, corpus_dir)
-        text = open(qlog, "rb").read()
+    corpus_dir, cinfo = ensure_corpus(a, 0, 1)
+    qlog = ensure_query_log(a, corpus_dir)
+    text = open(qlog, "rb").read()
 
     t0 = time.time()
     eng = GpuVacuumEngine(corpus_dir, device=local_rank, positions=a.workload.startswith("phrase")).Load()
     load_s = time.time() - t0
     info = eng.info()
-    shard = None
-    if world > 1:
-        from wiser_b200.dist import ShardedSearch
-        shard = ShardedSearch(eng, rank, world)
     qarr = eng.parse_query_log(text, a.k)
     n = len(qarr)
     batch = Batch(eng, qarr, a.k)
-    log(f"rank {rank}: index loaded in {load_s:.1f}s, {info.n_postings} postings, "
-        f"{info.hbm_bytes / 1e9:.2f} GB HBM, {n} queries")
-
-    def step():
-        batch.run()
-        if shard is not None:
-            shard.gather_merge(batch)
+    log(f"index loaded in {load_s:.1f}s, {info.n_postings} postings, {info.hbm_bytes / 1e9:.2f} GB HBM, {n} queries")
 
     def sync_all():
         batch.sync()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
 
     for _ in range(a.warmup):
-        step()
+        batch.run()
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -753,174 +733,94 @@ def ours(a, rank, world, local_rank):
     t_wall = time.perf_counter()
     ev0.record(stream)
     for _ in range(a.steps):
-        step()
+        batch.run()
     ev1.record(stream)
     sync_all()
     wall_ms = (time.perf_counter() - t_wall) * 1000.0
-    dev_ms = ev0.elapsed_time(ev1)
+    ms_per_step = ev0.elapsed_time(ev1) / a.steps
     clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([dev_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
-    ms_per_step = dev_ms / a.steps
 
     prof, st = profile_batch(batch)
-    listed = int(st.listed_postings)
-    if world > 1:
-        t = torch.tensor([listed, int(st.touched_bytes), int(st.decoded_postings)], device="cuda", dtype=torch.int64)
-        dist.all_reduce(t)
-        listed_all = int(t[0].item())
-    else:
-        listed_all = listed
+    listed_all = int(st.listed_postings)
     value = listed_all / (ms_per_step / 1000.0)
 
-    # ---- roofline of the dominant kernel (this rank)
+    # ---- roofline of the dominant kernel
     peak, peak_src = measured_peak_gbs()
     dom, roofline = roofline_of(prof, st, peak, peak_src)
     traffic, traffic_src = committed_traffic(a.workload, a.docs, a.queries, KERNEL_NAMES[dom])
     roofline["traffic"], roofline["traffic_source"] = traffic, traffic_src
     roofline["source_hash"] = source_hash()
-    # K1 (block decode) on the whole index, timed alone: algorithmic bytes = every block's reference
-    # doc-id and tf packs + 16 B (listed_bytes of a log naming every list once)
+    # K1 (block decode) on the whole index, timed alone. Algorithmic bytes: every block's reference
+    # doc-id and tf packs + 16 B of metadata = listed_bytes of a log naming every list once, which
+    # the loader sums per list (wsr_index_info does not carry it; the payload figure is OUR bytes)
     try:
         eng.decode_all()
-        _, k1_ms = eng.decode_all()
-        roofline["k1_decode_all"] = {"ms": k1_ms, "postings_per_s": info.n_postings / (k1_ms / 1000.0),
-                                     "payload_gbs": info.payload_bytes / (k1_ms / 1000.0) / 1e9}
+        k1 = min(eng.decode_all()[1] for _ in range(3))
+        roofline["k1_decode_all"] = {"ms": k1, "postings_per_s": info.n_postings / (k1 / 1000.0),
+                                     "payload_gbs": info.payload_bytes / (k1 / 1000.0) / 1e9,
+                                     "payload_frac_of_peak": info.payload_bytes / (k1 / 1000.0) / 1e9 / peak}
     except Exception:
         roofline["k1_decode_all"] = None
 
-    # ---- e2e through the host-buffer C ABI (term lookup + H2D + kernels + D2H every step)
+    # ---- e2e through the host-buffer C ABI: pinned log text in, pinned top-k AND doc_freqs out
+    # (the reference's SearchResult carries both), every step
     e2e_steps = max(1, min(a.steps, 20))
-    t_parse = t_search = 0.0
-    if world == 1:
-        hits_p = PinnedArray((n + 2, a.k), HIT_DTYPE)
-        nh_p = PinnedArray((n + 2,), np.int32)
-        text_p = PinnedArray((len(text),), np.uint8)      # the step's input: the log text, pinned
-        text_p.array[:] = np.frombuffer(text, np.uint8)
+    hits_p = PinnedArray((n + 2, a.k), HIT_DTYPE)
+    nh_p = PinnedArray((n + 2,), np.int32)
+    df_p = PinnedArray((n + 2, WSR_MAX_TERMS), np.uint32)
+    ndf_p = PinnedArray((n + 2,), np.int32)
+    text_p = PinnedArray((len(text),), np.uint8)      # the step's input: the log text, pinned
+    text_p.array[:] = np.frombuffer(text, np.uint8)
 
-        def e2e_step():
-            nonlocal t_parse, t_search
-            t0 = time.perf_counter()
-            h, c = eng.search_log(text_p.array, a.k, hits_p.array, nh_p.array)
-            assert len(c) == n
-            t_search += time.perf_counter() - t0
-    else:
-        batch2 = Batch(eng, qarr, a.k)
-        hits_t = torch.empty(n * a.k * 16, dtype=torch.uint8).pin_memory()
-        nh_t = torch.empty(n, dtype=torch.int32).pin_memory()
-        text_p = PinnedArray((len(text),), np.uint8)
-        text_p.array[:] = np.frombuffer(text, np.uint8)
-
-        def e2e_step():
-            nonlocal t_parse, t_search
-            t0 = time.perf_counter()
-            assert batch2.reset_log(text_p.array, a.k) == n
-            t1 = time.perf_counter()
-            batch2.run()
-            shard.gather_merge(batch2)
-            if rank == 0:        # the client-facing rank reads the merged top-k back to the host;
-                shard.fetch_merged(batch2, hits_t, nh_t)
-            else:                # the others hold it in HBM and only finish their stream
-                batch2.sync()
-            t_parse += t1 - t0
-            t_search += time.perf_counter() - t1
+    def e2e_step():
+        h, c = eng.search_log(text_p.array, a.k, hits_p.array, nh_p.array, df_p.array, ndf_p.array)
+        assert len(c) == n
     for _ in range(3):
         e2e_step()
-    if world > 1:
-        dist.barrier()
-    t_parse = t_search = 0.0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    merged_hits = merged_n = None
-    if world > 1:
-        # cross-check of the exchange (outside every timed region): the scatter exchange used in
-        # the timed steps must give, on every rank, what a plain all-gather + full merge gives
-        batch.run()
-        shard.gather_merge(batch)
-        h_sc, n_sc = shard.fetch_merged(batch)
-        h_sc, n_sc = h_sc.copy(), n_sc.copy()
-        used = shard.exchange
-        shard.exchange = "allgather"
-        batch.run()
-        shard.gather_merge(batch)
-        h_ag, n_ag = shard.fetch_merged(batch)
-        shard.exchange = used
-        assert np.array_equal(n_sc, n_ag), "scatter and all-gather exchanges disagree on hit counts"
-        m = np.arange(a.k)[None, :] < n_ag[:, None]
-        assert np.array_equal(h_sc["doc_id"][m], h_ag["doc_id"][m])
-        assert np.array_equal(h_sc["score"][m].view(np.uint64), h_ag["score"][m].view(np.uint64))
-        merged_hits, merged_n = h_sc, n_sc
-        # ... and the e2e path (device front end; read back on rank 0) the same
-        if rank == 0:
-            he = hits_t.numpy().view(HIT_DTYPE).reshape(n, a.k)
-            assert np.array_equal(nh_t.numpy(), n_ag)
-            assert np.array_equal(he["doc_id"][m], h_ag["doc_id"][m])
-    if world == 1:
-        # the e2e path (device front end) must return exactly what the device-timed batch did
-        hb, nb = batch.fetch()
-        assert np.array_equal(nb, nh_p.array[:n]), "e2e path and timed batch disagree on hit counts"
-        m = np.arange(a.k)[None, :] < nb[:, None]
-        assert np.array_equal(hb["doc_id"][m], hits_p.array[:n]["doc_id"][m])
-        assert np.array_equal(hb["score"][m].view(np.uint64), hits_p.array[:n]["score"][m].view(np.uint64))
+    # the e2e path (device front end) must return exactly what the device-timed batch did
+    hb, nb = batch.fetch()
+    assert np.array_equal(nb, nh_p.array[:n]), "e2e path and timed batch disagree on hit counts"
+    m = np.arange(a.k)[None, :] < nb[:, None]
+    assert np.array_equal(hb["doc_id"][m], hits_p.array[:n]["doc_id"][m])
+    assert np.array_equal(hb["score"][m].view(np.uint64), hits_p.array[:n]["score"][m].view(np.uint64))
     # bytes the library copied back per step: hit counts + either the packed hits (logs whose
-    # results fill under 10 % of n*k: wsr_search_log packs them on the GPU) or the full [n, k] array
+    # results fill under 10 % of n*k: wsr_search_log packs them on the GPU) or the full [n, k]
+    # array, + doc_freqs rows and counts
     d2h_bytes = int(n * a.k * 16 + n * 4)
-    if world == 1:
-        total_hits = int(nh_p.array[:n].sum())
-        if total_hits * 10 < n * a.k:
-            d2h_bytes = int(n * 4 + 4 + total_hits * 16)
+    total_hits = int(nh_p.array[:n].sum())
+    if total_hits * 10 < n * a.k:
+        d2h_bytes = int(n * 4 + 4 + total_hits * 16)
+    d2h_bytes += int(n * WSR_MAX_TERMS * 4 + n * 4)
     e2e = {"value": listed_all / e2e_s, "unit": UNIT,
            "h2d_bytes_per_step": int(len(text)),
            "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1000.0, "steps": e2e_steps,
            "queries_per_s": n / e2e_s,
-           "parse_lookup_ms": 1000.0 * t_parse / e2e_steps, "search_ms": 1000.0 * t_search / e2e_steps,
-           "path": ("wsr_search_log: pinned query-log text -> H2D -> parse + term lookup + planning kernels "
-                    "(frontend.cu) -> search kernels -> D2H into pinned host result buffers" if world == 1 else
-                    "pinned query-log text -> wsr_batch_reset_log (H2D + parse/lookup/plan kernels) -> search "
-                    "kernels -> NCCL all-to-all + merge kernel + all-gather -> D2H of the merged top-k on rank 0")}
+           "path": ("wsr_search_log_ex: pinned query-log text -> H2D -> parse + term lookup + planning kernels "
+                    "(frontend.cu) -> search kernels -> D2H of top-k and doc_freqs into pinned host buffers")}
 
-    # ---- parity spot check against the CPU oracle (outside every timed region). N = 1: the oracle
-    # on the same directory. N > 1: rank 0 checks the MERGED result against one oracle per partition
-    # in partition mode (collection statistics), merged on the host.
+    # ---- parity spot check against the CPU oracle on the same directory (outside timed regions)
     parity = None
-    if a.parity_sample > 0 and rank == 0:
-        from oracle_py import OracleIndex, parse_query_line, partitioned_search
+    if a.parity_sample > 0:
+        from oracle_py import OracleIndex, parse_query_line
         from parity import check_topk
         lines = text.decode().split("\n")
         idxs = list(range(0, n, max(1, n // a.parity_sample)))[:a.parity_sample]
-        if world == 1:
-            ora = OracleIndex(corpus_dir)
-            hits, nh = batch.fetch()
-            for i in idxs:
-                terms, is_phrase = parse_query_line(lines[i])
-                rd, rs, _ = ora.search(terms, a.k, is_phrase=is_phrase)
-                fd, fs, _ = ora.search(terms, 1 << 30, is_phrase=is_phrase)
-                check_topk(rd, rs, hits["doc_id"][i, :nh[i]], hits["score"][i, :nh[i]], fd, fs, what=lines[i])
-            parity = {"queries_checked": len(idxs), "against": "CPU oracle (bit-exact scores, tie-aware docs)"}
-        else:
-            sample_terms = sorted({t for i in idxs for t in parse_query_line(lines[i])[0]})
-            oras, bases = partition_oracles(a, world, sample_terms)
-            for i in idxs:
-                terms, is_phrase = parse_query_line(lines[i])
-                fd, fs, _ = partitioned_search(oras, bases, terms, 1 << 30, is_phrase)
-                check_topk(fd[:a.k], fs[:a.k], merged_hits["doc_id"][i, :merged_n[i]],
-                           merged_hits["score"][i, :merged_n[i]], fd, fs, what=lines[i])
-            parity = {"queries_checked": len(idxs),
-                      "against": f"{world} CPU oracles, one per partition directory, in partition mode (collection "
-                                 f"N / average length / df), merged on the host; bit-exact scores, tie-aware docs"}
-            for o in oras:
-                o.close()
+        ora = OracleIndex(corpus_dir)
+        for i in idxs:
+            terms, is_phrase = parse_query_line(lines[i])
+            rd, rs, rdf = ora.search(terms, a.k, is_phrase=is_phrase)
+            fd, fs, _ = ora.search(terms, 1 << 30, is_phrase=is_phrase)
+            check_topk(rd, rs, hb["doc_id"][i, :nb[i]], hb["score"][i, :nb[i]], fd, fs, what=lines[i])
+            assert list(df_p.array[i, :ndf_p.array[i]]) == rdf, f"doc_freqs of {lines[i]!r}"
+        parity = {"queries_checked": len(idxs),
+                  "against": "CPU oracle (bit-exact scores, tie-aware docs, doc_freqs)"}
 
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline and world == 1:
+    if not a.no_cpu_baseline:
         try:
             kind, threads, r = cpu_baseline(a, corpus_dir, qlog, 3)
             cpu = {"value": r["listed_postings_per_s"], "unit": UNIT, "cores": threads, "kind": kind,
@@ -928,11 +828,11 @@ def ours(a, rank, world, local_rank):
                    "sample": f"first {r['queries']} queries of the same log, {threads} threads on one shared "
                              f"engine, same index directory (page-cache resident), k={a.k}"}
             # T = 1 (SURVEY 8d asks for both): a fifth of the sample on one thread
-            one = argparse.Namespace(**{**vars(a), "cpu_sample": max(500, a.cpu_sample // 5)})
+            one = max(500, a.cpu_sample // 5)
             if kind == "reference":
-                r1 = run_reference_tool(corpus_dir, qlog, a.k, 1, 1, one.cpu_sample)
+                r1 = run_reference_tool(corpus_dir, qlog, a.k, 1, 1, one)
             else:
-                r1 = run_oracle_port(corpus_dir, qlog, a.k, 1, 1, one.cpu_sample)
+                r1 = run_oracle_port(corpus_dir, qlog, a.k, 1, 1, one)
             cpu["single_thread"] = {"value": r1["listed_postings_per_s"], "unit": UNIT, "cores": 1,
                                     "queries_per_s": r1["qps"], "seconds": r1["seconds"],
                                     "sample": f"first {r1['queries']} queries of the same log, 1 thread"}
@@ -940,37 +840,28 @@ def ours(a, rank, world, local_rank):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
 
     workloads = None
-    if rank == 0 and world == 1 and not a.no_secondary:
+    if not a.no_secondary:
         workloads = secondary_workloads(a, eng, corpus_dir, peak, peak_src, log)
 
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64 scores / u32 doc ids", "data": "synthetic",
-            "config": workload_config(a, cinfo, n_gpus=world),
-            "queries_per_s": n / (ms_per_step / 1000.0),
-            "wall_ms_per_step": wall_ms / a.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(st.kernel_launches) * a.steps + (a.steps if world > 1 else 0),
-            "parity": parity, "workloads": workloads,
-            "index": {"load_s": load_s, "hbm_bytes": int(info.hbm_bytes), "payload_bytes": int(info.payload_bytes),
-                      "blocks": int(info.n_blocks), "corpus_build_s": cinfo.get("wall_s")},
-            "matches_per_step": int(st.matches), "work_units_per_step": int(st.work_units),
-        }
-        os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    # orderly teardown, then a normal return: torch buffers that lived on the batch streams go
-    # first, then the batches (their streams), then the index, then the process group
-    if shard is not None:
-        shard._bufs.clear()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 scores / u32 doc ids", "data": "synthetic",
+        "config": workload_config(a, cinfo, n_gpus=1),
+        "queries_per_s": n / (ms_per_step / 1000.0),
+        "wall_ms_per_step": wall_ms / a.steps,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+        "gpu_launches": int(st.kernel_launches) * a.steps,
+        "parity": parity, "workloads": workloads,
+        "index": {"load_s": load_s, "hbm_bytes": int(info.hbm_bytes), "payload_bytes": int(info.payload_bytes),
+                  "blocks": int(info.n_blocks), "corpus_build_s": cinfo.get("wall_s")},
+        "matches_per_step": int(st.matches), "work_units_per_step": int(st.work_units),
+    }
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    # orderly teardown, then a normal return
     torch.cuda.synchronize()
-    if world > 1:
-        batch2.close()
     batch.close()
     eng.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     os.dup2(real_stdout, 1)
     os.close(real_stdout)
     sys.stdout.flush()

@@ -137,20 +137,21 @@ struct Chunk {               // output of one slice of terms
   std::vector<uint8_t> payload;
   std::vector<uint32_t> positions;   // optional position column, absolute in-document positions
   std::vector<uint32_t> blk_pos;     // per block: index of its first position
-  std::vector<uint16_t> rec_pos;     // per block 32 entries: positions before record r
+  std::vector<uint16_t> grp_pos;     // per block 8 entries: positions before record 4g
   bool no_positions = false;         // some list of the chunk has no position column
   int64_t postings = 0, postings_global = 0;
   std::string err;
 };
 
 struct Builder {
-  uint32_t filter_ppw = 2;   // postings per 32-bit filter word (WSR_FILTER_PPW overrides, 1..8)
+  uint32_t filter_ppw = kFilterPostingsPerWord;   // per 32-bit filter word (WSR_FILTER_PPW overrides, 1..8)
   bool want_positions = false;
   const FileView &vac;
   const std::vector<uint64_t> &list_offs;
   const HostIndex &ix;      // norms / cache already filled
   const float *tfn_tab;     // [64][256] exact-rounded-up tfn for tf < 64
   uint32_t doc_lo, doc_hi;
+  uint32_t filter_min_df = kFilterMinDf;   // shorter lists get no filter (WSR_FILTER_MIN_DF overrides)
 
   float TfnUpper(uint32_t tf, uint8_t norm) const {
     if (tf < 64) return tfn_tab[tf * 256 + norm];
@@ -268,7 +269,7 @@ struct Builder {
       sh.b = std::max(1, BitWidth(dmax));
       sh.n = n;
       const int rec_bits = sh.w0 + 3 * sh.b;
-      sh.rcode = rec_bits <= 32 ? 0 : rec_bits <= 64 ? 1 : 2;
+      sh.rcode = rec_bits <= 32 ? 0 : rec_bits <= 64 ? 1 : rec_bits <= 96 ? 3 : 2;
       sh.tcode = tmax < 16 ? 0 : tmax < 256 ? 1 : 2;
       sh.ref_dbits = std::max(1, BitWidth(refmax));
       sh.ref_tbits = std::max(1, BitWidth(tmax));
@@ -286,21 +287,21 @@ struct Builder {
         c->blk_heads.push_back(sh.w0 <= 16 && 4 * t < nl ? (uint16_t)first[4 * t] : (uint16_t)0xFFFF);
       if (want_positions && !keep_pos) {
         c->blk_pos.push_back(0u);
-        c->rec_pos.insert(c->rec_pos.end(), 32, (uint16_t)0);
+        c->grp_pos.insert(c->grp_pos.end(), 8, (uint16_t)0);
       }
       if (keep_pos) {
         if (c->positions.size() > 0xFFFFFFF0ull) { c->err = "more than 2^32 positions"; return false; }
         c->blk_pos.push_back((uint32_t)c->positions.size());
         uint64_t cnt = 0;
-        uint16_t rp[32];
+        uint16_t gp[8];
         for (int i = 0; i < 4 * 32; i++) {
-          if ((i & 3) == 0) rp[i >> 2] = (uint16_t)std::min<uint64_t>(cnt, 0xFFFF);
+          if ((i & 15) == 0) gp[i >> 4] = (uint16_t)std::min<uint64_t>(cnt, 0xFFFF);
           if (i < n) cnt += (*tfs)[s + i];
         }
         // a block with 65535+ positions keeps the sentinel everywhere: the kernel then sums tfs
         if (cnt >= 0xFFFF)
-          for (int r = 1; r < 32; r++) rp[r] = 0xFFFF;
-        c->rec_pos.insert(c->rec_pos.end(), rp, rp + 32);
+          for (int g = 1; g < 8; g++) gp[g] = 0xFFFF;
+        c->grp_pos.insert(c->grp_pos.end(), gp, gp + 8);
         c->positions.insert(c->positions.end(), pos_vals.begin() + pos_at, pos_vals.begin() + pos_at + cnt);
         pos_at += cnt;
       }
@@ -309,7 +310,7 @@ struct Builder {
     }
     // doc-range-partitioned Bloom filter of this (shard-local) list
     uint64_t flt = 0xFFFFFFFFull << 32;
-    if (b - a >= kFilterMinDf) {
+    if (b - a >= filter_min_df) {
       const uint64_t range = (uint64_t)doc_hi - doc_lo;
       uint32_t g = 0;
       while (g < 31 && (range >> (g + 1)) >= (uint64_t)(b - a) / filter_ppw + 1) g++;   // postings per word
@@ -351,7 +352,7 @@ void TermDict::Build(const std::vector<char> *arena, const std::vector<uint64_t>
   offs_ = offs;
   const size_t n = offs->size() - 1;
   size_t cap = 16;
-  while (cap < 2 * n) cap <<= 1;
+  while (2 * cap < 3 * n) cap <<= 1;   // load factor <= 2/3 (the device copy is 8 B per slot)
   mask_ = cap - 1;
   slots_.assign(cap, 0xFFFFFFFFu);
   for (size_t t = 0; t < n; t++) {
@@ -475,12 +476,16 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
       begin = end;
     }
   }
-  Builder builder{2, false, vac, list_offs, ix, tfn_tab.data(), (uint32_t)ix.doc_lo, (uint32_t)ix.doc_hi};
+  Builder builder{kFilterPostingsPerWord, false, vac, list_offs, ix, tfn_tab.data(), (uint32_t)ix.doc_lo, (uint32_t)ix.doc_hi};
   builder.want_positions = (flags & kLoadPositions) != 0;
   ix.has_positions = builder.want_positions;
   if (const char *e = getenv("WSR_FILTER_PPW")) {
     const int v = atoi(e);
     if (v >= 1 && v <= 8) builder.filter_ppw = (uint32_t)v;
+  }
+  if (const char *e = getenv("WSR_FILTER_MIN_DF")) {
+    const int v = atoi(e);
+    if (v >= 1) builder.filter_min_df = (uint32_t)v;
   }
   if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
   threads = (int)std::min<size_t>(threads, std::max<size_t>(1, chunks.size()));
@@ -524,7 +529,7 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
   if (ix.has_positions) {
     ix.positions.assign(tot_pos + 1, 0u);
     ix.blk_pos.assign(tot_blocks + 1, 0u);
-    ix.rec_pos.assign((tot_blocks + 1) * 32, (uint16_t)0);
+    ix.grp_pos.assign((tot_blocks + 1) * 8, (uint16_t)0);
   }
   std::vector<size_t> blk_base(chunks.size()), pay_base(chunks.size()), flt_base(chunks.size()),
       pos_base(chunks.size());
@@ -562,8 +567,8 @@ bool LoadVacuumDir(const std::string &dir, int shard, int n_shards, int threads,
       std::vector<uint32_t>().swap(c.filters);
       if (ix.has_positions) {
         for (size_t j = 0; j < c.blk_pos.size(); j++) ix.blk_pos[b0 + j] = c.blk_pos[j] + (uint32_t)pos_base[i];
-        if (!c.rec_pos.empty()) memcpy(ix.rec_pos.data() + b0 * 32, c.rec_pos.data(), c.rec_pos.size() * 2);
-        std::vector<uint16_t>().swap(c.rec_pos);
+        if (!c.grp_pos.empty()) memcpy(ix.grp_pos.data() + b0 * 8, c.grp_pos.data(), c.grp_pos.size() * 2);
+        std::vector<uint16_t>().swap(c.grp_pos);
         if (!c.positions.empty())
           memcpy(ix.positions.data() + pos_base[i], c.positions.data(), c.positions.size() * 4);
         std::vector<uint32_t>().swap(c.positions);

@@ -7,7 +7,7 @@
 // cross-lane prefix sum (ncu on the first, reference-layout kernel showed the path is bound
 // by instruction issue, not HBM: ~70 warp instructions per block went into unpack + scan).
 //   payload   u8[]      per block, 16 B aligned:
-//                         doc records  nl = ceil(n/4) records of R words (R in {1,2,4}); record l =
+//                         doc records  nl = ceil(n/4) records of R words (R in {1,2,3,4}); record l =
 //                                      [f : w0 bits][d1 : b][d2 : b][d3 : b] LSB first, where
 //                                      f  = doc[4l] - base_doc, d_i = doc[4l+i] - doc[4l+i-1];
 //                                      padded to 16 B
@@ -15,7 +15,9 @@
 //                                      padded to 16 B
 //                       slots past n in the last record repeat the last posting (delta 0, same tf)
 //   blk_info  uint4[]   {base_doc, payload_off/16, bits, max_tfn f32}; bits =
-//                       (w0-1) | (b-1)<<5 | (n-1)<<10 | rcode<<17 | tcode<<19 |
+//                       (w0-1) | (b-1)<<5 | (n-1)<<10 | rcode<<17 | tcode<<19 |   (rcode 0/1/2/3 =
+//                       records of 1/2/4/3 words; 96-bit records serve the sparse lists, whose
+//                       records need 65-90 bits)
 //                       (ref_dbits-1)<<21 | (ref_tbits-1)<<26
 //                       base_doc = doc id the block is relative to (the reference's skip-row
 //                       previous_doc_id, flash_containers.h:22-30; shard lower bound for a
@@ -32,21 +34,26 @@
 //                       to bound the k-th score before touching any payload
 //   lists     uint4[]   per term {first_block, n_blocks, df_shard, df_global}
 //   list_flt  uint2[]   per term {first filter word, shift g | 0xFFFFFFFF = no filter}
-//   filters   u32[]     per list a doc-range-partitioned Bloom filter, ~16 bits per posting
-//                       (false-positive rate ~0.5 %): doc d sets bits h1(d), h2(d), h3(d) of
-//                       word (d - doc_lo) >> g, g chosen for ~2 postings per word. An AND query
-//                       tests the driver's candidates against the other lists' filters first, so
-//                       the exact probe (block lookup + record search) runs only for the few
-//                       percent that may be present. No false negatives.
+//   filters   u32[]     per list (df >= kFilterMinDf) a doc-range-partitioned Bloom filter, ~8 bits
+//                       per posting (false-positive rate ~3 %): doc d sets the three bits of
+//                       FilterPattern(FilterIndex(d)) in word (d - doc_lo) >> g, g chosen for
+//                       ~kFilterPostingsPerWord postings per word. An AND query tests the driver's
+//                       candidates against the other lists' filters first, so the exact probe (block
+//                       lookup + record search) runs only for the few percent that may be present.
+//                       No false negatives.
 //   positions u32[]     (optional, phrase queries) token positions of every posting, absolute
 //                       inside the document, postings back to back in list order — the
 //                       reference's position column (delta-coded "cozy box" packs addressed
 //                       through the skip list, flash_iterators.h:558-661) with the deltas summed
 //   blk_pos   u32[]     index into positions[] of each block's first posting; a posting's run
 //                       starts at blk_pos + sum of the tfs before it in the block
-//   rec_pos   u16[32][] per block: number of positions before record r (postings 0..4r-1), so the
-//                       run of posting 4r+i starts at blk_pos + rec_pos[r] + the i tfs before it in
-//                       the record; all 0xFFFF (r >= 1) when the block holds >= 65535 positions
+//   grp_pos   u16[8][]  per block: number of positions before record 4g (postings 0..16g-1), so the
+//                       run of posting 4r+i starts at blk_pos + grp_pos[r/4] + the tfs of the up to
+//                       three records before r in its group + the i tfs before it in the record (the
+//                       tf records of a group are adjacent: 8 or 16 bytes); all 0xFFFF (g >= 1) when
+//                       the block holds >= 65535 positions
+//   positions are kept as u16 when every in-document position of the shard is < 65536 (always,
+//   unless a document has more than 65535 tokens), else as u32
 //   norms     u8[]      DocLengthCharStore bytes indexed by GLOBAL doc id
 //   cache     f64[256]  Bm25Similarity::cache_ (scoring.h:85-90)
 #ifndef WSR_HOST_INDEX_H
@@ -78,7 +85,7 @@ static_assert(sizeof(ListInfo) == 16, "ListInfo must be 16 bytes");
 struct BlockShape {      // decoded view of BlockInfo::bits
   int w0, b, n, rcode, tcode, ref_dbits, ref_tbits;
   int nl() const { return (n + 3) / 4; }
-  int rec_words() const { return 1 << rcode; }                   // 1, 2, 4
+  int rec_words() const { return rcode == 3 ? 3 : 1 << rcode; }  // rcode 0, 1, 2, 3 -> 1, 2, 4, 3 words
   int tf_bits() const { return tcode == 0 ? 4 : tcode == 1 ? 8 : 32; }
   uint32_t doc_bytes() const { return (uint32_t)((nl() * rec_words() * 4 + 15) / 16 * 16); }
   uint32_t tf_bytes() const { return (uint32_t)((nl() * tf_bits() / 2 + 15) / 16 * 16); }
@@ -126,7 +133,11 @@ __host__ __device__
 #endif
 inline uint32_t FilterIndex(uint32_t doc) { return (doc * 0x9E3779B1u) >> 22; }
 inline uint32_t FilterBits(uint32_t doc) { return FilterPattern(FilterIndex(doc)); }
-constexpr uint32_t kFilterMinDf = 256;   // shorter lists are probed directly
+// Lists shorter than this are probed directly (WSR_FILTER_MIN_DF overrides). With 4 postings per
+// filter word and this floor the filters of the C2 corpus take 0.9 GB instead of 2.0 GB (2 per word,
+// floor 256) for +1.5 % on the two-term step (profiles/r2_notes.md).
+constexpr uint32_t kFilterMinDf = 1024;
+constexpr uint32_t kFilterPostingsPerWord = 4;
 
 inline uint32_t AlgorithmicBytes(const BlockShape &s) {
   return RefStreamBytes(s.n, s.ref_dbits) + RefStreamBytes(s.n, s.ref_tbits) + 16;
@@ -173,7 +184,7 @@ struct HostIndex {
   bool has_positions = false;
   std::vector<uint32_t> positions;
   std::vector<uint32_t> blk_pos;
-  std::vector<uint16_t> rec_pos;    // 32 per block
+  std::vector<uint16_t> grp_pos;    // 8 per block
   std::vector<uint64_t> list_alg_bytes;  // algorithmic bytes of all blocks of each list
   int64_t n_postings = 0, n_postings_global = 0;
   int shard = 0, n_shards = 1;

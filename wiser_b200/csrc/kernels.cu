@@ -48,10 +48,12 @@ __device__ __forceinline__ uint32_t ShRcode(uint32_t b) { return (b >> 17) & 3u;
 __device__ __forceinline__ uint32_t ShTcode(uint32_t b) { return (b >> 19) & 3u; }
 __device__ __forceinline__ uint32_t ShRefD(uint32_t b) { return ((b >> 21) & 31u) + 1u; }
 __device__ __forceinline__ uint32_t ShRefT(uint32_t b) { return ((b >> 26) & 31u) + 1u; }
+// 32-bit words of a doc record: rcode 0, 1, 2, 3 -> 1, 2, 4, 3 (host_index.h BlockShape::rec_words)
+__device__ __forceinline__ uint32_t RecWords(uint32_t rc) { return rc == 3u ? 3u : 1u << rc; }
 // 16-byte granules of the doc-record stream of a block
 __device__ __forceinline__ uint32_t DocGranules(uint32_t bits) {
   const uint32_t nl = (ShN(bits) + 3u) >> 2;
-  return ((nl << ShRcode(bits)) + 3u) >> 2;
+  return (nl * RecWords(ShRcode(bits)) + 3u) >> 2;
 }
 // Algorithmic bytes of a block: the reference's pack sizes + 16 B metadata
 __device__ __forceinline__ uint32_t AlgBytes(uint32_t bits, bool with_tf) {
@@ -73,8 +75,11 @@ __device__ __forceinline__ uint4 LoadRecord(const DevIndexView &ix, const uint4 
   } else if (rc == 1) {
     const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src) + rec);
     r.x = v.x; r.y = v.y;
-  } else {
+  } else if (rc == 2) {
     r = __ldg(src + rec);
+  } else {   // 96-bit records: three words, 4-byte aligned
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(src) + 3u * rec;
+    r.x = __ldg(w); r.y = __ldg(w + 1); r.z = __ldg(w + 2);
   }
   return r;
 }
@@ -560,17 +565,18 @@ __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, u
     } else {
       // wide blocks (span >= 2^16 docs or 16-byte records): two levels of strided head loads
       const uint32_t *rp = reinterpret_cast<const uint32_t *>(ix.payload + info.y);
+      const uint32_t rw = RecWords(rcs);
       uint32_t grp = 0;
 #pragma unroll
       for (uint32_t t = 1; t < 8; t++) {
         const uint32_t mid = 4u * t;
-        if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) grp = t;   // heads ascend: last true wins
+        if (mid < nl && (__ldg(rp + mid * rw) & m0) <= rel) grp = t;   // heads ascend: last true wins
       }
       uint32_t add = 0;
 #pragma unroll
       for (uint32_t t = 1; t < 4; t++) {
         const uint32_t mid = 4u * grp + t;
-        if (mid < nl && (__ldg(rp + (mid << rcs)) & m0) <= rel) add = t;
+        if (mid < nl && (__ldg(rp + mid * rw) & m0) <= rel) add = t;
       }
       rec = 4u * grp + add;
       DecodeRecord(ix, info, rec, e);
@@ -599,9 +605,13 @@ __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, u
 // terms occur at consecutive positions, in query order. Only existence matters (the score
 // ignores the phrase frequency). Runs per intersection hit, one hit per lane.
 struct PosRun {
-  const uint32_t *p;   // the posting's positions, ascending
+  const void *p;       // the posting's positions, ascending (u16 or u32 entries: DevIndexView::pos16)
   uint32_t n;          // = tf
 };
+__device__ __forceinline__ uint32_t PosAt(const PosRun &r, uint32_t i, bool p16) {
+  return p16 ? (uint32_t)__ldg(reinterpret_cast<const unsigned short *>(r.p) + i)
+             : __ldg(reinterpret_cast<const uint32_t *>(r.p) + i);
+}
 // tf of posting `pos` and the start of its run in positions[]: the block's first position index
 // plus the tfs of the postings before it in the block.
 __device__ __forceinline__ void LoadTfs4(const uint4 *src, uint32_t tc, uint32_t r, uint32_t t[4]) {
@@ -620,30 +630,35 @@ __device__ __forceinline__ PosRun PositionsOf(const DevIndexView &ix, uint32_t p
   const uint32_t blk = pos >> 7, slot = pos & 127u, rec = slot >> 2;
   const uint4 info = __ldg(&ix.blk_info[blk]);
   const uint32_t first = __ldg(&ix.blk_pos[blk]);
-  uint32_t before = rec ? (uint32_t)__ldg(&ix.rec_pos[(size_t)blk * 32u + rec]) : 0u;
+  const uint32_t grp = rec >> 2;
+  uint32_t before = grp ? (uint32_t)__ldg(&ix.grp_pos[(size_t)blk * 8u + grp]) : 0u;
   const uint32_t bits = info.z, tc = ShTcode(bits);
   const uint4 *src = ix.payload + info.y + DocGranules(bits);
   uint32_t t[4];
-  if (before == 0xFFFFu) {   // block with >= 65535 positions: sum the tfs of the records before
+  uint32_t r0 = grp << 2;   // the tfs of the (at most three) records before `rec` in its group
+  if (before == 0xFFFFu) {   // block with >= 65535 positions: sum from the block's first record
     before = 0;
-    for (uint32_t r = 0; r < rec; r++) {
-      LoadTfs4(src, tc, r, t);
-      before += t[0] + t[1] + t[2] + t[3];
-    }
+    r0 = 0;
+  }
+  for (uint32_t r = r0; r < rec; r++) {
+    LoadTfs4(src, tc, r, t);
+    before += t[0] + t[1] + t[2] + t[3];
   }
   LoadTfs4(src, tc, rec, t);
   const uint32_t s = slot & 3u;
   before += (s > 0 ? t[0] : 0u) + (s > 1 ? t[1] : 0u) + (s > 2 ? t[2] : 0u);
   PosRun run;
-  run.p = ix.positions + first + before;
+  const size_t at = (size_t)first + before;
+  run.p = ix.pos16 ? static_cast<const void *>(reinterpret_cast<const unsigned short *>(ix.positions) + at)
+                   : static_cast<const void *>(reinterpret_cast<const uint32_t *>(ix.positions) + at);
   run.n = s == 0 ? t[0] : s == 1 ? t[1] : s == 2 ? t[2] : t[3];
   return run;
 }
 // exists p in a with p + 1 in b
-__device__ __forceinline__ bool PhraseTwo(const PosRun a, const PosRun b) {
+__device__ __forceinline__ bool PhraseTwo(const PosRun a, const PosRun b, bool p16) {
   uint32_t i = 0, j = 0;
   while (i < a.n && j < b.n) {
-    const uint32_t x = __ldg(a.p + i) + 1u, y = __ldg(b.p + j);
+    const uint32_t x = PosAt(a, i, p16) + 1u, y = PosAt(b, j, p16);
     if (x == y) return true;
     if (x < y) i++; else j++;
   }
@@ -672,7 +687,7 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
       uint32_t tfa, tfb;
       if (q.flags & 1u) {   // phrase: query term 0 must be directly followed by term 1
         const PosRun ra = PositionsOf(ix, h.pos_a), rb = PositionsOf(ix, h.pos_b);
-        keep = drv == 0 ? PhraseTwo(ra, rb) : PhraseTwo(rb, ra);
+        keep = drv == 0 ? PhraseTwo(ra, rb, ix.pos16 != 0u) : PhraseTwo(rb, ra, ix.pos16 != 0u);
         tfa = ra.n;           // a posting's run length IS its tf
         tfb = rb.n;
         WSR_STAT(st.bytes += 4ull * (ra.n + rb.n););
@@ -967,7 +982,7 @@ __device__ void ProcessTwoMerge(const DevIndexView &ix, const BatchView &bv, con
       }
       WSR_STAT(st.decoded += nB; st.bytes += AlgBytes(infoB.z, true););
     }
-    if (ShRcode(infoB.z) == 2u) DecodeDocsWide(ix, infoB, lane, dB);
+    if (ShRcode(infoB.z) >= 2u) DecodeDocsWide(ix, infoB, lane, dB);
     else DecodeRaw64(infoB, rawB, dB);
     const uint32_t lastB = __shfl_sync(kFull, dB[3], (int)((nB + 3u) >> 2) - 1);
     // ---- driver blocks that reach into this partner block join the set. Ring slots reused here
@@ -977,7 +992,7 @@ __device__ void ProcessTwoMerge(const DevIndexView &ix, const BatchView &bv, con
     while (ja < b1 && (infoA.x < lastB || ja == 0u) && ja - jr < (uint32_t)kRingBlocks) {
       const uint32_t nA = ShN(infoA.z), nlA = (nA + 3u) >> 2, tcA = ShTcode(infoA.z);
       uint32_t dA[4];
-      if (ShRcode(infoA.z) == 2u) DecodeDocsWide(ix, infoA, lane, dA);
+      if (ShRcode(infoA.z) >= 2u) DecodeDocsWide(ix, infoA, lane, dA);
       else DecodeRaw64(infoA, rawA, dA);
       const uint32_t lastA = __shfl_sync(kFull, dA[3], (int)nlA - 1);
       if ((uint32_t)lane >= nlA) dA[0] = dA[1] = dA[2] = dA[3] = lastA;   // keeps the ring sorted
@@ -1204,15 +1219,16 @@ __device__ bool MultiBatch(const DevIndexView &ix, const BatchView &bv, const De
 #pragma unroll
       for (int t = 0; t < WSR_MAX_TERMS; t++) ptr[t] = 0;
       bool found = false;
+      const bool p16 = ix.pos16 != 0u;
       for (uint32_t a0 = 0; a0 < run[0].n && !found; a0++) {
-        const uint32_t p0 = __ldg(run[0].p + a0);
+        const uint32_t p0 = PosAt(run[0], a0, p16);
         bool ok = true;
 #pragma unroll
         for (int t = 1; t < WSR_MAX_TERMS; t++) {
           if (t < m && ok) {
             const uint32_t want = p0 + (uint32_t)t;
-            while (ptr[t] < run[t].n && __ldg(run[t].p + ptr[t]) < want) ptr[t]++;
-            ok = ptr[t] < run[t].n && __ldg(run[t].p + ptr[t]) == want;
+            while (ptr[t] < run[t].n && PosAt(run[t], ptr[t], p16) < want) ptr[t]++;
+            ok = ptr[t] < run[t].n && PosAt(run[t], ptr[t], p16) == want;
           }
         }
         found = ok;
@@ -1528,26 +1544,80 @@ DecodeListKernel(const DevIndexView ix, uint32_t first_block, uint32_t n_blocks,
   }
 }
 
-// Raw tf record of the lane (16 / 32 / 128 bits), and its unpacking.
-__device__ __forceinline__ uint4 LoadTfRecord(const DevIndexView &ix, const uint4 info, uint32_t rec) {
-  const uint32_t bits = info.z, tc = ShTcode(bits);
-  const uint4 *src = ix.payload + info.y + DocGranules(bits);
-  uint4 r = make_uint4(0u, 0u, 0u, 0u);
-  if (tc == 0) r.x = __ldg(reinterpret_cast<const unsigned short *>(src) + rec);
-  else if (tc == 1) r.x = __ldg(reinterpret_cast<const uint32_t *>(src) + rec);
-  else r = __ldg(src + rec);
-  return r;
-}
-__device__ __forceinline__ void UnpackTfs(const uint4 info, const uint4 raw, uint32_t tf[4]) {
-  const uint32_t tc = ShTcode(info.z), v = raw.x;
-  if (tc == 0) { tf[0] = v & 15u; tf[1] = (v >> 4) & 15u; tf[2] = (v >> 8) & 15u; tf[3] = v >> 12; }
-  else if (tc == 1) { tf[0] = v & 255u; tf[1] = (v >> 8) & 255u; tf[2] = (v >> 16) & 255u; tf[3] = v >> 24; }
-  else { tf[0] = raw.x; tf[1] = raw.y; tf[2] = raw.z; tf[3] = raw.w; }
+// Whole-index decode (K1 roofline kernel): a pure stream over blk_info and the payload. A warp
+// takes U consecutive blocks per step and issues all of their metadata loads, then all of their
+// record loads, before decoding any. The kernel was 70 % issue-bound at 130 warp instructions per
+// block (round 1: run-time format dispatch per field, eight predicated 64-bit checksum adds), so
+// the decode below is written for instruction count: one uniform branch per block picks the
+// record format, the common 32/64-bit formats extract their fields with funnel shifts, the four
+// doc ids and the four tfs of a lane are summed in 32 bits (doc ids are < 2^31 and are added in
+// pairs, tfs are < 2^20) and enter the 64-bit checksum with three adds, and the "slot < n" tests
+// run only for a list's last, partial block.
+template <int U>
+__device__ __forceinline__ void DecodeAllStep(const DevIndexView &ix, uint32_t b, uint32_t n_blocks, int lane,
+                                              unsigned long long &sum) {
+  uint4 info[U];
+  uint2 rd[U];
+  uint32_t rt[U];
+#pragma unroll
+  for (int u = 0; u < U; u++)
+    info[u] = b + u < n_blocks ? __ldg(&ix.blk_info[b + u]) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    // 32/64-bit doc records and 4/8-bit tf records; the wide formats are read where they are decoded
+    const uint32_t bits = info[u].z, rc = ShRcode(bits), tc = ShTcode(bits);
+    const bool on = b + u < n_blocks && (uint32_t)lane < ((ShN(bits) + 3u) >> 2);
+    const uint4 *src = ix.payload + info[u].y;
+    rd[u] = make_uint2(0u, 0u);
+    rt[u] = 0u;
+    if (on) {
+      if (rc == 1u) rd[u] = __ldg(reinterpret_cast<const uint2 *>(src) + lane);
+      else if (rc == 0u) rd[u].x = __ldg(reinterpret_cast<const uint32_t *>(src) + lane);
+      const uint4 *ts = src + DocGranules(bits);
+      if (tc == 0u) rt[u] = __ldg(reinterpret_cast<const unsigned short *>(ts) + lane);
+      else if (tc == 1u) rt[u] = __ldg(reinterpret_cast<const uint32_t *>(ts) + lane);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    if (b + u >= n_blocks) continue;
+    const uint32_t bits = info[u].z, n = ShN(bits), rc = ShRcode(bits), tc = ShTcode(bits);
+    uint32_t d[4], t[4];
+    if (rc <= 1u) {
+      // [f:w0][d1:b][d2:b][d3:b] in 64 bits, LSB first: three funnel shifts
+      const uint32_t w0 = ShW0(bits), bw = ShB(bits);
+      const uint32_t mb = 0xffffffffu >> (32u - bw);
+      const uint32_t f = rd[u].x & (0xffffffffu >> (32u - w0));
+      const uint32_t s1 = w0, s2 = w0 + bw, s3 = s2 + bw;
+      const uint32_t d1 = (s1 < 32u ? __funnelshift_r(rd[u].x, rd[u].y, s1) : rd[u].y >> (s1 - 32u)) & mb;
+      const uint32_t d2 = (s2 < 32u ? __funnelshift_r(rd[u].x, rd[u].y, s2) : rd[u].y >> (s2 - 32u)) & mb;
+      const uint32_t d3 = (s3 < 32u ? __funnelshift_r(rd[u].x, rd[u].y, s3) : rd[u].y >> (s3 - 32u)) & mb;
+      d[0] = info[u].x + f;
+      d[1] = d[0] + d1;
+      d[2] = d[1] + d2;
+      d[3] = d[2] + d3;
+    } else {
+      d[0] = d[1] = d[2] = d[3] = 0u;
+      if ((uint32_t)lane < ((n + 3u) >> 2)) DecodeRecord(ix, info[u], (uint32_t)lane, d);
+    }
+    if (tc == 0u) {
+      t[0] = rt[u] & 15u; t[1] = (rt[u] >> 4) & 15u; t[2] = (rt[u] >> 8) & 15u; t[3] = rt[u] >> 12;
+    } else if (tc == 1u) {
+      t[0] = rt[u] & 255u; t[1] = (rt[u] >> 8) & 255u; t[2] = (rt[u] >> 16) & 255u; t[3] = rt[u] >> 24;
+    } else {
+      DecodeTfs(ix, info[u], lane, t);
+    }
+    if (n != 128u) {   // a list's last block: slots past n do not count (they repeat the last posting)
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (4u * lane + i >= n) { d[i] = 0u; t[i] = 0u; }
+    }
+    sum += (unsigned long long)(d[0] + d[1]);
+    sum += (unsigned long long)(d[2] + d[3]);
+    sum += (unsigned long long)(t[0] + t[1] + t[2] + t[3]);
+  }
 }
 
-// Whole-index decode (K1 roofline kernel): a warp takes 4 consecutive blocks per step and issues
-// all of their metadata loads, then all of their record loads, before decoding any — the kernel is
-// a pure stream and only memory-level parallelism keeps HBM busy.
 __global__ void __launch_bounds__(kThreadsPerCta)
 DecodeAllKernel(const DevIndexView ix, uint32_t n_blocks, unsigned long long *checksum) {
   constexpr int U = 4;
@@ -1555,29 +1625,7 @@ DecodeAllKernel(const DevIndexView ix, uint32_t n_blocks, unsigned long long *ch
   const uint32_t warps = gridDim.x * kWarpsPerCta;
   const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   unsigned long long sum = 0;
-  for (uint32_t b = w * U; b < n_blocks; b += warps * U) {
-    uint4 info[U], rd[U], rt[U];
-#pragma unroll
-    for (int u = 0; u < U; u++)
-      info[u] = b + u < n_blocks ? __ldg(&ix.blk_info[b + u]) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const bool on = b + u < n_blocks && (uint32_t)lane < ((ShN(info[u].z) + 3u) >> 2);
-      rd[u] = on ? LoadRecord(ix, info[u], (uint32_t)lane) : make_uint4(0u, 0u, 0u, 0u);
-      rt[u] = on ? LoadTfRecord(ix, info[u], (uint32_t)lane) : make_uint4(0u, 0u, 0u, 0u);
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (b + u >= n_blocks) continue;
-      const uint32_t n = ShN(info[u].z);
-      uint32_t d[4], tf[4];
-      DecodeRaw(info[u], rd[u], d);
-      UnpackTfs(info[u], rt[u], tf);
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (4u * lane + i < n) sum += (unsigned long long)d[i] + tf[i];
-    }
-  }
+  for (uint32_t b = w * U; b < n_blocks; b += warps * U) DecodeAllStep<U>(ix, b, n_blocks, lane, sum);
 #pragma unroll
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
   if (lane == 0 && sum) atomicAdd(checksum, sum);
@@ -1646,6 +1694,26 @@ __global__ void MergeShardsKernel(const wsr_hit *__restrict__ g, const int32_t *
     rank += lo;
   }
   if (rank < k_stride) out[(size_t)q * k_stride + rank] = me;
+}
+
+// doc_freqs across document partitions: every partition reports the collection-wide df of the
+// terms ITS dictionary holds (0 terms when one is missing there), so the merged row is the
+// element-wise maximum, and the term count the maximum count.
+__global__ void MergeDocFreqsKernel(const uint32_t *__restrict__ g_df, const int32_t *__restrict__ g_ndf,
+                                    int n_shards, int n, uint32_t *__restrict__ out_df,
+                                    int32_t *__restrict__ out_ndf) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * WSR_MAX_TERMS) return;
+  const int q = (int)(t / WSR_MAX_TERMS), j = (int)(t % WSR_MAX_TERMS);
+  uint32_t m = 0;
+  int32_t c = 0;
+  for (int s = 0; s < n_shards; s++) {
+    const int32_t cs = g_ndf[(size_t)s * n + q];
+    if (j < cs) m = max(m, g_df[((size_t)s * n + q) * WSR_MAX_TERMS + j]);
+    c = max(c, cs);
+  }
+  out_df[t] = j < c ? m : 0u;
+  if (j == 0) out_ndf[q] = c;
 }
 
 // ---- collect mode epilogue ---------------------------------------------------------------------
@@ -1766,6 +1834,13 @@ void LaunchMergeShards(const wsr_hit *gathered, const int32_t *gathered_n, int n
   const unsigned grid = (unsigned)((total + threads - 1) / threads);
   MergeShardsKernel<<<grid, threads, 0, s>>>(gathered, gathered_n, n_shards, n_queries, k_stride,
                                              out, out_n);
+}
+
+void LaunchMergeDocFreqs(const uint32_t *g_df, const int32_t *g_ndf, int n_shards, int n, uint32_t *out_df,
+                         int32_t *out_ndf, cudaStream_t s) {
+  const long long total = (long long)n * WSR_MAX_TERMS;
+  if (total <= 0) return;
+  MergeDocFreqsKernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(g_df, g_ndf, n_shards, n, out_df, out_ndf);
 }
 
 size_t CollectSortTempBytes(uint32_t n_entries, uint32_t n_collect) {

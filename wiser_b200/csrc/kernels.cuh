@@ -32,9 +32,11 @@ struct DevIndexView {
   const float *blk_max;       // SoA copy of blk_info.w
   const uint32_t *filters;    // per-list doc-range-partitioned Bloom filters
   const uint2 *list_flt;      // per term {first filter word, shift g (0xFFFFFFFF: no filter)}
-  const uint32_t *positions;  // optional: in-document token positions, postings back to back
+  const void *positions;      // optional: in-document token positions, postings back to back; u16 entries
+                              // when pos16 (every position of the shard < 65536), else u32
   const uint32_t *blk_pos;    // optional: index into positions[] of each block's first posting
-  const uint16_t *rec_pos;    // optional: 32 per block, positions before record r of the block
+  const uint16_t *grp_pos;    // optional: 8 per block, positions before record 4g of the block
+  uint32_t pos16;
   uint32_t n_terms;
   uint32_t n_docs;
   uint32_t doc_lo;            // first doc id held by this shard (filter origin)
@@ -120,6 +122,10 @@ void LaunchRefreshBlockMax(const DevIndexView &ix, uint32_t n_blocks, uint4 *blk
 void LaunchMergeShards(const wsr_hit *gathered, const int32_t *gathered_n, int n_shards,
                        int n_queries, int k_stride, wsr_hit *out, int32_t *out_n,
                        cudaStream_t s);
+// doc_freqs of n queries reported by n_shards partitions (g_df[shard][n][WSR_MAX_TERMS],
+// g_ndf[shard][n]) -> element-wise maximum.
+void LaunchMergeDocFreqs(const uint32_t *g_df, const int32_t *g_ndf, int n_shards, int n, uint32_t *out_df,
+                         int32_t *out_ndf, cudaStream_t s);
 // Collect mode epilogue: per query segment sort by (score desc, doc asc) and copy the first k.
 // seg_begin/seg_end: device arrays [n_collect]; tmp buffers sized like the segment arrays.
 size_t CollectSortTempBytes(uint32_t n_entries, uint32_t n_collect);

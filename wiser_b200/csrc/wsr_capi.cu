@@ -170,8 +170,8 @@ struct wsr_index {
   DevBuf<float> d_blk_max;
   DevBuf<uint32_t> d_filters;
   DevBuf<uint2> d_list_flt;
-  DevBuf<uint32_t> d_positions, d_blk_pos;
-  DevBuf<uint16_t> d_rec_pos;
+  DevBuf<uint32_t> d_positions, d_blk_pos;   // d_positions holds u16 entries when view.pos16
+  DevBuf<uint16_t> d_grp_pos;
   // device copy of the term dictionary for the query-log front end (frontend.cu)
   DevBuf<uint2> d_dict_slots;
   DevBuf<uint32_t> d_term_off;
@@ -700,22 +700,50 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
   if (const char *mr = getenv("WSR_MERGE_RATIO_X4")) v.merge_ratio_x4 = (uint32_t)std::max(0, atoi(mr));
   v.positions = nullptr;
   v.blk_pos = nullptr;
-  v.rec_pos = nullptr;
+  v.grp_pos = nullptr;
+  v.pos16 = 0;
   if (h.has_positions) {
-    if (!cu(ix->d_positions.Ensure(h.positions.size() + 1), "cudaMalloc positions") ||
+    // 16-bit positions when they all fit (a document would need 65536+ tokens otherwise)
+    bool fits16 = true;
+    {
+      const int T = HostThreads(h.positions.size(), 1 << 20);
+      std::vector<uint8_t> big(T, 0);
+      ParallelFor(T, [&](int t, int TT) {
+        const size_t lo = h.positions.size() * t / TT, hi = h.positions.size() * (t + 1) / TT;
+        uint32_t m = 0;
+        for (size_t i = lo; i < hi; i++) m |= h.positions[i];
+        big[t] = m > 0xFFFFu;
+      });
+      for (uint8_t x : big) fits16 = fits16 && !x;
+    }
+    const size_t n_pos = h.positions.size();
+    const void *pos_src = h.positions.data();
+    std::vector<uint16_t> pos16;
+    if (fits16) {
+      pos16.resize(n_pos);
+      const int T = HostThreads(n_pos, 1 << 20);
+      ParallelFor(T, [&](int t, int TT) {
+        for (size_t i = n_pos * t / TT, e = n_pos * (t + 1) / TT; i < e; i++) pos16[i] = (uint16_t)h.positions[i];
+      });
+      std::vector<uint32_t>().swap(h.positions);
+      pos_src = pos16.data();
+    }
+    const size_t pos_bytes = n_pos * (fits16 ? 2 : 4);
+    if (!cu(ix->d_positions.Ensure(pos_bytes / 4 + 2), "cudaMalloc positions") ||
         !cu(ix->d_blk_pos.Ensure(h.blk_pos.size() + 1), "cudaMalloc blk_pos") ||
-        !cu(ix->d_rec_pos.Ensure(h.rec_pos.size() + 1), "cudaMalloc rec_pos") ||
-        !cu(cudaMemcpy(ix->d_rec_pos.p, h.rec_pos.data(), h.rec_pos.size() * 2, cudaMemcpyHostToDevice), "H2D rec_pos") ||
-        !cu(cudaMemcpy(ix->d_positions.p, h.positions.data(), h.positions.size() * 4, cudaMemcpyHostToDevice), "H2D positions") ||
+        !cu(ix->d_grp_pos.Ensure(h.grp_pos.size() + 1), "cudaMalloc grp_pos") ||
+        !cu(cudaMemcpy(ix->d_grp_pos.p, h.grp_pos.data(), h.grp_pos.size() * 2, cudaMemcpyHostToDevice), "H2D grp_pos") ||
+        !cu(cudaMemcpy(ix->d_positions.p, pos_src, pos_bytes, cudaMemcpyHostToDevice), "H2D positions") ||
         !cu(cudaMemcpy(ix->d_blk_pos.p, h.blk_pos.data(), h.blk_pos.size() * 4, cudaMemcpyHostToDevice), "H2D blk_pos"))
       return fail(e);
     v.positions = ix->d_positions.p;
     v.blk_pos = ix->d_blk_pos.p;
-    v.rec_pos = ix->d_rec_pos.p;
-    ix->hbm_bytes += (int64_t)h.positions.size() * 4 + (int64_t)h.blk_pos.size() * 4 + (int64_t)h.rec_pos.size() * 2;
+    v.grp_pos = ix->d_grp_pos.p;
+    v.pos16 = fits16 ? 1u : 0u;
+    ix->hbm_bytes += (int64_t)pos_bytes + (int64_t)h.blk_pos.size() * 4 + (int64_t)h.grp_pos.size() * 2;
     std::vector<uint32_t>().swap(h.positions);
     std::vector<uint32_t>().swap(h.blk_pos);
-    std::vector<uint16_t>().swap(h.rec_pos);
+    std::vector<uint16_t>().swap(h.grp_pos);
   }
   // term dictionary in HBM for the query-log front end: the host table's slots with a 32-bit tag
   // (so most probes never touch the term bytes), 32-bit term offsets, the term arena

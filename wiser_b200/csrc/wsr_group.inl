@@ -82,6 +82,11 @@ struct wsr_comm {
   DevBuf<int32_t> g_n, m_n, full_n;
   const wsr_hit *res_hits = nullptr;           // result of the last exchange (device pointers)
   const int32_t *res_n = nullptr;
+  // doc_freqs travel with the lists when the caller wants them (same groups, same slices)
+  DevBuf<uint32_t> g_df, m_df, full_df;
+  DevBuf<int32_t> g_ndf, m_ndf, full_ndf;
+  const uint32_t *res_df = nullptr;
+  const int32_t *res_ndf = nullptr;
 };
 
 namespace {
@@ -94,12 +99,16 @@ inline uint32_t SliceLo(uint32_t n, int world, int r) { return std::min<uint32_t
 // Enqueues the exchange of (loc_hits[n*k], loc_n[n]) on `stream`; afterwards c->res_* point at the
 // merged result (n queries) on every rank. mode 0: scatter exchange, 1: plain all-gather.
 int ExchangeOnStream(wsr_comm *c, const wsr_hit *loc_hits, const int32_t *loc_n, uint32_t n, uint32_t k,
-                     cudaStream_t stream, int mode) {
+                     cudaStream_t stream, int mode, const uint32_t *loc_df = nullptr,
+                     const int32_t *loc_ndf = nullptr) {
+  c->res_df = loc_df;
+  c->res_ndf = loc_ndf;
   if (c->world == 1) {
     c->res_hits = loc_hits;
     c->res_n = loc_n;
     return WSR_OK;
   }
+  if (loc_df && mode == 1) return Fail(WSR_ERR_UNSUPPORTED, "doc_freqs travel with the scatter exchange only");
   NcclApi *nc = Nccl();
   if (!nc->error.empty()) return Fail(WSR_ERR_UNSUPPORTED, nc->error);
   const int W = c->world;
@@ -126,6 +135,14 @@ int ExchangeOnStream(wsr_comm *c, const wsr_hit *loc_hits, const int32_t *loc_n,
   CU(c->m_n.Ensure((size_t)s + 1));
   CU(c->full_hits.Ensure((size_t)W * s * k + 1));
   CU(c->full_n.Ensure((size_t)W * s + 1));
+  if (loc_df) {
+    CU(c->g_df.Ensure((size_t)W * s * WSR_MAX_TERMS + 1));
+    CU(c->g_ndf.Ensure((size_t)W * s + 1));
+    CU(c->m_df.Ensure((size_t)s * WSR_MAX_TERMS + 1));
+    CU(c->m_ndf.Ensure((size_t)s + 1));
+    CU(c->full_df.Ensure((size_t)W * s * WSR_MAX_TERMS + 1));
+    CU(c->full_ndf.Ensure((size_t)W * s + 1));
+  }
   // (1) every rank hands rank j its lists of slice j: hits and counts travel in ONE group
   NC(nc->GroupStart());
   for (int j = 0; j < W; j++) {
@@ -133,10 +150,18 @@ int ExchangeOnStream(wsr_comm *c, const wsr_hit *loc_hits, const int32_t *loc_n,
     if (cnt) {
       NC(nc->Send(loc_hits + (size_t)lo * k, (size_t)cnt * k * sizeof(wsr_hit), kNcclUint8, j, c->comm, stream));
       NC(nc->Send(loc_n + lo, (size_t)cnt * 4, kNcclUint8, j, c->comm, stream));
+      if (loc_df) {
+        NC(nc->Send(loc_df + (size_t)lo * WSR_MAX_TERMS, (size_t)cnt * WSR_MAX_TERMS * 4, kNcclUint8, j, c->comm, stream));
+        NC(nc->Send(loc_ndf + lo, (size_t)cnt * 4, kNcclUint8, j, c->comm, stream));
+      }
     }
     if (mine) {
       NC(nc->Recv(c->g_hits.p + (size_t)j * mine * k, (size_t)mine * k * sizeof(wsr_hit), kNcclUint8, j, c->comm, stream));
       NC(nc->Recv(c->g_n.p + (size_t)j * mine, (size_t)mine * 4, kNcclUint8, j, c->comm, stream));
+      if (loc_df) {
+        NC(nc->Recv(c->g_df.p + (size_t)j * mine * WSR_MAX_TERMS, (size_t)mine * WSR_MAX_TERMS * 4, kNcclUint8, j, c->comm, stream));
+        NC(nc->Recv(c->g_ndf.p + (size_t)j * mine, (size_t)mine * 4, kNcclUint8, j, c->comm, stream));
+      }
     }
   }
   NC(nc->GroupEnd());
@@ -144,12 +169,25 @@ int ExchangeOnStream(wsr_comm *c, const wsr_hit *loc_hits, const int32_t *loc_n,
   // starts at query r*s, so the first n queries of full_* are the result)
   LaunchMergeShards(c->g_hits.p, c->g_n.p, W, (int)mine, (int)k, c->m_hits.p, c->m_n.p, stream);
   CU(cudaGetLastError());
+  if (loc_df) {
+    LaunchMergeDocFreqs(c->g_df.p, c->g_ndf.p, W, (int)mine, c->m_df.p, c->m_ndf.p, stream);
+    CU(cudaGetLastError());
+  }
   NC(nc->GroupStart());
   NC(nc->AllGather(c->m_hits.p, c->full_hits.p, (size_t)s * k * sizeof(wsr_hit), kNcclUint8, c->comm, stream));
   NC(nc->AllGather(c->m_n.p, c->full_n.p, (size_t)s * 4, kNcclUint8, c->comm, stream));
+  if (loc_df) {
+    NC(nc->AllGather(c->m_df.p, c->full_df.p, (size_t)s * WSR_MAX_TERMS * 4, kNcclUint8, c->comm, stream));
+    NC(nc->AllGather(c->m_ndf.p, c->full_ndf.p, (size_t)s * 4, kNcclUint8, c->comm, stream));
+  }
   NC(nc->GroupEnd());
+  CU(cudaGetLastError());
   c->res_hits = c->full_hits.p;
   c->res_n = c->full_n.p;
+  if (loc_df) {
+    c->res_df = c->full_df.p;
+    c->res_ndf = c->full_ndf.p;
+  }
   return WSR_OK;
 }
 
@@ -243,8 +281,12 @@ struct GroupDevice {
   wsr_comm *comm = nullptr;               // rank of this device in the exchange
   DevBuf<wsr_hit> lg_hits, loc_hits;      // local partitions' lists gathered / merged
   DevBuf<int32_t> lg_n, loc_n;
+  DevBuf<uint32_t> lg_df, loc_df;         // the same for doc_freqs
+  DevBuf<int32_t> lg_ndf, loc_ndf;
   const wsr_hit *res_hits = nullptr;
   const int32_t *res_n = nullptr;
+  const uint32_t *res_df = nullptr;
+  const int32_t *res_ndf = nullptr;
   int rc = 0;
   std::string err;
 };
@@ -324,26 +366,37 @@ void GroupLoadOn(wsr_group *g, GroupDevice &d, const char *text, size_t len, int
 }
 
 // Enqueues one pass on a device: search kernels of every local partition, local merge, exchange.
-void GroupRunOn(wsr_group *g, GroupDevice &d, int mode) {
+void GroupRunOn(wsr_group *g, GroupDevice &d, int mode, bool with_df) {
   d.rc = 0;
   auto fail = [&](int rc) { d.rc = rc; d.err = g_err; };
   if (cudaSetDevice(d.device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return fail(WSR_ERR_CUDA); }
   const size_t P = d.batches.size();
   wsr_batch *lead = d.batches[0];
   const uint32_t n = (uint32_t)lead->n, k = (uint32_t)lead->k_stride;
+  auto cu = [&](cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    fail(WSR_ERR_CUDA);
+    return false;
+  };
   for (size_t p = 0; p < P; p++) {
-    int rc = EnqueueRun(d.batches[p]);
+    wsr_batch *b = d.batches[p];
+    int rc = EnqueueRun(b);
     if (rc) return fail(rc);
+    if (with_df) {   // needs the device planner's unplaced queries (k <= 32)
+      if (!b->d_tmp.p || !DeviceFrontEndUsable(b->idx, 1, (int)k)) {
+        g_err = "doc_freqs of a group need the device front end (k <= 32)";
+        return fail(WSR_ERR_UNSUPPORTED);
+      }
+      if (!cu(b->d_df.Ensure((size_t)n * WSR_MAX_TERMS + 1), "cudaMalloc") || !cu(b->d_ndf.Ensure((size_t)n + 1), "cudaMalloc")) return;
+      LaunchDocFreqs(b->d_tmp.p, n, b->idx->view, b->d_df.p, b->d_ndf.p, b->stream);
+    }
   }
   const wsr_hit *loc_hits = lead->out_hits;
   const int32_t *loc_n = lead->out_n;
+  const uint32_t *loc_df = with_df ? lead->d_df.p : nullptr;
+  const int32_t *loc_ndf = with_df ? lead->d_ndf.p : nullptr;
   if (P > 1) {
-    auto cu = [&](cudaError_t e, const char *what) {
-      if (e == cudaSuccess) return true;
-      g_err = std::string(what) + ": " + cudaGetErrorString(e);
-      fail(WSR_ERR_CUDA);
-      return false;
-    };
     if (!cu(d.lg_hits.Ensure(P * (size_t)n * k + 1), "cudaMalloc") || !cu(d.lg_n.Ensure(P * (size_t)n + 1), "cudaMalloc") ||
         !cu(d.loc_hits.Ensure((size_t)n * k + 1), "cudaMalloc") || !cu(d.loc_n.Ensure((size_t)n + 1), "cudaMalloc"))
       return;
@@ -362,6 +415,23 @@ void GroupRunOn(wsr_group *g, GroupDevice &d, int mode) {
     }
     LaunchMergeShards(d.lg_hits.p, d.lg_n.p, (int)P, (int)n, (int)k, d.loc_hits.p, d.loc_n.p, lead->stream);
     if (!cu(cudaGetLastError(), "merge kernel")) return;
+    if (with_df) {
+      if (!cu(d.lg_df.Ensure(P * (size_t)n * WSR_MAX_TERMS + 1), "cudaMalloc") || !cu(d.lg_ndf.Ensure(P * (size_t)n + 1), "cudaMalloc") ||
+          !cu(d.loc_df.Ensure((size_t)n * WSR_MAX_TERMS + 1), "cudaMalloc") || !cu(d.loc_ndf.Ensure((size_t)n + 1), "cudaMalloc"))
+        return;
+      for (size_t p = 0; p < P; p++) {   // (the waits on the partitions' streams were enqueued above)
+        wsr_batch *b = d.batches[p];
+        if (!cu(cudaMemcpyAsync(d.lg_df.p + p * (size_t)n * WSR_MAX_TERMS, b->d_df.p, (size_t)n * WSR_MAX_TERMS * 4,
+                                cudaMemcpyDeviceToDevice, lead->stream), "D2D doc_freqs") ||
+            !cu(cudaMemcpyAsync(d.lg_ndf.p + p * (size_t)n, b->d_ndf.p, (size_t)n * 4, cudaMemcpyDeviceToDevice,
+                                lead->stream), "D2D doc_freq counts"))
+          return;
+      }
+      LaunchMergeDocFreqs(d.lg_df.p, d.lg_ndf.p, (int)P, (int)n, d.loc_df.p, d.loc_ndf.p, lead->stream);
+      if (!cu(cudaGetLastError(), "doc_freqs merge kernel")) return;
+      loc_df = d.loc_df.p;
+      loc_ndf = d.loc_ndf.p;
+    }
     // the next pass of partition p > 0 must not overwrite its results before they were copied
     if (!cu(cudaEventRecord(d.done[0], lead->stream), "cudaEventRecord")) return;
     for (size_t p = 1; p < P; p++)
@@ -369,10 +439,12 @@ void GroupRunOn(wsr_group *g, GroupDevice &d, int mode) {
     loc_hits = d.loc_hits.p;
     loc_n = d.loc_n.p;
   }
-  const int rc = ExchangeOnStream(d.comm, loc_hits, loc_n, n, k, lead->stream, mode);
+  const int rc = ExchangeOnStream(d.comm, loc_hits, loc_n, n, k, lead->stream, mode, loc_df, loc_ndf);
   if (rc) return fail(rc);
   d.res_hits = d.comm->res_hits;
   d.res_n = d.comm->res_n;
+  d.res_df = d.comm->res_df;
+  d.res_ndf = d.comm->res_ndf;
 }
 
 }  // namespace
@@ -542,7 +614,7 @@ int wsr_group_load_log(wsr_group *g, const char *text, size_t len, int k, int *n
 
 int wsr_group_run(wsr_group *g, int mode) {
   if (!g || !g->loaded || mode < 0 || mode > 1) return Fail(WSR_ERR_ARG, "no log loaded");
-  g->RunOnDevices([&](GroupDevice &d, int) { GroupRunOn(g, d, mode); });
+  g->RunOnDevices([&](GroupDevice &d, int) { GroupRunOn(g, d, mode, false); });
   return GroupFirstError(g);
 }
 
@@ -606,30 +678,44 @@ int wsr_group_search_log(wsr_group *g, const char *text, size_t len, int k, wsr_
   int n = 0;
   int rc = wsr_group_load_log(g, text, len, k, &n);
   if (rc) return rc;
+  if (hits && n > cap_q) return Fail(WSR_ERR_ARG, "result buffers too small");
+  // doc_freqs are computed by every partition from its own dictionary and merged with the lists
+  // (a term may be missing from one partition's dictionary and present in another's). Every rank
+  // of a multi-process job must make the same choice, so they always travel when k allows it.
+  const bool with_df = k <= kMaxFastK;
+  if (doc_freqs && !with_df) return Fail(WSR_ERR_UNSUPPORTED, "doc_freqs of a group need the device front end (k <= 32)");
+  g->RunOnDevices([&](GroupDevice &d, int) { GroupRunOn(g, d, 0, with_df); });
+  rc = GroupFirstError(g);
+  if (rc) return rc;
   if (!hits) {   // a rank of a multi-process job that does not face the client: search + exchange only
-    rc = wsr_group_run(g, 0);
-    if (rc == WSR_OK) rc = wsr_group_sync(g);
+    rc = wsr_group_sync(g);
     if (rc == WSR_OK) *n_queries = n;
     return rc;
   }
-  if (n > cap_q) return Fail(WSR_ERR_ARG, "result buffers too small");
-  rc = wsr_group_run(g, 0);
-  if (rc) return rc;
-  // doc_freqs: from the first partition's dictionary (collection-wide df after the stats exchange)
+  GroupDevice &d0 = g->devs[0];
+  wsr_batch *lead = d0.batches[0];
   bool df_staged = false;
-  wsr_batch *lead = g->devs[0].batches[0];
-  if (doc_freqs && DeviceFrontEndUsable(lead->idx, len, k)) {
-    CU(cudaSetDevice(g->devs[0].device));
-    rc = EnqueueDocFreqs(lead, doc_freqs, n_doc_freqs, &df_staged);
-    if (rc) return rc;
-  } else if (doc_freqs) {
-    return Fail(WSR_ERR_UNSUPPORTED, "doc_freqs of a group need the device front end (k <= 32)");
+  if (doc_freqs) {
+    CU(cudaSetDevice(d0.device));
+    uint32_t *df = doc_freqs;
+    int32_t *ndf = n_doc_freqs;
+    if (!IsPinned(doc_freqs) || !IsPinned(n_doc_freqs)) {
+      CU(lead->h_df.Ensure((size_t)n * WSR_MAX_TERMS + 1));
+      CU(lead->h_ndf.Ensure((size_t)n + 1));
+      df = lead->h_df.p;
+      ndf = lead->h_ndf.p;
+      df_staged = true;
+    }
+    if (n) {
+      CU(cudaMemcpyAsync(df, d0.res_df, (size_t)n * WSR_MAX_TERMS * 4, cudaMemcpyDeviceToHost, lead->stream));
+      CU(cudaMemcpyAsync(ndf, d0.res_ndf, (size_t)n * 4, cudaMemcpyDeviceToHost, lead->stream));
+    }
   }
   rc = wsr_group_fetch(g, hits, n_hits);
   if (rc) return rc;
   rc = wsr_group_sync(g);
   if (rc) return rc;
-  if (df_staged) {
+  if (df_staged && n) {
     memcpy(doc_freqs, lead->h_df.p, (size_t)n * WSR_MAX_TERMS * 4);
     memcpy(n_doc_freqs, lead->h_ndf.p, (size_t)n * 4);
   }

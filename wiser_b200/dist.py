@@ -189,7 +189,8 @@ class ShardGroup:
         if multi:
             gd = capi.GroupDist()
             gd.rank, gd.world = rank, world
-            gd.comm_id = _new_comm_id(rank)
+            cid = _new_comm_id(rank)          # 128 raw bytes (may contain NULs: no string assignment)
+            C.memmove(C.addressof(gd) + capi.GroupDist.comm_id.offset, cid, capi.WSR_COMM_ID_BYTES)
         err = C.create_string_buffer(512)
         self._g = lib().wsr_group_open(arr, len(self.dirs), devs, len(self.devices), loader_threads,
                                        capi.WSR_OPEN_POSITIONS if positions else 0,
