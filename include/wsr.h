@@ -263,6 +263,8 @@ int wsr_batch_fetch_exchanged(wsr_batch *b, wsr_comm *c, wsr_hit *hits, int32_t 
  * exchange rank per device. Multi-process (one device per process): dist names this process's
  * rank, the world size and the communicator id; the caller then sets the collection statistics on
  * each wsr_group_part() with wsr_index_set_global_stats, because only it can reach the other ranks. */
+/* A group serves one batch at a time: calls on the same wsr_group must not overlap (the adapter's
+ * request coalescer serialises them). */
 typedef struct wsr_group wsr_group;
 typedef struct {
   int rank, world;

@@ -1,5 +1,6 @@
 #include "gpu_vacuum_engine.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +19,8 @@ namespace {
 
 struct GpuVacuumEngine::Pending {
   wsr_query q;
+  const SearchQuery *src = nullptr;   // group mode: the query text is sent, not term ids
+  std::string err;                    // message of a failed batch (set by the leader's thread)
   std::vector<wsr_hit> hits;
   int32_t n_hits = 0;
   bool done = false;
@@ -33,12 +36,35 @@ GpuVacuumEngine::GpuVacuumEngine(const std::string engine_dir_path, int bloom_en
     : dir_(engine_dir_path), bloom_enable_factor_(bloom_enable_factor), opt_(opt) {}
 
 GpuVacuumEngine::~GpuVacuumEngine() {
-  if (idx_) wsr_index_close(idx_);
+  if (group_) wsr_group_close(group_);
+  else if (idx_) wsr_index_close(idx_);
+}
+
+bool GpuVacuumEngine::LookupAnyPartition(const std::string &term, uint32_t *df) const {
+  // a term may be missing from one partition's dictionary and present in another's; the df a
+  // partition reports is the collection-wide one (set by the group's statistics exchange)
+  const int n = group_ ? wsr_group_n_parts(group_) : 1;
+  for (int p = 0; p < n; p++) {
+    uint32_t id;
+    wsr_index *ix = group_ ? wsr_group_part(group_, p) : idx_;
+    if (wsr_term_lookup(ix, term.data(), term.size(), &id, df) == 0) return true;
+  }
+  return false;
 }
 
 void GpuVacuumEngine::Load() {
   if (idx_) Fatal("Engine is already loaded.");                     // vacuum_engine.h:145
   char err[512] = {0};
+  if (!opt_.partition_dirs.empty()) {
+    std::vector<const char *> dirs;
+    for (const std::string &d : opt_.partition_dirs) dirs.push_back(d.c_str());
+    std::vector<int> devs = opt_.devices.empty() ? std::vector<int>{opt_.device} : opt_.devices;
+    group_ = wsr_group_open(dirs.data(), (int)dirs.size(), devs.data(), (int)devs.size(), opt_.loader_threads,
+                            opt_.load_positions ? WSR_OPEN_POSITIONS : 0u, nullptr, err, sizeof(err));
+    if (!group_) Fatal(std::string("wsr_group_open: ") + err);
+    idx_ = wsr_group_part(group_, 0);
+    return;
+  }
   idx_ = wsr_index_open_ex(dir_.c_str(), opt_.device, opt_.shard, opt_.n_shards, opt_.loader_threads,
                            opt_.load_positions ? WSR_OPEN_POSITIONS : 0u, err, sizeof(err));
   if (!idx_) Fatal(std::string("wsr_index_open: ") + err);
@@ -53,8 +79,8 @@ int GpuVacuumEngine::TermCount() const {
 std::map<std::string, int> GpuVacuumEngine::PostinglistSizes(const TermList &terms) {
   std::map<std::string, int> ret;
   for (auto &term : terms) {
-    uint32_t id, df;
-    if (wsr_term_lookup(idx_, term.data(), term.size(), &id, &df) == 0) ret[term] = (int)df;
+    uint32_t df;
+    if (LookupAnyPartition(term, &df)) ret[term] = (int)df;
   }
   return ret;
 }
@@ -80,11 +106,38 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
   SearchResult result;
   if (!idx_) Fatal("Engine is not yet loaded");
   Pending p;
-  if (!ToWsrQuery(query, &p.q)) return result;
-  for (size_t t = 0; t < query.terms.size(); t++) {                  // vacuum_engine.h:217-219
-    uint32_t id, df;
-    wsr_term_lookup(idx_, query.terms[t].data(), query.terms[t].size(), &id, &df);
-    result.doc_freqs.push_back((int)df);
+  if (group_) {
+    // group mode: every partition resolves the terms in its own dictionary on the GPU; here only
+    // the early-outs and doc_freqs (vacuum_engine.h:206-219)
+    if (query.n_results <= 0 || query.terms.empty()) return result;
+    if (query.terms.size() > WSR_MAX_TERMS) Fatal("more than WSR_MAX_TERMS query terms");
+    std::vector<int> dfs;
+    for (const Term &t : query.terms) {
+      uint32_t df;
+      if (!LookupAnyPartition(t, &df)) return result;
+      dfs.push_back((int)df);
+    }
+    result.doc_freqs = dfs;
+    memset(&p.q, 0, sizeof(p.q));
+    p.q.k = (uint32_t)query.n_results;
+    p.src = &query;
+  } else {
+    // one dictionary lookup per term: ids for the query, dfs for doc_freqs (vacuum_engine.h:217-219)
+    memset(&p.q, 0, sizeof(p.q));
+    if (query.n_results <= 0 || query.terms.empty()) return result;           // vacuum_engine.h:206-208
+    if (query.terms.size() > WSR_MAX_TERMS) Fatal("more than WSR_MAX_TERMS query terms");
+    p.q.n_terms = (uint32_t)query.terms.size();
+    p.q.k = (uint32_t)query.n_results;
+    p.q.flags = query.is_phrase ? WSR_QUERY_PHRASE : 0u;
+    std::vector<int> dfs;
+    for (size_t t = 0; t < query.terms.size(); t++) {
+      uint32_t id, df;
+      if (wsr_term_lookup(idx_, query.terms[t].data(), query.terms[t].size(), &id, &df) != 0)
+        return result;                                                         // vacuum_engine.h:213-215
+      p.q.term_ids[t] = id;
+      dfs.push_back((int)df);
+    }
+    result.doc_freqs = dfs;
   }
   p.hits.resize(p.q.k);
   thread_local std::shared_ptr<std::condition_variable> my_cv = std::make_shared<std::condition_variable>();
@@ -95,7 +148,8 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
     pending_.push_back(&p);
     std::vector<Pending *> take;
     while (!p.done) {
-      if (inflight_ < std::max(1, opt_.max_inflight) && !pending_.empty()) {
+      // (a group runs one batch at a time: its per-device batches and exchange buffers are single)
+      if (inflight_ < (group_ ? 1 : std::max(1, opt_.max_inflight)) && !pending_.empty()) {
         // lead: everything queued so far (this caller is in it unless another leader took it)
         inflight_++;
         if (opt_.coalesce_window_us > 0 && (int)pending_.size() < opt_.coalesce_max_batch)
@@ -109,7 +163,8 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
           pending_.erase(pending_.begin(), pending_.begin() + opt_.coalesce_max_batch);
         }
         lk.unlock();
-        RunBatch(take);
+        if (group_) RunGroupBatch(take);
+        else RunBatch(take);
         lk.lock();
         inflight_--;
         wake.clear();
@@ -127,7 +182,7 @@ SearchResult GpuVacuumEngine::Search(const SearchQuery &query) {
       }
     }
   }
-  if (p.rc != 0) Fatal(std::string("wsr_search_batch: ") + wsr_last_error());
+  if (p.rc != 0) Fatal(std::string("search batch failed: ") + p.err);
   for (int i = 0; i < p.n_hits; i++) {
     SearchResultEntry e;
     e.doc_id = p.hits[i].doc_id;
@@ -152,16 +207,87 @@ void GpuVacuumEngine::RunBatch(const std::vector<Pending *> &take) {
   n_hits.assign(qs.size(), 0);
   const int rc = wsr_search_batch(idx_, qs.data(), (int)qs.size(), (int)k_stride, hits.data(),
                                   n_hits.data(), nullptr, nullptr);
+  const std::string msg = rc ? wsr_last_error() : "";   // this (the leader's) thread's message
   for (size_t i = 0; i < take.size(); i++) {
     Pending *p = take[i];
     p->rc = rc;
+    p->err = msg;
     p->n_hits = rc == 0 ? n_hits[i] : 0;
     for (int j = 0; j < p->n_hits; j++) p->hits[j] = hits[i * (size_t)k_stride + j];
   }
 }
 
+// Group mode: the coalesced queries travel as query-log text (one line each; a phrase in double
+// quotes) to wsr_group_search_log; a query asking for fewer results than the batch's k takes the
+// head of its list.
+void GpuVacuumEngine::RunGroupBatch(const std::vector<Pending *> &take) {
+  thread_local std::string text;
+  thread_local std::vector<wsr_hit> hits;
+  thread_local std::vector<int32_t> n_hits;
+  uint32_t k = 1;
+  text.clear();
+  for (Pending *p : take) {
+    if (p->q.k > k) k = p->q.k;
+    if (p->src->is_phrase) text += '"';
+    for (size_t t = 0; t < p->src->terms.size(); t++) {
+      if (t) text += ' ';
+      text += p->src->terms[t];
+    }
+    if (p->src->is_phrase) text += '"';
+    text += '\n';
+  }
+  hits.resize(take.size() * (size_t)k);
+  n_hits.assign(take.size(), 0);
+  int got = 0;
+  int rc = wsr_group_search_log(group_, text.data(), text.size(), (int)k, hits.data(), n_hits.data(), nullptr,
+                                nullptr, (int)take.size(), &got);
+  std::string msg = rc ? wsr_last_error() : "";
+  if (rc == 0 && got != (int)take.size()) { rc = WSR_ERR_ARG; msg = "query text produced a different number of lines"; }
+  for (size_t i = 0; i < take.size(); i++) {
+    Pending *p = take[i];
+    p->rc = rc;
+    p->err = msg;
+    p->n_hits = rc == 0 ? std::min<int32_t>(n_hits[i], (int32_t)p->q.k) : 0;
+    for (int j = 0; j < p->n_hits; j++) p->hits[j] = hits[i * (size_t)k + j];
+  }
+}
+
 std::vector<SearchResult> GpuVacuumEngine::SearchBatch(const std::vector<SearchQuery> &queries) {
   std::vector<SearchResult> out(queries.size());
+  if (group_) {
+    std::vector<Pending> pend(queries.size());
+    std::vector<Pending *> take;
+    for (size_t i = 0; i < queries.size(); i++) {
+      const SearchQuery &q = queries[i];
+      if (q.n_results <= 0 || q.terms.empty()) continue;
+      if (q.terms.size() > WSR_MAX_TERMS) Fatal("more than WSR_MAX_TERMS query terms");
+      bool ok = true;
+      std::vector<int> dfs;
+      for (const Term &t : q.terms) {
+        uint32_t df;
+        if (!LookupAnyPartition(t, &df)) { ok = false; break; }
+        dfs.push_back((int)df);
+      }
+      if (!ok) continue;
+      out[i].doc_freqs = dfs;
+      memset(&pend[i].q, 0, sizeof(wsr_query));
+      pend[i].q.k = (uint32_t)q.n_results;
+      pend[i].src = &q;
+      pend[i].hits.resize(q.n_results);
+      take.push_back(&pend[i]);
+    }
+    if (!take.empty()) RunGroupBatch(take);
+    for (size_t i = 0; i < queries.size(); i++) {
+      if (pend[i].rc != 0) Fatal(std::string("search batch failed: ") + pend[i].err);
+      for (int j = 0; j < pend[i].n_hits; j++) {
+        SearchResultEntry e;
+        e.doc_id = pend[i].hits[j].doc_id;
+        e.doc_score = pend[i].hits[j].score;
+        out[i].entries.push_back(e);
+      }
+    }
+    return out;
+  }
   std::vector<wsr_query> qs(queries.size());
   uint32_t k_stride = 1;
   for (size_t i = 0; i < queries.size(); i++) {

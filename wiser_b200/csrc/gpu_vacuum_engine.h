@@ -75,6 +75,13 @@ namespace wsr {
 
 struct GpuEngineOptions {
   int device = 0;
+  // Document-partitioned deployment behind the same seam: when partition_dirs is not
+  // empty the engine serves the partitions (one vacuum directory each, local doc ids) as ONE
+  // collection through the group API of wsr.h — spread evenly over `devices` (default: `device`),
+  // collection statistics exchanged by the library, per-partition top-k merged on the device and
+  // across devices over NCCL. engine_dir_path is then only a label.
+  std::vector<std::string> partition_dirs;
+  std::vector<int> devices;
   int shard = 0, n_shards = 1;       // document partition held by this engine
   int loader_threads = 0;            // 0 = all cores
   bool load_positions = true;        // position column in HBM: needed by phrase queries
@@ -111,16 +118,20 @@ class GpuVacuumEngine : public SearchEngineServiceNew {
   // ---- batch interface used by the replay driver
   std::vector<SearchResult> SearchBatch(const std::vector<SearchQuery> &queries);
   wsr_index *handle() const { return idx_; }
+  wsr_group *group() const { return group_; }
 
  private:
   struct Pending;
   bool ToWsrQuery(const SearchQuery &q, wsr_query *out) const;
   void RunBatch(const std::vector<Pending *> &take);
+  void RunGroupBatch(const std::vector<Pending *> &take);
+  bool LookupAnyPartition(const std::string &term, uint32_t *df) const;
 
   std::string dir_;
   int bloom_enable_factor_;
   GpuEngineOptions opt_;
-  wsr_index *idx_ = nullptr;
+  wsr_index *idx_ = nullptr;     // single-index mode; in group mode: partition 0 (borrowed from group_)
+  wsr_group *group_ = nullptr;
   // request coalescer
   std::mutex mu_;
   std::vector<Pending *> pending_;

@@ -65,6 +65,7 @@
 namespace wsr {
 
 constexpr int kBlock = 128;
+constexpr uint32_t kDecodeStageBytes = 8192;   // K1 streams the payload in stages of this size (kernels.cu)
 
 struct BlockInfo {       // 16 B, mirrors a device uint4
   uint32_t base_doc;

@@ -626,32 +626,53 @@ __device__ __forceinline__ void LoadTfs4(const uint4 *src, uint32_t tc, uint32_t
     t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
   }
 }
+__device__ __forceinline__ uint32_t ByteSum(uint32_t x) { return (uint32_t)__dp4a(x, 0x01010101u, 0u); }
+__device__ __forceinline__ uint32_t NibbleSum(uint32_t x) {
+  return ByteSum(x & 0x0f0f0f0fu) + ByteSum((x >> 4) & 0x0f0f0f0fu);
+}
 __device__ __forceinline__ PosRun PositionsOf(const DevIndexView &ix, uint32_t pos) {
-  const uint32_t blk = pos >> 7, slot = pos & 127u, rec = slot >> 2;
+  const uint32_t blk = pos >> 7, slot = pos & 127u, rec = slot >> 2, grp = rec >> 2;
   const uint4 info = __ldg(&ix.blk_info[blk]);
   const uint32_t first = __ldg(&ix.blk_pos[blk]);
-  const uint32_t grp = rec >> 2;
   uint32_t before = grp ? (uint32_t)__ldg(&ix.grp_pos[(size_t)blk * 8u + grp]) : 0u;
   const uint32_t bits = info.z, tc = ShTcode(bits);
   const uint4 *src = ix.payload + info.y + DocGranules(bits);
-  uint32_t t[4];
-  uint32_t r0 = grp << 2;   // the tfs of the (at most three) records before `rec` in its group
-  if (before == 0xFFFFu) {   // block with >= 65535 positions: sum from the block's first record
-    before = 0;
-    r0 = 0;
-  }
-  for (uint32_t r = r0; r < rec; r++) {
-    LoadTfs4(src, tc, r, t);
-    before += t[0] + t[1] + t[2] + t[3];
-  }
-  LoadTfs4(src, tc, rec, t);
-  const uint32_t s = slot & 3u;
-  before += (s > 0 ? t[0] : 0u) + (s > 1 ? t[1] : 0u) + (s > 2 ? t[2] : 0u);
+  const uint32_t r = rec & 3u, sl = slot & 3u;
   PosRun run;
+  if (before != 0xFFFFu && tc == 0u) {
+    // the group's four tf records (4 x 4 nibbles) in one 8-byte load; positions before the
+    // posting inside its group = sum of the nibbles below it
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(src) + grp);
+    uint32_t w = v.x, nb = 16u * r + 4u * sl;
+    if (nb >= 32u) { before += NibbleSum(w); w = v.y; nb -= 32u; }
+    before += NibbleSum(w & ((1u << nb) - 1u));
+    run.n = (w >> nb) & 15u;
+  } else if (before != 0xFFFFu && tc == 1u) {
+    // four records of four bytes: one 16-byte load
+    const uint4 v = __ldg(src + grp);
+    const uint32_t w = r == 0u ? v.x : r == 1u ? v.y : r == 2u ? v.z : v.w;
+    before += (r > 0u ? ByteSum(v.x) : 0u) + (r > 1u ? ByteSum(v.y) : 0u) + (r > 2u ? ByteSum(v.z) : 0u);
+    before += ByteSum(w & ((1u << (8u * sl)) - 1u));
+    run.n = (w >> (8u * sl)) & 255u;
+  } else {
+    // 32-bit tfs, or a block with >= 65535 positions (prefixes not stored): walk the tf records
+    uint32_t t[4];
+    uint32_t r0 = grp << 2;
+    if (before == 0xFFFFu) {
+      before = 0;
+      r0 = 0;
+    }
+    for (uint32_t q = r0; q < rec; q++) {
+      LoadTfs4(src, tc, q, t);
+      before += t[0] + t[1] + t[2] + t[3];
+    }
+    LoadTfs4(src, tc, rec, t);
+    before += (sl > 0 ? t[0] : 0u) + (sl > 1 ? t[1] : 0u) + (sl > 2 ? t[2] : 0u);
+    run.n = sl == 0 ? t[0] : sl == 1 ? t[1] : sl == 2 ? t[2] : t[3];
+  }
   const size_t at = (size_t)first + before;
   run.p = ix.pos16 ? static_cast<const void *>(reinterpret_cast<const unsigned short *>(ix.positions) + at)
                    : static_cast<const void *>(reinterpret_cast<const uint32_t *>(ix.positions) + at);
-  run.n = s == 0 ? t[0] : s == 1 ? t[1] : s == 2 ? t[2] : t[3];
   return run;
 }
 // exists p in a with p + 1 in b
@@ -1544,88 +1565,205 @@ DecodeListKernel(const DevIndexView ix, uint32_t first_block, uint32_t n_blocks,
   }
 }
 
-// Whole-index decode (K1 roofline kernel): a pure stream over blk_info and the payload. A warp
-// takes U consecutive blocks per step and issues all of their metadata loads, then all of their
-// record loads, before decoding any. The kernel was 70 % issue-bound at 130 warp instructions per
-// block (round 1: run-time format dispatch per field, eight predicated 64-bit checksum adds), so
-// the decode below is written for instruction count: one uniform branch per block picks the
-// record format, the common 32/64-bit formats extract their fields with funnel shifts, the four
-// doc ids and the four tfs of a lane are summed in 32 bits (doc ids are < 2^31 and are added in
-// pairs, tfs are < 2^20) and enter the 64-bit checksum with three adds, and the "slot < n" tests
-// run only for a list's last, partial block.
-template <int U>
-__device__ __forceinline__ void DecodeAllStep(const DevIndexView &ix, uint32_t b, uint32_t n_blocks, int lane,
-                                              unsigned long long &sum) {
-  uint4 info[U];
-  uint2 rd[U];
-  uint32_t rt[U];
-#pragma unroll
-  for (int u = 0; u < U; u++)
-    info[u] = b + u < n_blocks ? __ldg(&ix.blk_info[b + u]) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-  for (int u = 0; u < U; u++) {
-    // 32/64-bit doc records and 4/8-bit tf records; the wide formats are read where they are decoded
-    const uint32_t bits = info[u].z, rc = ShRcode(bits), tc = ShTcode(bits);
-    const bool on = b + u < n_blocks && (uint32_t)lane < ((ShN(bits) + 3u) >> 2);
-    const uint4 *src = ix.payload + info[u].y;
-    rd[u] = make_uint2(0u, 0u);
-    rt[u] = 0u;
-    if (on) {
-      if (rc == 1u) rd[u] = __ldg(reinterpret_cast<const uint2 *>(src) + lane);
-      else if (rc == 0u) rd[u].x = __ldg(reinterpret_cast<const uint32_t *>(src) + lane);
-      const uint4 *ts = src + DocGranules(bits);
-      if (tc == 0u) rt[u] = __ldg(reinterpret_cast<const unsigned short *>(ts) + lane);
-      else if (tc == 1u) rt[u] = __ldg(reinterpret_cast<const uint32_t *>(ts) + lane);
+// ---- K1, whole-index decode: a pure stream over blk_info and the payload -------------------------
+// Round 1 walked the blocks with per-lane LDGs behind a dependent blk_info load (70 % issue-bound at
+// 130 warp instructions per block, two exposed round trips per step). This version is a bulk-copy
+// pipeline: the payload is cut into fixed 8 KB stages (+ 1 KB of overlap, the largest block), a
+// persistent CTA streams its stages — payload bytes and the blk_info rows of the blocks that START
+// in the stage — into a 4-deep shared-memory ring with cp.async.bulk, completion signalled on an
+// mbarrier per slot, and its warps decode the staged blocks from shared memory. No global load, no
+// address arithmetic on 64-bit pointers and no load latency is left in the decode loop.
+constexpr uint32_t kK1StageBytes = 8192;                 // host_index.h kDecodeStageBytes
+constexpr uint32_t kK1Overlap = 1024;                    // 32 x 16 B doc records + 32 x 16 B tf records
+constexpr uint32_t kK1MaxBlocks = kK1StageBytes / 32u;   // a block has at least 16 + 16 payload bytes
+constexpr int kK1Depth = 4;
+struct __align__(128) K1Slot {
+  uint4 pay[(kK1StageBytes + kK1Overlap) / 16];
+  uint4 info[kK1MaxBlocks];
+};
+struct __align__(128) K1Shared {
+  K1Slot slot[kK1Depth];
+  unsigned long long full[kK1Depth];   // mbarriers: the slot's bytes have landed
+  uint32_t done[kK1Depth];             // warps of the CTA that finished reading the slot
+};
+
+__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void MbarInit(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void MbarExpectTx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void MbarWait(unsigned long long *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(SmemAddr(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP): 16-byte aligned, size a multiple of 16
+__device__ __forceinline__ void BulkLoad(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(SmemAddr(dst)), "l"(src), "r"(bytes), "r"(SmemAddr(bar)) : "memory");
+}
+
+// One staged record: doc ids and tfs of the four postings of record `rec` of the block described
+// by `info`, whose payload starts at `pay` in shared memory; slots past the block's n come back as
+// zeros. Written for instruction count: sequential funnel shifts walk the fields of the 32/64/96/
+// 128-bit record formats (w0, b <= 31: doc ids are < 2^31), the four tfs come out of one word.
+__device__ __forceinline__ void K1DecodeRecord(const uint4 info, const uint4 *pay, uint32_t rec,
+                                               uint32_t d[4], uint32_t t[4]) {
+  const uint32_t bits = info.z, n = ShN(bits), rc = ShRcode(bits), tc = ShTcode(bits);
+  const uint32_t w0 = ShW0(bits), bw = ShB(bits);
+  const uint32_t m0 = 0xffffffffu >> (32u - w0), mb = 0xffffffffu >> (32u - bw);
+  uint32_t f, d1, d2, d3;
+  if (rc <= 1u) {
+    uint32_t lo, hi = 0u;
+    if (rc == 1u) {
+      const uint2 v = reinterpret_cast<const uint2 *>(pay)[rec];
+      lo = v.x; hi = v.y;
+    } else {
+      lo = reinterpret_cast<const uint32_t *>(pay)[rec];
     }
+    f = lo & m0;
+    lo = __funnelshift_r(lo, hi, w0); hi >>= w0;
+    d1 = lo & mb;
+    lo = __funnelshift_r(lo, hi, bw); hi >>= bw;
+    d2 = lo & mb;
+    lo = __funnelshift_r(lo, hi, bw);
+    d3 = lo & mb;
+  } else {
+    uint32_t x0, x1, x2, x3 = 0u;
+    if (rc == 2u) {
+      const uint4 v = pay[rec];
+      x0 = v.x; x1 = v.y; x2 = v.z; x3 = v.w;
+    } else {
+      const uint32_t *w = reinterpret_cast<const uint32_t *>(pay) + 3u * rec;
+      x0 = w[0]; x1 = w[1]; x2 = w[2];
+    }
+    f = x0 & m0;
+    x0 = __funnelshift_r(x0, x1, w0); x1 = __funnelshift_r(x1, x2, w0); x2 = __funnelshift_r(x2, x3, w0); x3 >>= w0;
+    d1 = x0 & mb;
+    x0 = __funnelshift_r(x0, x1, bw); x1 = __funnelshift_r(x1, x2, bw); x2 = __funnelshift_r(x2, x3, bw);
+    d2 = x0 & mb;
+    x0 = __funnelshift_r(x0, x1, bw);
+    d3 = x0 & mb;
   }
+  d[0] = info.x + f;
+  d[1] = d[0] + d1;
+  d[2] = d[1] + d2;
+  d[3] = d[2] + d3;
+  const uint4 *ts = pay + DocGranules(bits);
+  if (tc == 0u) {
+    const uint32_t v = reinterpret_cast<const unsigned short *>(ts)[rec];
+    t[0] = v & 15u; t[1] = (v >> 4) & 15u; t[2] = (v >> 8) & 15u; t[3] = v >> 12;
+  } else if (tc == 1u) {
+    const uint32_t v = reinterpret_cast<const uint32_t *>(ts)[rec];
+    t[0] = v & 255u; t[1] = (v >> 8) & 255u; t[2] = (v >> 16) & 255u; t[3] = v >> 24;
+  } else {
+    const uint4 v = ts[rec];
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+  if (4u * rec + 4u > n) {   // the block's last, partial record: slots past n repeat the last posting
 #pragma unroll
-  for (int u = 0; u < U; u++) {
-    if (b + u >= n_blocks) continue;
-    const uint32_t bits = info[u].z, n = ShN(bits), rc = ShRcode(bits), tc = ShTcode(bits);
-    uint32_t d[4], t[4];
-    if (rc <= 1u) {
-      // [f:w0][d1:b][d2:b][d3:b] in 64 bits, LSB first: three funnel shifts
-      const uint32_t w0 = ShW0(bits), bw = ShB(bits);
-      const uint32_t mb = 0xffffffffu >> (32u - bw);
-      const uint32_t f = rd[u].x & (0xffffffffu >> (32u - w0));
-      const uint32_t s1 = w0, s2 = w0 + bw, s3 = s2 + bw;
-      const uint32_t d1 = (s1 < 32u ? __funnelshift_r(rd[u].x, rd[u].y, s1) : rd[u].y >> (s1 - 32u)) & mb;
-      const uint32_t d2 = (s2 < 32u ? __funnelshift_r(rd[u].x, rd[u].y, s2) : rd[u].y >> (s2 - 32u)) & mb;
-      const uint32_t d3 = (s3 < 32u ? __funnelshift_r(rd[u].x, rd[u].y, s3) : rd[u].y >> (s3 - 32u)) & mb;
-      d[0] = info[u].x + f;
-      d[1] = d[0] + d1;
-      d[2] = d[1] + d2;
-      d[3] = d[2] + d3;
-    } else {
-      d[0] = d[1] = d[2] = d[3] = 0u;
-      if ((uint32_t)lane < ((n + 3u) >> 2)) DecodeRecord(ix, info[u], (uint32_t)lane, d);
-    }
-    if (tc == 0u) {
-      t[0] = rt[u] & 15u; t[1] = (rt[u] >> 4) & 15u; t[2] = (rt[u] >> 8) & 15u; t[3] = rt[u] >> 12;
-    } else if (tc == 1u) {
-      t[0] = rt[u] & 255u; t[1] = (rt[u] >> 8) & 255u; t[2] = (rt[u] >> 16) & 255u; t[3] = rt[u] >> 24;
-    } else {
-      DecodeTfs(ix, info[u], lane, t);
-    }
-    if (n != 128u) {   // a list's last block: slots past n do not count (they repeat the last posting)
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-        if (4u * lane + i >= n) { d[i] = 0u; t[i] = 0u; }
-    }
-    sum += (unsigned long long)(d[0] + d[1]);
-    sum += (unsigned long long)(d[2] + d[3]);
-    sum += (unsigned long long)(t[0] + t[1] + t[2] + t[3]);
+    for (int i = 0; i < 4; i++)
+      if (4u * rec + i >= n) { d[i] = 0u; t[i] = 0u; }
   }
 }
 
 __global__ void __launch_bounds__(kThreadsPerCta)
 DecodeAllKernel(const DevIndexView ix, uint32_t n_blocks, unsigned long long *checksum) {
-  constexpr int U = 4;
-  const int lane = threadIdx.x & 31;
-  const uint32_t warps = gridDim.x * kWarpsPerCta;
-  const uint32_t w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  extern __shared__ __align__(128) unsigned char k1_smem[];
+  K1Shared *sh = reinterpret_cast<K1Shared *>(k1_smem);
+  const uint32_t tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_stages = ix.k1_stages;
+  const unsigned long long pay_bytes = (unsigned long long)ix.payload_granules * 16ull;
+  if (tid == 0) {
+    for (int i = 0; i < kK1Depth; i++) {
+      MbarInit(&sh->full[i], 1u);
+      sh->done[i] = 0u;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // stage `it` of this CTA = global stage blockIdx.x + it * gridDim.x
+  auto issue = [&](uint32_t it) {
+    const unsigned long long stage = (unsigned long long)blockIdx.x + (unsigned long long)it * gridDim.x;
+    if (stage >= n_stages) return;
+    const uint32_t f0 = __ldg(&ix.k1_stage_first[stage]), f1 = __ldg(&ix.k1_stage_first[stage + 1]);
+    if (f1 == f0) return;   // no block starts in this stage (only the tail padding can do that)
+    const unsigned long long off = stage * kK1StageBytes;
+    const uint32_t pb = (uint32_t)min((unsigned long long)(kK1StageBytes + kK1Overlap), pay_bytes - off);
+    const uint32_t ib = (f1 - f0) * 16u;
+    K1Slot &sl = sh->slot[it % kK1Depth];
+    MbarExpectTx(&sh->full[it % kK1Depth], pb + ib);
+    BulkLoad(sl.pay, reinterpret_cast<const unsigned char *>(ix.payload) + off, pb, &sh->full[it % kK1Depth]);
+    BulkLoad(sl.info, ix.blk_info + f0, ib, &sh->full[it % kK1Depth]);
+  };
+  if (tid == 0)
+    for (uint32_t it = 0; it < (uint32_t)kK1Depth; it++) issue(it);
   unsigned long long sum = 0;
-  for (uint32_t b = w * U; b < n_blocks; b += warps * U) DecodeAllStep<U>(ix, b, n_blocks, lane, sum);
+  uint32_t phase_bits = 0;   // per slot: parity of the phase to wait for next
+  for (uint32_t it = 0;; it++) {
+    const unsigned long long stage = (unsigned long long)blockIdx.x + (unsigned long long)it * gridDim.x;
+    if (stage >= n_stages) break;
+    const uint32_t f0 = __ldg(&ix.k1_stage_first[stage]), f1 = __ldg(&ix.k1_stage_first[stage + 1]);
+    const int slot = it % kK1Depth;
+    const uint32_t nblk = f1 - f0;   // 0 only for a stage made of tail padding: nothing was copied
+    if (nblk) {
+      MbarWait(&sh->full[slot], (phase_bits >> slot) & 1u);
+      phase_bits ^= 1u << slot;
+    }
+    const K1Slot &sl = sh->slot[slot];
+    const uint32_t base16 = (uint32_t)(stage * (kK1StageBytes / 16u));
+    // A warp takes 4 consecutive blocks per step. Short blocks (at most 8 records: the single-block
+    // lists that make up 40 % of all blocks) are decoded four at a time, one per group of 8 lanes;
+    // a step that holds a longer block decodes its blocks one after the other with all 32 lanes.
+    for (uint32_t j0 = 4u * (uint32_t)warp; j0 < nblk; j0 += 4u * kWarpsPerCta) {
+      const uint32_t jg = min(j0 + ((uint32_t)lane >> 3), nblk - 1u);
+      const uint4 ig = sl.info[jg];
+      const uint32_t nlg = (ShN(ig.z) + 3u) >> 2;
+      const bool in_range = j0 + ((uint32_t)lane >> 3) < nblk;
+      if (__all_sync(kFull, nlg <= 8u || !in_range)) {
+        const uint32_t rec = (uint32_t)lane & 7u;
+        if (in_range && rec < nlg) {
+          uint32_t d[4], t[4];
+          K1DecodeRecord(ig, sl.pay + (ig.y - base16), rec, d, t);
+          sum += (unsigned long long)(d[0] + d[1]);
+          sum += (unsigned long long)(d[2] + d[3]);
+          sum += (unsigned long long)(t[0] + t[1] + t[2] + t[3]);
+        }
+      } else {
+        const uint32_t jend = min(j0 + 4u, nblk);
+        for (uint32_t j = j0; j < jend; j++) {
+          const uint4 info = sl.info[j];
+          if ((uint32_t)lane < ((ShN(info.z) + 3u) >> 2)) {
+            uint32_t d[4], t[4];
+            K1DecodeRecord(info, sl.pay + (info.y - base16), (uint32_t)lane, d, t);
+            sum += (unsigned long long)(d[0] + d[1]);
+            sum += (unsigned long long)(d[2] + d[3]);
+            sum += (unsigned long long)(t[0] + t[1] + t[2] + t[3]);
+          }
+        }
+      }
+    }
+    // the warp is done with the slot; the last of the CTA's warps to get here refills it (no
+    // CTA-wide barrier: warps drift apart by up to the depth of the ring)
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&sh->done[slot], 1u) == (uint32_t)kWarpsPerCta - 1u) {
+        sh->done[slot] = 0u;
+        __threadfence_block();
+        issue(it + kK1Depth);
+      }
+    }
+  }
 #pragma unroll
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(kFull, sum, o);
   if (lane == 0 && sum) atomicAdd(checksum, sum);
@@ -1811,10 +1949,16 @@ void LaunchDecodeList(const DevIndexView &ix, uint32_t first_block, uint32_t n_b
 
 void LaunchDecodeAll(const DevIndexView &ix, uint32_t n_blocks, unsigned long long *checksum,
                      int sm_count, cudaStream_t s) {
-  if (!n_blocks) return;
-  const uint32_t grid = std::min<uint32_t>((n_blocks + kWarpsPerCta - 1) / kWarpsPerCta,
-                                           (uint32_t)(sm_count * 8));
-  DecodeAllKernel<<<grid, kThreadsPerCta, 0, s>>>(ix, n_blocks, checksum);
+  if (!n_blocks || !ix.k1_stages) return;
+  static int occ = 0;
+  if (!occ) {
+    int o = 0;
+    cudaFuncSetAttribute(DecodeAllKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Shared));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, DecodeAllKernel, kThreadsPerCta, sizeof(K1Shared));
+    occ = o > 0 ? o : 1;
+  }
+  const uint32_t grid = std::min<uint32_t>(ix.k1_stages, (uint32_t)(sm_count * occ));
+  DecodeAllKernel<<<grid, kThreadsPerCta, sizeof(K1Shared), s>>>(ix, n_blocks, checksum);
 }
 
 void LaunchRefreshBlockMax(const DevIndexView &ix, uint32_t n_blocks, uint4 *blk_info_rw,

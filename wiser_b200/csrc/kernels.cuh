@@ -42,6 +42,11 @@ struct DevIndexView {
   uint32_t doc_lo;            // first doc id held by this shard (filter origin)
   uint32_t n_filter_words;    // length of filters[] (bound for look-ahead prefetches)
   uint32_t merge_ratio_x4;    // planner rule for the two-term merge path (UseMergePath)
+  // K1 (whole-index decode): the payload cut into kDecodeStageBytes stages; k1_stage_first[s] = first
+  // block whose payload starts in stage s (k1_stages + 1 entries)
+  const uint32_t *k1_stage_first;
+  uint32_t k1_stages;
+  uint32_t payload_granules;  // 16-byte granules of payload[] (tail padding included)
 };
 
 // One planned query. unit_begin = index of its first work unit in its class queue.

@@ -170,6 +170,7 @@ struct wsr_index {
   DevBuf<float> d_blk_max;
   DevBuf<uint32_t> d_filters;
   DevBuf<uint2> d_list_flt;
+  DevBuf<uint32_t> d_k1_first;    // K1 stage table (DevIndexView::k1_stage_first)
   DevBuf<uint32_t> d_positions, d_blk_pos;   // d_positions holds u16 entries when view.pos16
   DevBuf<uint16_t> d_grp_pos;
   // device copy of the term dictionary for the query-log front end (frontend.cu)
@@ -696,6 +697,25 @@ wsr_index *wsr_index_open_ex(const char *vacuum_dir, int device, int shard, int 
   v.n_docs = (uint32_t)h.n_docs;
   v.doc_lo = (uint32_t)h.doc_lo;
   v.n_filter_words = (uint32_t)h.filters.size();
+  {
+    // K1 stage table: first block whose payload starts at or after s * kDecodeStageBytes
+    const uint64_t pay_bytes = (uint64_t)n_gran * 16;
+    const uint32_t n_stages = (uint32_t)((pay_bytes + kDecodeStageBytes - 1) / kDecodeStageBytes);
+    std::vector<uint32_t> first((size_t)n_stages + 1, (uint32_t)h.blk_info.size());
+    size_t b = 0;
+    for (uint32_t st = 0; st < n_stages; st++) {
+      const uint64_t lo16 = (uint64_t)st * (kDecodeStageBytes / 16);
+      while (b < h.blk_info.size() && h.blk_info[b].payload_off16 < lo16) b++;
+      first[st] = (uint32_t)b;
+    }
+    if (!cu(ix->d_k1_first.Ensure(first.size()), "cudaMalloc k1 stages") ||
+        !cu(cudaMemcpy(ix->d_k1_first.p, first.data(), first.size() * 4, cudaMemcpyHostToDevice), "H2D k1 stages"))
+      return fail(e);
+    v.k1_stage_first = ix->d_k1_first.p;
+    v.k1_stages = n_stages;
+    v.payload_granules = (uint32_t)n_gran;
+    ix->hbm_bytes += (int64_t)first.size() * 4;
+  }
   v.merge_ratio_x4 = kMergeRatioX4;
   if (const char *mr = getenv("WSR_MERGE_RATIO_X4")) v.merge_ratio_x4 = (uint32_t)std::max(0, atoi(mr));
   v.positions = nullptr;
