@@ -552,6 +552,7 @@ def ours_group(a, rank, world, local_rank):
     ev0.record(stream)
     for _ in range(a.steps):
         group.run()
+    group.join()                 # the last pass's exchange runs on its own stream: wait for it
     ev1.record(stream)
     sync_all()
     wall_ms = (time.perf_counter() - t_wall) * 1000.0

@@ -289,6 +289,11 @@ int wsr_group_search_log(wsr_group *g, const char *text, size_t len, int k, wsr_
  * device's leading stream (cudaStream_t) for CUDA-event timing. */
 int wsr_group_load_log(wsr_group *g, const char *text, size_t len, int k, int *n_queries);
 int wsr_group_run(wsr_group *g, int mode);
+/* wsr_group_run is pipelined across passes: the exchange of pass i runs on a stream of its own (from
+ * a staged copy of the local lists) while the search kernels of pass i+1 run on the leading
+ * stream. wsr_group_join makes the leading stream wait for the last exchange (call it before
+ * recording an end-of-region event there); wsr_group_fetch and wsr_group_sync join by themselves. */
+int wsr_group_join(wsr_group *g);
 int wsr_group_sync(wsr_group *g);
 int wsr_group_stream(wsr_group *g, void **stream);
 int wsr_group_fetch(wsr_group *g, wsr_hit *hits, int32_t *n_hits);

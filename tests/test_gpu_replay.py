@@ -82,3 +82,33 @@ def test_replay_driver_over_a_partitioned_group(golden_dir, tmp_path):
         assert len(set(gd.tolist())) == len(gd)
         for doc, sc in zip(gd.tolist(), gs.tolist()):
             assert doc in ref_score and np.isclose(ref_score[doc], sc, rtol=1e-12, atol=0), lines[i]
+
+
+def test_adapter_in_group_mode_serves_search_callers(golden_dir, tmp_path):
+    """GpuVacuumEngine with GpuEngineOptions::partition_dirs (the reference maintainer's multi-GPU
+    engine): 8 client threads call Search() on the two zipf2k partitions served as one collection;
+    doc ids, counts and doc_freqs equal the reference's on the whole index."""
+    import numpy as np
+    d = os.path.join(golden_dir, "zipf2k")
+    lines = [l for l in open(os.path.join(d, "queries.txt")).read().split("\n")[:-1]]
+    keep = [i for i, l in enumerate(lines) if not l.startswith('"')][:1500]
+    qpath = str(tmp_path / "q.txt")
+    with open(qpath, "w") as f:
+        f.write("\n".join(lines[i] for i in keep) + "\n")
+    out = str(tmp_path / "dump.txt")
+    dirs = ",".join(os.path.join(golden_dir, f"zipf2k_p{s}") for s in range(2))
+    log = subprocess.check_output([REPLAY, f"-dirs={dirs}", "-devices=0", f"-query_path={qpath}", "-n_results=10",
+                                   "-exp_mode=locallog", "-n_threads=8", f"-dump={out}"]).decode()
+    assert "WSR_REPLAY_JSON" in log
+    got = read_ref_results(out)
+    ref = read_ref_results(os.path.join(d, "ref_top10.txt.gz"))
+    full = read_ref_results(os.path.join(d, "ref_full.txt.gz"))
+    assert len(got) == len(keep)
+    for (gd, gs, gdf), i in zip(got, keep):
+        rd, rs, rdf = ref[i]
+        fd, fs, _ = full[i]
+        assert len(gd) == len(rd) and gdf == rdf, lines[i]
+        assert np.allclose(gs, rs, rtol=1e-12, atol=0), lines[i]
+        ref_score = dict(zip(fd.tolist(), fs.tolist()))
+        for doc, sc in zip(gd.tolist(), gs.tolist()):
+            assert doc in ref_score and np.isclose(ref_score[doc], sc, rtol=1e-12, atol=0), lines[i]

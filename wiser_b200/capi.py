@@ -46,7 +46,7 @@ EXPORTS = [
     "wsr_search_log_ex", "wsr_comm_unique_id", "wsr_comm_init_rank", "wsr_comm_destroy", "wsr_batch_exchange",
     "wsr_batch_exchanged_results", "wsr_batch_fetch_exchanged", "wsr_group_open", "wsr_group_close",
     "wsr_group_n_parts", "wsr_group_part", "wsr_group_search_log", "wsr_group_load_log", "wsr_group_run",
-    "wsr_group_sync", "wsr_group_stream", "wsr_group_fetch", "wsr_group_stats",
+    "wsr_group_sync", "wsr_group_join", "wsr_group_stream", "wsr_group_fetch", "wsr_group_stats",
 ]
 
 WSR_COMM_ID_BYTES = 128
@@ -123,6 +123,7 @@ def lib():
     L.wsr_group_load_log.argtypes = [vp, vp, sz, C.c_int, C.POINTER(C.c_int)]
     L.wsr_group_run.argtypes = [vp, C.c_int]
     L.wsr_group_sync.argtypes = [vp]
+    L.wsr_group_join.argtypes = [vp]
     L.wsr_group_stream.argtypes = [vp, C.POINTER(vp)]
     L.wsr_group_fetch.argtypes = [vp, vp, vp]
     L.wsr_group_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),

@@ -1599,11 +1599,11 @@ __device__ __forceinline__ void MbarWait(unsigned long long *bar, uint32_t parit
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"   // %2: suspend-time hint, the warp
+      "@p bra WAIT_DONE;\n"                                            // sleeps in hardware instead of
+      "bra WAIT_LOOP;\n"                                               // spinning on issue slots
       "WAIT_DONE:\n"
-      "}\n" ::"r"(SmemAddr(bar)), "r"(parity) : "memory");
+      "}\n" ::"r"(SmemAddr(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP): 16-byte aligned, size a multiple of 16
 __device__ __forceinline__ void BulkLoad(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {

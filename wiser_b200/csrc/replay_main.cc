@@ -177,8 +177,19 @@ int main(int argc, char **argv) {
     return 1;
   }
   const std::string dirs_flag = FlagStr(argc, argv, "dirs", "");
-  if (!dirs_flag.empty()) return ReplayGroup(argc, argv, dirs_flag, text, n_results, batch_size, repeat, dump);
-  std::unique_ptr<SearchEngineServiceNew> engine = wsr::CreateSearchEngine(engine_url);
+  if (!dirs_flag.empty() && mode != "locallog")
+    return ReplayGroup(argc, argv, dirs_flag, text, n_results, batch_size, repeat, dump);
+  std::unique_ptr<SearchEngineServiceNew> engine;
+  if (!dirs_flag.empty()) {
+    // Search() callers over a partitioned collection: the adapter in group mode
+    wsr::GpuEngineOptions opt;
+    opt.partition_dirs = Split(dirs_flag, ',');
+    for (const std::string &d : Split(FlagStr(argc, argv, "devices", "0"), ',')) opt.devices.push_back(atoi(d.c_str()));
+    opt.load_positions = false;
+    engine.reset(new wsr::GpuVacuumEngine("group", 1, opt));
+  } else {
+    engine = wsr::CreateSearchEngine(engine_url);
+  }
   const auto t_load = std::chrono::steady_clock::now();
   engine->Load();
   const double load_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load).count();

@@ -287,6 +287,13 @@ struct GroupDevice {
   const int32_t *res_n = nullptr;
   const uint32_t *res_df = nullptr;
   const int32_t *res_ndf = nullptr;
+  // pipelined runs (wsr_group_run): the exchange of pass i runs on its own stream, from a staged
+  // copy of the local lists, while the search kernels of pass i+1 run on the leading stream
+  cudaStream_t xstream = nullptr;
+  cudaEvent_t ev_staged = nullptr, ev_xdone = nullptr;
+  DevBuf<wsr_hit> stage_hits;
+  DevBuf<int32_t> stage_n;
+  bool x_pending = false;                 // an exchange on xstream has not been joined yet
   int rc = 0;
   std::string err;
 };
@@ -366,7 +373,7 @@ void GroupLoadOn(wsr_group *g, GroupDevice &d, const char *text, size_t len, int
 }
 
 // Enqueues one pass on a device: search kernels of every local partition, local merge, exchange.
-void GroupRunOn(wsr_group *g, GroupDevice &d, int mode, bool with_df) {
+void GroupRunOn(wsr_group *g, GroupDevice &d, int mode, bool with_df, bool pipelined) {
   d.rc = 0;
   auto fail = [&](int rc) { d.rc = rc; d.err = g_err; };
   if (cudaSetDevice(d.device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return fail(WSR_ERR_CUDA); }
@@ -439,8 +446,28 @@ void GroupRunOn(wsr_group *g, GroupDevice &d, int mode, bool with_df) {
     loc_hits = d.loc_hits.p;
     loc_n = d.loc_n.p;
   }
-  const int rc = ExchangeOnStream(d.comm, loc_hits, loc_n, n, k, lead->stream, mode, loc_df, loc_ndf);
-  if (rc) return fail(rc);
+  int rc;
+  if (pipelined && d.comm->world > 1 && !with_df) {
+    // stage the local lists (a device-to-device copy of n*k*16 B), hand the exchange to its own
+    // stream and return: the next pass's search kernels overlap this pass's exchange. The staging
+    // copy waits for the previous exchange, which still reads the staging buffers.
+    if (!cu(d.stage_hits.Ensure((size_t)n * k + 1), "cudaMalloc") || !cu(d.stage_n.Ensure((size_t)n + 1), "cudaMalloc")) return;
+    if (d.x_pending && !cu(cudaStreamWaitEvent(lead->stream, d.ev_xdone, 0), "cudaStreamWaitEvent")) return;
+    if (!cu(cudaMemcpyAsync(d.stage_hits.p, loc_hits, (size_t)n * k * sizeof(wsr_hit), cudaMemcpyDeviceToDevice, lead->stream), "D2D stage") ||
+        !cu(cudaMemcpyAsync(d.stage_n.p, loc_n, (size_t)n * 4, cudaMemcpyDeviceToDevice, lead->stream), "D2D stage") ||
+        !cu(cudaEventRecord(d.ev_staged, lead->stream), "cudaEventRecord") ||
+        !cu(cudaStreamWaitEvent(d.xstream, d.ev_staged, 0), "cudaStreamWaitEvent"))
+      return;
+    rc = ExchangeOnStream(d.comm, d.stage_hits.p, d.stage_n.p, n, k, d.xstream, mode);
+    if (rc) return fail(rc);
+    if (!cu(cudaEventRecord(d.ev_xdone, d.xstream), "cudaEventRecord")) return;
+    d.x_pending = true;
+  } else {
+    if (d.x_pending && !cu(cudaStreamWaitEvent(lead->stream, d.ev_xdone, 0), "cudaStreamWaitEvent")) return;
+    d.x_pending = false;
+    rc = ExchangeOnStream(d.comm, loc_hits, loc_n, n, k, lead->stream, mode, loc_df, loc_ndf);
+    if (rc) return fail(rc);
+  }
   d.res_hits = d.comm->res_hits;
   d.res_n = d.comm->res_n;
   d.res_df = d.comm->res_df;
@@ -470,6 +497,9 @@ wsr_group *wsr_group_open(const char *const *dirs, int n_dirs, const int *device
     for (GroupDevice &d : g->devs) {
       for (wsr_batch *b : d.batches) FreeBatch(b);
       for (cudaEvent_t e : d.done) if (e) cudaEventDestroy(e);
+      if (d.xstream) cudaStreamDestroy(d.xstream);
+      if (d.ev_staged) cudaEventDestroy(d.ev_staged);
+      if (d.ev_xdone) cudaEventDestroy(d.ev_xdone);
       if (d.comm) wsr_comm_destroy(d.comm);
     }
     for (wsr_index *ix : g->parts) wsr_index_close(ix);
@@ -548,6 +578,13 @@ wsr_group *wsr_group_open(const char *const *dirs, int n_dirs, const int *device
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cleanup(); return fail("cudaEventCreate failed"); }
       d.done.push_back(e);
     }
+    cudaSetDevice(d.device);
+    if (cudaStreamCreateWithFlags(&d.xstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.ev_staged, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&d.ev_xdone, cudaEventDisableTiming) != cudaSuccess) {
+      cleanup();
+      return fail("cannot create the exchange stream");
+    }
   }
   // exchange ranks: the devices of this process are consecutive ranks starting at rank0
   g->world = dist && dist->world > 1 ? dist->world : n_dev;
@@ -582,8 +619,12 @@ void wsr_group_close(wsr_group *g) {
   for (std::thread &t : g->workers) t.join();
   for (GroupDevice &d : g->devs) {
     cudaSetDevice(d.device);
+    if (d.xstream) cudaStreamSynchronize(d.xstream);
     for (wsr_batch *b : d.batches) FreeBatch(b);
     for (cudaEvent_t e : d.done) if (e) cudaEventDestroy(e);
+    if (d.xstream) cudaStreamDestroy(d.xstream);
+    if (d.ev_staged) cudaEventDestroy(d.ev_staged);
+    if (d.ev_xdone) cudaEventDestroy(d.ev_xdone);
     if (d.comm) wsr_comm_destroy(d.comm);
   }
   for (wsr_index *ix : g->parts) wsr_index_close(ix);
@@ -614,8 +655,19 @@ int wsr_group_load_log(wsr_group *g, const char *text, size_t len, int k, int *n
 
 int wsr_group_run(wsr_group *g, int mode) {
   if (!g || !g->loaded || mode < 0 || mode > 1) return Fail(WSR_ERR_ARG, "no log loaded");
-  g->RunOnDevices([&](GroupDevice &d, int) { GroupRunOn(g, d, mode, false); });
+  g->RunOnDevices([&](GroupDevice &d, int) { GroupRunOn(g, d, mode, false, true); });
   return GroupFirstError(g);
+}
+
+int wsr_group_join(wsr_group *g) {
+  if (!g) return Fail(WSR_ERR_ARG, "null group");
+  for (GroupDevice &d : g->devs) {
+    if (!d.x_pending) continue;
+    CU(cudaSetDevice(d.device));
+    CU(cudaStreamWaitEvent(d.batches[0]->stream, d.ev_xdone, 0));
+    d.x_pending = false;
+  }
+  return WSR_OK;
 }
 
 int wsr_group_sync(wsr_group *g) {
@@ -623,6 +675,7 @@ int wsr_group_sync(wsr_group *g) {
   for (GroupDevice &d : g->devs) {
     CU(cudaSetDevice(d.device));
     for (wsr_batch *b : d.batches) CU(cudaStreamSynchronize(b->stream));
+    CU(cudaStreamSynchronize(d.xstream));
   }
   return WSR_OK;
 }
@@ -637,6 +690,7 @@ int wsr_group_fetch(wsr_group *g, wsr_hit *hits, int32_t *n_hits) {
   if (!g || !g->loaded || !hits || !n_hits) return Fail(WSR_ERR_ARG, "bad argument");
   GroupDevice &d = g->devs[0];
   if (!d.res_hits) return Fail(WSR_ERR_ARG, "wsr_group_run has not run");
+  { const int jrc = wsr_group_join(g); if (jrc) return jrc; }
   CU(cudaSetDevice(d.device));
   wsr_batch *lead = d.batches[0];
   const size_t nh = (size_t)g->n * g->k;
@@ -684,7 +738,7 @@ int wsr_group_search_log(wsr_group *g, const char *text, size_t len, int k, wsr_
   // of a multi-process job must make the same choice, so they always travel when k allows it.
   const bool with_df = k <= kMaxFastK;
   if (doc_freqs && !with_df) return Fail(WSR_ERR_UNSUPPORTED, "doc_freqs of a group need the device front end (k <= 32)");
-  g->RunOnDevices([&](GroupDevice &d, int) { GroupRunOn(g, d, 0, with_df); });
+  g->RunOnDevices([&](GroupDevice &d, int) { GroupRunOn(g, d, 0, with_df, false); });
   rc = GroupFirstError(g);
   if (rc) return rc;
   if (!hits) {   // a rank of a multi-process job that does not face the client: search + exchange only

@@ -238,6 +238,10 @@ class ShardGroup:
     def sync(self):
         check(lib().wsr_group_sync(self._g))
 
+    def join(self):
+        """The leading stream waits for the last (pipelined) exchange: call before an end event."""
+        check(lib().wsr_group_join(self._g))
+
     def stream(self):
         s = C.c_void_p(0)
         check(lib().wsr_group_stream(self._g, C.byref(s)))
