@@ -164,8 +164,9 @@ int wsr_search_batch(wsr_index *idx, const wsr_query *queries, int n, int k_stri
  * WSR_HOST_FRONTEND=1) parse and plan on host threads, in up to 4 chunks overlapped with the GPU.
  * hits: cap_q * k entries (query i at hits[i*k], entries past n_hits[i] unspecified); n_hits:
  * cap_q entries; *n_queries receives the number of log lines. Pinned buffers (wsr_host_alloc) are
- * written by DMA directly; logs whose results are sparse come back packed and are scattered into
- * hits[] by host threads. A line with more than WSR_MAX_TERMS terms fails the call. */
+ * written by the kernels themselves, a row when its query finishes (no result copy behind the
+ * kernels); other buffers are filled through a pinned stage (sparse results packed on the GPU
+ * first). A line with more than WSR_MAX_TERMS terms fails the call. */
 int wsr_search_log(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
                    int32_t *n_hits, int cap_q, int *n_queries);
 /* Same with SearchResult::doc_freqs (vacuum_engine.h:217-219): doc_freqs[i*WSR_MAX_TERMS + t] =

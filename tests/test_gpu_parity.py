@@ -471,3 +471,26 @@ def test_search_log_doc_freqs(engines):
     for i, r in enumerate(res):
         assert list(dfs[i, :ndf[i]]) == r.doc_freqs, lines[i]
         assert int(nh[i]) == len(r.entries)
+
+
+def test_search_log_zero_copy_equals_staged_results(engines):
+    """wsr_search_log_ex with pinned result buffers (the kernels write rows, counts and doc_freqs
+    straight into host memory) against the same call with pageable buffers (pinned stage + copy)."""
+    from wiser_b200.capi import HIT_DTYPE, WSR_MAX_TERMS, PinnedArray
+    eng, _, d = engines["zipf2k"]
+    text = open(os.path.join(d, "queries.txt"), "rb").read()
+    n = text.count(b"\n")
+    for k in (10, 3):
+        hp, cp = PinnedArray((n + 2, k), HIT_DTYPE), PinnedArray((n + 2,), np.int32)
+        dp, mp = PinnedArray((n + 2, WSR_MAX_TERMS), np.uint32), PinnedArray((n + 2,), np.int32)
+        hp.array["doc_id"][:] = -7     # stale contents must not leak into counted rows
+        cp.array[:] = 99
+        h1, c1 = eng.search_log(text, k, hp.array, cp.array, dp.array, mp.array)
+        hs, cs = np.zeros((n + 2, k), HIT_DTYPE), np.zeros(n + 2, np.int32)
+        ds, ms = np.zeros((n + 2, WSR_MAX_TERMS), np.uint32), np.zeros(n + 2, np.int32)
+        h2, c2 = eng.search_log(text, k, hs, cs, ds, ms)
+        assert len(c1) == len(c2) == n
+        _same_hits(h2, c2, h1, c1, k)
+        assert np.array_equal(mp.array[:n], ms[:n])
+        m = np.arange(WSR_MAX_TERMS)[None, :] < ms[:n, None]
+        assert np.array_equal(dp.array[:n][m], ds[:n][m])

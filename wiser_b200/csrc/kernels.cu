@@ -26,6 +26,7 @@
 #include "host_index.h"
 
 #include <algorithm>
+#include <cstddef>
 #include <cub/device/device_segmented_sort.cuh>
 
 namespace wsr {
@@ -39,6 +40,30 @@ constexpr double kK1Plus1 = 1.2 + 1;   // (k1_ + 1) evaluated in double, scoring
 #endif
 constexpr int kCandCap = 160;          // survivors: 31 carried over + up to 128 of one driver block
 constexpr int kHitCap = 64;            // hits: 31 queued + up to 32 of one probe batch
+
+// ---- shared memory through 32-bit shared-window addresses --------------------------------------
+// The scratch of a warp and the CTA's tables are reached through generic pointers handed down the
+// (inlined) call chain; ptxas converts such a pointer back to a shared-window address in front of
+// every access (S2R SR_CgaCtaId + MOV + LEA: 37 of the 574 warp instructions per driver block in
+// the round-2 profile of the two-term kernel). The hot accesses therefore use explicit ld/st.shared
+// on an address converted once per unit.
+__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t LdsU32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void StsU32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint2 LdsU64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void StsU64(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
 
 // ---- block shape (host_index.h PackShape) --------------------------------------------------
 __device__ __forceinline__ uint32_t ShW0(uint32_t b) { return (b & 31u) + 1u; }
@@ -465,6 +490,10 @@ __device__ __forceinline__ bool FilterTest(const CtaShared *sh, uint32_t w, uint
   const uint32_t need = sh->fpat[FilterIndex(doc)];   // host_index.h FilterBits
   return (w & need) == need;
 }
+__device__ __forceinline__ bool FilterTestS(uint32_t fpat_addr, uint32_t w, uint32_t doc) {
+  const uint32_t need = LdsU32(fpat_addr + 4u * FilterIndex(doc));
+  return (w & need) == need;
+}
 // Filter word of a candidate (all ones = "may be present" when the list has no filter). Slots past
 // a block's postings decode to docs inside the shard's range, so their word may be read as well.
 __device__ __forceinline__ uint32_t FilterWord(const DevIndexView &ix, const ListFilter &lf, uint32_t doc) {
@@ -475,9 +504,10 @@ __device__ __forceinline__ uint32_t FilterWord(const DevIndexView &ix, const Lis
 // Exact probe of ONE candidate per lane (filter survivors, doc ascending across lanes):
 // skip metadata -> block; blk_heads (one 16-byte load) -> 4-record group; the group's records in
 // one or two 16-byte loads -> record -> membership. Three dependent round trips, three sectors.
-// Returns false when the list has nothing at or after the first candidate.
+// Returns false when the list has nothing at or after the first candidate. `win`: shared-window
+// address of the warp's 128-word scratch window.
 template <class ST>
-__device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, uint32_t *win, bool has,
+__device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, uint32_t win, bool has,
                                          uint32_t x, bool *hit, uint32_t *pos, int lane,
                                          ST &st) {
   *hit = false;
@@ -489,32 +519,32 @@ __device__ __forceinline__ bool ProbeOne(const DevIndexView &ix, ProbeList &p, u
   if (mx <= __shfl_sync(kFull, p.wl, 31)) {
     // every candidate falls inside the 32-block register window
     __syncwarp();
-    win[lane] = p.wl;
+    StsU32(win + 4u * (uint32_t)lane, p.wl);
     __syncwarp();
     uint32_t c = 0;
 #pragma unroll
     for (uint32_t s = 16; s; s >>= 1)
-      if (win[c + s - 1] < x) c += s;
-    c += win[c] < x;
+      if (LdsU32(win + 4u * (c + s - 1u)) < x) c += s;
+    c += LdsU32(win + 4u * c) < x;
     j = p.wbase + c;
     if (c >= 32u) has = false;
   } else {
     // the batch spans more: stage the next 96 entries too (coalesced, usually L2 hits) and search
     // the 128-entry window in shared memory; only candidates beyond it walk blk_last in global
     __syncwarp();
-    win[lane] = p.wl;
+    StsU32(win + 4u * (uint32_t)lane, p.wl);
 #pragma unroll
     for (uint32_t i = 1; i < 4; i++) {
       const uint32_t at = p.wbase + 32u * i + (uint32_t)lane;
-      win[32u * i + lane] = at < p.nb ? __ldg(p.last + at) : kNoDoc;
+      StsU32(win + 4u * (32u * i + (uint32_t)lane), at < p.nb ? __ldg(p.last + at) : kNoDoc);
     }
     __syncwarp();
-    if (!has || x <= win[127]) {
+    if (!has || x <= LdsU32(win + 4u * 127u)) {
       uint32_t c = 0;
 #pragma unroll
       for (uint32_t s = 64; s; s >>= 1)
-        if (win[c + s - 1] < x) c += s;
-      c += win[c] < x;
+        if (LdsU32(win + 4u * (c + s - 1u)) < x) c += s;
+      c += LdsU32(win + 4u * c) < x;
       j = p.wbase + c;
     } else {
       uint32_t lo = p.wbase + 128u, hi = p.nb;
@@ -693,7 +723,7 @@ __device__ __forceinline__ bool PhraseTwo(const PosRun a, const PosRun b, bool p
 // latency-heavy tf / norm gathers and the fp64 divisions stay off the per-block path.
 template <bool COLLECT, class ST>
 __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const DevQuery &q, uint32_t qi,
-                          const CtaShared *sh, ProbeScratch *ws, int nq, int drv, double idf0,
+                          const CtaShared *sh, uint32_t a_ws, int nq, int drv, double idf0,
                           double idf1, TopK &top, double &published, bool multi, int lane,
                           ST &st) {
   __syncwarp();
@@ -703,7 +733,11 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
     double s = 0.0;
     int doc = 0;
     if (has) {
-      const HitRec h = ws->hits[base + lane];
+      HitRec h;
+      {
+        const uint32_t ha = a_ws + (uint32_t)offsetof(ProbeScratch, hits) + 12u * (uint32_t)(base + lane);
+        h.doc = LdsU32(ha); h.pos_a = LdsU32(ha + 4u); h.pos_b = LdsU32(ha + 8u);
+      }
       doc = (int)h.doc;
       uint32_t tfa, tfb;
       if (q.flags & 1u) {   // phrase: query term 0 must be directly followed by term 1
@@ -734,23 +768,25 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
 
 // Probes the first n (<= 32) queued survivors and appends the hits to the hit queue.
 template <class ST>
-__device__ __forceinline__ bool ProbeBatch(const DevIndexView &ix, ProbeList &pb, ProbeScratch *ws,
+__device__ __forceinline__ bool ProbeBatch(const DevIndexView &ix, ProbeList &pb, uint32_t wsa,
                                            int base, int n, int &nq, int lane, ST &st) {
   const bool has = lane < n;
   CandRec c;
   c.doc = 0; c.pos_a = 0;
-  if (has) c = ws->cand[base + lane];
+  if (has) {
+    const uint2 v = LdsU64(wsa + (uint32_t)offsetof(ProbeScratch, cand) + 8u * (uint32_t)(base + lane));
+    c.doc = v.x; c.pos_a = v.y;
+  }
   bool hit;
   uint32_t pos = 0;
-  const bool more = ProbeOne(ix, pb, ws->win, has, c.doc, &hit, &pos, lane, st);
+  const bool more = ProbeOne(ix, pb, wsa + (uint32_t)offsetof(ProbeScratch, win), has, c.doc, &hit, &pos, lane, st);
   const unsigned m = __ballot_sync(kFull, hit);
   if (m) {
     if (hit) {
-      HitRec h;
-      h.doc = c.doc;
-      h.pos_a = c.pos_a;
-      h.pos_b = pos;
-      ws->hits[nq + __popc(m & ((1u << lane) - 1u))] = h;
+      const uint32_t ha = wsa + (uint32_t)offsetof(ProbeScratch, hits) + 12u * (uint32_t)(nq + __popc(m & ((1u << lane) - 1u)));
+      StsU32(ha, c.doc);
+      StsU32(ha + 4u, c.pos_a);
+      StsU32(ha + 8u, pos);
     }
     nq += __popc(m);
   }
@@ -760,7 +796,7 @@ __device__ __forceinline__ bool ProbeBatch(const DevIndexView &ix, ProbeList &pb
 template <bool COLLECT, class ST>
 __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
                            uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
-                           const CtaShared *sh, ProbeScratch *ws, int lane, ST &st) {
+                           const CtaShared *sh, uint32_t a_sh, uint32_t a_ws, int lane, ST &st) {
   const int drv = (int)q.driver, oth = 1 - drv;
   const uint4 la = __ldg(&ix.lists[q.term[drv]]);
   const uint4 lb = __ldg(&ix.lists[q.term[oth]]);
@@ -775,6 +811,8 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
   ProbeInit(pb, ix, lb, lane);
   int nq = 0, nc = 0;
   bool more = true;
+  const uint32_t a_fpat = a_sh + (uint32_t)offsetof(CtaShared, fpat);
+  const uint32_t a_cand = a_ws + (uint32_t)offsetof(ProbeScratch, cand);
 
   // Software pipeline over driver blocks: blk_info two ahead, the lane's raw record one ahead,
   // and the Bloom filter words of block ja+1 are requested BEFORE the survivors of block ja are
@@ -826,7 +864,7 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
     bool pass[4];
     unsigned bm[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) pass[i] = FilterTest(sh, fw[i], d[i]);
+    for (int i = 0; i < 4; i++) pass[i] = FilterTestS(a_fpat, fw[i], d[i]);
     if (na != 128u) {   // a list's last block: padded slots repeat the last doc
 #pragma unroll
       for (int i = 0; i < 4; i++) pass[i] = pass[i] && 4u * lane + i < na;
@@ -834,15 +872,13 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
 #pragma unroll
     for (int i = 0; i < 4; i++) bm[i] = __ballot_sync(kFull, pass[i]);
     const unsigned lt = (1u << lane) - 1u;
-    int at = nc + __popc(bm[0] & lt) + __popc(bm[1] & lt) + __popc(bm[2] & lt) + __popc(bm[3] & lt);
-    const uint32_t ga = (first_a + ja) << 7;
+    uint32_t at = a_cand + 8u * (uint32_t)(nc + __popc(bm[0] & lt) + __popc(bm[1] & lt) + __popc(bm[2] & lt) + __popc(bm[3] & lt));
+    const uint32_t ga = ((first_a + ja) << 7) | (4u * (uint32_t)lane);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (pass[i]) {
-        CandRec c;
-        c.doc = d[i];
-        c.pos_a = ga | (4u * lane + i);
-        ws->cand[at++] = c;
+        StsU64(at, d[i], ga | (uint32_t)i);   // CandRec {doc, pos_a}
+        at += 8u;
       }
     }
     nc += __popc(bm[0]) + __popc(bm[1]) + __popc(bm[2]) + __popc(bm[3]);
@@ -859,19 +895,18 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
     // ---- exact probe, 32 survivors at a time
     int base = 0;
     for (; nc - base >= 32 && more; base += 32) {
-      more = ProbeBatch(ix, pb, ws, base, 32, nq, lane, st);
+      more = ProbeBatch(ix, pb, a_ws, base, 32, nq, lane, st);
       if (nq >= 32) {
-        FlushHits<COLLECT>(ix, bv, q, qi, sh, ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
+        FlushHits<COLLECT>(ix, bv, q, qi, sh, a_ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
         nq = 0;
       }
     }
     if (base) {   // move the leftover (< 32) to the front
-      CandRec c;
-      c.doc = 0; c.pos_a = 0;
+      uint2 c = make_uint2(0u, 0u);
       const bool mv = base + lane < nc;
-      if (mv) c = ws->cand[base + lane];
+      if (mv) c = LdsU64(a_cand + 8u * (uint32_t)(base + lane));
       __syncwarp();
-      if (mv) ws->cand[lane] = c;
+      if (mv) StsU64(a_cand + 8u * (uint32_t)lane, c.x, c.y);
       nc -= base;
       __syncwarp();
     }
@@ -880,8 +915,8 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
 #pragma unroll
     for (int i = 0; i < 4; i++) { d[i] = dn[i]; fw[i] = fwn[i]; }
   }
-  if (nc && more) ProbeBatch(ix, pb, ws, 0, nc, nq, lane, st);
-  if (nq) FlushHits<COLLECT>(ix, bv, q, qi, sh, ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
+  if (nc && more) ProbeBatch(ix, pb, a_ws, 0, nc, nq, lane, st);
+  if (nq) FlushHits<COLLECT>(ix, bv, q, qi, sh, a_ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
 }
 
@@ -1212,7 +1247,7 @@ __device__ bool MultiBatch(const DevIndexView &ix, const BatchView &bv, const De
     ProbeList pl = Unpark(ix, ws->list[t], lane);
     bool hit = false;
     uint32_t pb = 0;
-    const bool some = ProbeOne(ix, pl, ws->ps.win, has, c.doc, &hit, &pb, lane, st);
+    const bool some = ProbeOne(ix, pl, SmemAddr(ws->ps.win), has, c.doc, &hit, &pb, lane, st);
     __syncwarp();
     Park(ws->list[t], pl, lane);
     __syncwarp();
@@ -1438,6 +1473,10 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
   const int lane = (int)(tid & 31u);
   auto *ws = &scratch[tid >> 5];
   (void)ws;
+  // shared-window addresses of the CTA's tables and the warp's scratch, made opaque so that they
+  // live in two registers instead of being re-derived (S2R + MOV + LEA) at every use
+  uint32_t a_sh = SmemAddr(&sh), a_ws = SmemAddr(ws);
+  asm volatile("" : "+r"(a_sh), "+r"(a_ws));
   const uint32_t n_units = bv.class_units[CLASS];
   UnitStatsT<STATS> st = {0ull, 0ull, 0ull, 0ull, kNoDoc};
   unsigned long long units = 0;
@@ -1463,12 +1502,12 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
       ProcessOneTerm<false>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
     } else if constexpr (CLASS == kClassTwo) {
       if constexpr (MERGE) ProcessTwoMerge(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
-      else ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
+      else ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, a_sh, a_ws, lane, st);
     } else if constexpr (CLASS == kClassMany) {
       ProcessMulti<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     } else {
       if (q.n_terms == 1) ProcessOneTerm<true>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
-      else if (q.n_terms == 2) ProcessTwo<true>(ix, bv, q, qi, local, b0, b1, &sh, &ws->ps, lane, st);
+      else if (q.n_terms == 2) ProcessTwo<true>(ix, bv, q, qi, local, b0, b1, &sh, a_sh, a_ws, lane, st);
       else ProcessMulti<true>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     }
     units++;
@@ -1587,7 +1626,6 @@ struct __align__(128) K1Shared {
   uint32_t done[kK1Depth];             // warps of the CTA that finished reading the slot
 };
 
-__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void MbarInit(unsigned long long *bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count));
 }

@@ -120,7 +120,9 @@ int ReplayGroup(int argc, char **argv, const std::string &dirs_flag, const std::
   FILE *df = dump.empty() ? nullptr : fopen(dump.c_str(), "w");
   uint64_t n_queries = 0, listed = 0, entries = 0;
   const auto t0 = std::chrono::steady_clock::now();
+  double best_rep = 1e30;
   for (int rep = 0; rep < repeat; rep++) {
+    const auto t_rep = std::chrono::steady_clock::now();
     for (int lo = 0; lo < n; lo += B) {
       const int m = std::min(B, n - lo);
       int got = 0;
@@ -142,6 +144,7 @@ int ReplayGroup(int argc, char **argv, const std::string &dirs_flag, const std::
       }
       n_queries += m;
     }
+    best_rep = std::min(best_rep, std::chrono::duration<double>(std::chrono::steady_clock::now() - t_rep).count());
   }
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   if (df) fclose(df);
@@ -149,8 +152,9 @@ int ReplayGroup(int argc, char **argv, const std::string &dirs_flag, const std::
   wsr_group_close(g);
   printf("WSR_REPLAY_JSON {\"mode\": \"group\", \"partitions\": %zu, \"devices\": %zu, \"queries\": %" PRIu64
          ", \"seconds\": %.6f, \"qps\": %.3f, \"listed_postings\": %" PRIu64 ", \"listed_postings_per_s\": %.3f, "
-         "\"result_entries\": %" PRIu64 ", \"load_seconds\": %.3f}\n",
-         dirs.size(), devices.size(), n_queries, secs, n_queries / secs, listed, listed / secs, entries, load_s);
+         "\"result_entries\": %" PRIu64 ", \"load_seconds\": %.3f, \"best_pass_seconds\": %.6f, \"best_pass_qps\": %.3f}\n",
+         dirs.size(), devices.size(), n_queries, secs, n_queries / secs, listed, listed / secs, entries, load_s,
+         best_rep, (double)n / best_rep);
   return 0;
 }
 

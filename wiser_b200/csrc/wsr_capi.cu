@@ -192,6 +192,7 @@ struct wsr_batch {
   int n = 0;
   int k_stride = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;       // doc_freqs of a log travel here, under the search kernels
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // host plan
   std::vector<DevQuery> planned;
@@ -545,6 +546,7 @@ void FreeBatch(wsr_batch *b) {
   if (!b) return;
   cudaSetDevice(b->idx->device);
   if (b->stream) { cudaStreamSynchronize(b->stream); cudaStreamDestroy(b->stream); }
+  if (b->side) { cudaStreamSynchronize(b->side); cudaStreamDestroy(b->side); }
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   delete b;
@@ -575,6 +577,10 @@ struct PooledBatch {
   ~PooledBatch() {
     if (!b) return;
     cudaStreamSynchronize(b->stream);
+    if (b->side) cudaStreamSynchronize(b->side);
+    // a zero-copy run pointed the kernels at the caller's buffers: never leave those behind
+    b->view.hits = b->out_hits;
+    b->view.n_hits = b->out_n;
     ReleasePooled(idx, b);
   }
   PooledBatch(const PooledBatch &) = delete;
@@ -1389,20 +1395,71 @@ int EnqueueDocFreqs(wsr_batch *b, uint32_t *doc_freqs, int32_t *n_doc_freqs, boo
 int SearchLogOnDevice(wsr_index *idx, const char *text, size_t len, int k, wsr_hit *hits,
                       int32_t *n_hits, uint32_t *doc_freqs, int32_t *n_doc_freqs, int cap_q,
                       int *n_queries) {
+  // WSR_TRACE=1: host-side stage times of this call on stderr (where the end-to-end time goes)
+  static const bool trace = getenv("WSR_TRACE") && atoi(getenv("WSR_TRACE")) != 0;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
   PooledBatch pooled(idx);
   wsr_batch *b = pooled.b;
   if (!b) return Fail(WSR_ERR_CUDA, "cannot create batch");
   int rc = PlanLogOnDevice(b, text, len, k, cap_q);
+  if (rc) return rc;
+  const double t_plan = since();
   const uint32_t n = (uint32_t)b->n;
-  if (rc == WSR_OK) rc = EnqueueRun(b);
+  const size_t nh = (size_t)n * k;
+  const bool pinned = IsPinned(hits) && IsPinned(n_hits);
+  // Pinned result buffers: the kernels write every query's top-k row and count STRAIGHT into the
+  // caller's memory (page-locked host memory is device-addressable under UVA), a row when its query
+  // finishes — the 16.4 MB result copy behind the last kernel (0.3 ms per 100k-query log) disappears
+  // under the search kernels, and only rows that exist cross PCIe. doc_freqs (if asked for) are
+  // written the same way by DocFreqsKernel on a side stream: they depend on the planned queries
+  // only, which are complete at this point (the planner's totals have been read back).
+  static const bool zero_copy = !(getenv("WSR_NO_ZEROCOPY") && atoi(getenv("WSR_NO_ZEROCOPY")) != 0);
+  if (pinned && zero_copy) {
+    const bool df_direct = doc_freqs && IsPinned(doc_freqs) && IsPinned(n_doc_freqs);
+    bool df_staged = false;
+    if (doc_freqs) {
+      if (df_direct) {
+        if (!b->side) CU(cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking));
+        LaunchDocFreqs(b->d_tmp.p, n, idx->view, doc_freqs, n_doc_freqs, b->side);
+        CU(cudaGetLastError());
+      } else {
+        rc = EnqueueDocFreqs(b, doc_freqs, n_doc_freqs, &df_staged);
+        if (rc) return rc;
+      }
+    }
+    if (n) memset(n_hits, 0, (size_t)n * 4);   // queries without work units never write their count
+    b->view.hits = hits;
+    b->view.n_hits = n_hits;
+    rc = EnqueueRun(b);
+    if (rc) return rc;
+    const double t_enq = since();
+    CU(cudaStreamSynchronize(b->stream));
+    if (b->side) CU(cudaStreamSynchronize(b->side));
+    const double t_done = since();
+    b->view.hits = b->out_hits;
+    b->view.n_hits = b->out_n;
+    size_t total = 0;
+    for (uint32_t i = 0; i < n; i++) total += (size_t)n_hits[i];
+    if (trace)
+      fprintf(stderr, "[wsr trace] search_log n=%u: plan (H2D + front end + totals) %.0f us, enqueue %.0f us, "
+                      "kernels + result stores %.0f us, tail %.0f us\n",
+              n, t_plan, t_enq - t_plan, t_done - t_enq, since() - t_done);
+    if (nh) idx->result_fill_ppm.store((int)(total * 1000000ull / nh), std::memory_order_relaxed);
+    if (df_staged) {
+      memcpy(doc_freqs, b->h_df.p, (size_t)n * WSR_MAX_TERMS * 4);
+      memcpy(n_doc_freqs, b->h_ndf.p, (size_t)n * 4);
+    }
+    *n_queries = (int)n;
+    return WSR_OK;
+  }
+  rc = EnqueueRun(b);
   if (rc) return rc;
   bool df_staged = false;
   if (doc_freqs && n_doc_freqs) {
     rc = EnqueueDocFreqs(b, doc_freqs, n_doc_freqs, &df_staged);
     if (rc) return rc;
   }
-  const size_t nh = (size_t)n * k;
-  const bool pinned = IsPinned(hits) && IsPinned(n_hits);
   int32_t *cnt = n_hits;
   if (!pinned) {
     CU(b->h_n.Ensure((size_t)n + 1));
