@@ -4,10 +4,10 @@
 cp wiser_b200/libwsr.so /tmp/libwsr_base.so
 for spec in "$@"; do
   IFS=: read v ppw wl <<< "$spec"
-  ppw=${ppw:-2}; wl=${wl:-two_term}
+  ppw=${ppw:-4}; wl=${wl:-two_term}
   if [ $v = base ]; then cp /tmp/libwsr_base.so wiser_b200/libwsr.so; else cp _var/libwsr_$v.so wiser_b200/libwsr.so; fi
   echo "== $spec"
-  WSR_FILTER_PPW=$ppw python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline --parity-sample 50 2>/dev/null | python -c "
+  WSR_FILTER_PPW=$ppw python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline --no-secondary --parity-sample 50 2>/dev/null | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
