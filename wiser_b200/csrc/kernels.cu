@@ -65,6 +65,28 @@ __device__ __forceinline__ void StsU64(uint32_t a, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
 
+__device__ __forceinline__ uint4 LdsU128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void StsU128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// Asynchronous global -> shared copies (LDGSTS): the look-ahead loads of the two-term driver loop
+// land in the warp's scratch instead of in registers. With 64 registers per thread ptxas spilled
+// every looked-ahead value right behind its load (STL of a register an LDG had just been issued
+// into), which waits for the load on the spot: 15 % of the kernel's stall samples in the round-2
+// profile sat on such stores and the software pipeline hid nothing.
+__device__ __forceinline__ void CpAsync4(uint32_t sa, const void *g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void CpAsync16(uint32_t sa, const void *g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g) : "memory");
+}
+__device__ __forceinline__ void CpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void CpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---- block shape (host_index.h PackShape) --------------------------------------------------
 __device__ __forceinline__ uint32_t ShW0(uint32_t b) { return (b & 31u) + 1u; }
 __device__ __forceinline__ uint32_t ShB(uint32_t b) { return ((b >> 5) & 31u) + 1u; }
@@ -254,6 +276,11 @@ struct __align__(16) ProbeScratch {
   uint32_t win[128];             // the probe list's blk_last window, for per-lane block lookup
   CandRec cand[kCandCap];        // filter survivors awaiting the exact probe (doc ascending)
   HitRec hits[kHitCap];          // intersection hits awaiting scoring
+  // look-ahead staging of the two-term driver loop (cp.async targets, see ProcessTwo)
+  uint4 inf[4];                  // blk_info of driver blocks ja .. ja+3, ring by (ja - b0) & 3
+  uint32_t rec[2][128];          // doc-record stream of driver blocks ja+1 / ja+2 (<= 32 granules)
+  uint32_t fw[2][128];           // filter words of blocks ja / ja+1, lane-private: 4 per lane
+  uint32_t docs[128];            // decoded doc ids of block ja (+1 once staged), 4 per lane
 };
 struct __align__(16) NoScratch { uint32_t unused; };
 
@@ -793,6 +820,39 @@ __device__ __forceinline__ bool ProbeBatch(const DevIndexView &ix, ProbeList &pb
   return more;
 }
 
+// ---- staged look-ahead of the two-term driver loop (see ProcessTwo) -----------------------------
+// the doc-record stream of a block (<= 32 granules of 16 bytes) into the warp's scratch
+__device__ __forceinline__ void IssueRecords(const DevIndexView &ix, uint32_t ra, const uint4 info, int lane) {
+  if ((uint32_t)lane < DocGranules(info.z)) CpAsync16(ra + 16u * (uint32_t)lane, ix.payload + info.y + lane);
+}
+// record `rec` of a staged stream (zero for lanes past the block's records, like LoadRecord's callers)
+__device__ __forceinline__ uint4 StagedRecord(uint32_t ra, uint32_t bits, uint32_t rec) {
+  const uint32_t rc = ShRcode(bits);
+  uint4 r = make_uint4(0u, 0u, 0u, 0u);
+  if (rec < ((ShN(bits) + 3u) >> 2)) {
+    if (rc == 0u) {
+      r.x = LdsU32(ra + 4u * rec);
+    } else if (rc == 1u) {
+      const uint2 v = LdsU64(ra + 8u * rec);
+      r.x = v.x; r.y = v.y;
+    } else if (rc == 2u) {
+      r = LdsU128(ra + 16u * rec);
+    } else {
+      r.x = LdsU32(ra + 12u * rec); r.y = LdsU32(ra + 12u * rec + 4u); r.z = LdsU32(ra + 12u * rec + 8u);
+    }
+  }
+  return r;
+}
+// the four filter words of a lane's docs into its private 16-byte slot
+__device__ __forceinline__ void IssueFilterWords(const DevIndexView &ix, const ListFilter &lf, uint32_t fa, const uint32_t d[4]) {
+  if (lf.words == nullptr) {
+    StsU128(fa, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) CpAsync4(fa + 4u * (uint32_t)i, lf.words + ((d[i] - ix.doc_lo) >> lf.shift));
+  }
+}
+
 template <bool COLLECT, class ST>
 __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
                            uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
@@ -814,41 +874,66 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
   const uint32_t a_fpat = a_sh + (uint32_t)offsetof(CtaShared, fpat);
   const uint32_t a_cand = a_ws + (uint32_t)offsetof(ProbeScratch, cand);
 
-  // Software pipeline over driver blocks: blk_info two ahead, the lane's raw record one ahead,
-  // and the Bloom filter words of block ja+1 are requested BEFORE the survivors of block ja are
-  // probed, so neither the record nor the filter load sits on the critical path.
-  uint4 info_cur = __ldg(&ix.blk_info[first_a + b0]);
-  uint4 info_nxt = b0 + 1 < b1 ? __ldg(&ix.blk_info[first_a + b0 + 1]) : info_cur;
-  uint32_t d[4], fw[4];
+  // Software pipeline over driver blocks, staged through the warp's scratch with cp.async: while
+  // block ja is tested and its survivors are probed, the filter words of block ja+1, the doc
+  // records of block ja+2 and the blk_info row of block ja+3 are in flight. Each copy group has a
+  // whole iteration to land and occupies no register meanwhile.
+  const uint32_t a_inf = a_ws + (uint32_t)offsetof(ProbeScratch, inf);
+  const uint32_t a_rec = a_ws + (uint32_t)offsetof(ProbeScratch, rec);
+  const uint32_t a_fw = a_ws + (uint32_t)offsetof(ProbeScratch, fw) + 16u * (uint32_t)lane;
+  const uint32_t a_docs = a_ws + (uint32_t)offsetof(ProbeScratch, docs) + 16u * (uint32_t)lane;
+  if (lane < 3 && b0 + (uint32_t)lane < b1) CpAsync16(a_inf + 16u * (uint32_t)lane, &ix.blk_info[first_a + b0 + (uint32_t)lane]);
+  CpAsyncCommit();
+  CpAsyncWaitAll();
+  __syncwarp();
   {
-    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-    if ((uint32_t)lane < ((ShN(info_cur.z) + 3u) >> 2)) raw = LoadRecord(ix, info_cur, (uint32_t)lane);
-    DecodeRaw(info_cur, raw, d);
-#pragma unroll
-    for (int i = 0; i < 4; i++) fw[i] = FilterWord(ix, flt, d[i]);
+    const uint4 i0 = LdsU128(a_inf);
+    IssueRecords(ix, a_rec, i0, lane);
+    if (b0 + 1 < b1) IssueRecords(ix, a_rec + 512u, LdsU128(a_inf + 16u), lane);
+    CpAsyncCommit();
+    CpAsyncWaitAll();
+    __syncwarp();
+    uint32_t d0[4];
+    DecodeRaw(i0, StagedRecord(a_rec, i0.z, (uint32_t)lane), d0);
+    StsU128(a_docs, d0[0], d0[1], d0[2], d0[3]);
+    IssueFilterWords(ix, flt, a_fw, d0);
+    CpAsyncCommit();
   }
-  uint4 raw_nxt = make_uint4(0u, 0u, 0u, 0u);
-  if (b0 + 1 < b1 && (uint32_t)lane < ((ShN(info_nxt.z) + 3u) >> 2))
-    raw_nxt = LoadRecord(ix, info_nxt, (uint32_t)lane);
   for (uint32_t ja = b0; ja < b1 && more; ja++) {
+    const uint32_t t = ja - b0;
+    CpAsyncWaitAll();
+    __syncwarp();
+    const uint4 info_cur = LdsU128(a_inf + 16u * (t & 3u));
     const uint32_t na = ShN(info_cur.z);
     WSR_STAT(st.decoded += na;);
     WSR_STAT(st.bytes += AlgBytes(info_cur.z, false););
-    // ---- stage for block ja+1: decode its record, request its filter words, fetch ja+2's record
-    uint32_t dn[4] = {kNoDoc, kNoDoc, kNoDoc, kNoDoc}, fwn[4] = {0u, 0u, 0u, 0u};
-    uint4 info_nxt2 = info_nxt;
+    uint32_t d[4];
+    {
+      const uint4 dv = LdsU128(a_docs);
+      d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
+    }
+    // ---- stage: docs + filter words of block ja+1, records of ja+2, blk_info of ja+3
     if (ja + 1 < b1) {
-      DecodeRaw(info_nxt, raw_nxt, dn);
-#pragma unroll
-      for (int i = 0; i < 4; i++) fwn[i] = FilterWord(ix, flt, dn[i]);
+      const uint4 info_nxt = LdsU128(a_inf + 16u * ((t + 1u) & 3u));
+      uint32_t dn[4];
+      DecodeRaw(info_nxt, StagedRecord(a_rec + 512u * ((t + 1u) & 1u), info_nxt.z, (uint32_t)lane), dn);
+      StsU128(a_docs, dn[0], dn[1], dn[2], dn[3]);
+      IssueFilterWords(ix, flt, a_fw + 512u * ((t + 1u) & 1u), dn);
       if (ja + 2 < b1) {
-        info_nxt2 = __ldg(&ix.blk_info[first_a + ja + 2]);
+        const uint4 info_nxt2 = LdsU128(a_inf + 16u * ((t + 2u) & 3u));
+        IssueRecords(ix, a_rec + 512u * (t & 1u), info_nxt2, lane);
+        if (ja + 3 < b1 && lane == 0) CpAsync16(a_inf + 16u * ((t + 3u) & 3u), &ix.blk_info[first_a + ja + 3]);
+#ifndef WSR_NO_PREFETCH
+        // the driver list's own payload is contiguous: the two blocks after ja+2 into L2
+        if (ja + 4 < b1 && lane < 6)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(ix.payload + info_nxt2.y) + 128 * (lane + 1)));
+#endif
       }
 #ifndef WSR_NO_PREFETCH
       // The driver walks the doc-id space upwards, so the filter words it will need are the ones
       // just above the words of block ja+1: pull the next two blocks' worth (estimated from this
       // block's span) into L2, one 128-byte line per lane, when that is at most 32 lines.
-      if (flt.words != nullptr && ja + 3 < b1 && ((ja - b0) & 1u) == 0u) {   // every other block, twice the reach
+      if (flt.words != nullptr && ja + 3 < b1 && (t & 1u) == 0u) {   // every other block, twice the reach
         const uint32_t nl1 = (ShN(info_nxt.z) + 3u) >> 2;
         const uint32_t w_lo = (__shfl_sync(kFull, dn[0], 0) - ix.doc_lo) >> flt.shift;
         const uint32_t w_hi = (__shfl_sync(kFull, dn[3], (int)nl1 - 1) - ix.doc_lo) >> flt.shift;
@@ -860,7 +945,13 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
       }
 #endif
     }
+    CpAsyncCommit();
     // ---- Bloom pre-test of block ja, then compaction in (lane, slot) = doc order
+    uint32_t fw[4];
+    {
+      const uint4 fv = LdsU128(a_fw + 512u * (t & 1u));
+      fw[0] = fv.x; fw[1] = fv.y; fw[2] = fv.z; fw[3] = fv.w;
+    }
     bool pass[4];
     unsigned bm[4];
 #pragma unroll
@@ -883,15 +974,6 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
     }
     nc += __popc(bm[0]) + __popc(bm[1]) + __popc(bm[2]) + __popc(bm[3]);
     __syncwarp();
-    // the record of block ja+2 (its info has had a whole iteration to arrive)
-    raw_nxt = make_uint4(0u, 0u, 0u, 0u);
-    if (ja + 2 < b1 && (uint32_t)lane < ((ShN(info_nxt2.z) + 3u) >> 2))
-      raw_nxt = LoadRecord(ix, info_nxt2, (uint32_t)lane);
-#ifndef WSR_NO_PREFETCH
-    // ... and the driver list's own payload is contiguous: the two blocks after ja+2
-    if (ja + 4 < b1 && lane < 6)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(ix.payload + info_nxt2.y) + 128 * (lane + 1)));
-#endif
     // ---- exact probe, 32 survivors at a time
     int base = 0;
     for (; nc - base >= 32 && more; base += 32) {
@@ -910,11 +992,10 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
       nc -= base;
       __syncwarp();
     }
-    info_cur = info_nxt;
-    info_nxt = info_nxt2;
-#pragma unroll
-    for (int i = 0; i < 4; i++) { d[i] = dn[i]; fw[i] = fwn[i]; }
   }
+  // nothing of this unit may still be in flight when the next unit reuses the staging slots
+  CpAsyncWaitAll();
+  __syncwarp();
   if (nc && more) ProbeBatch(ix, pb, a_ws, 0, nc, nq, lane, st);
   if (nq) FlushHits<COLLECT>(ix, bv, q, qi, sh, a_ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
