@@ -35,9 +35,6 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kNoDoc = 0xffffffffu;
 constexpr double kK1Plus1 = 1.2 + 1;   // (k1_ + 1) evaluated in double, scoring.h:68
-#ifndef WSR_PF_MULT
-#define WSR_PF_MULT 2u   // look-ahead of the filter prefetch, in driver-block spans
-#endif
 constexpr int kCandCap = 160;          // survivors: 31 carried over + up to 128 of one driver block
 constexpr int kHitCap = 64;            // hits: 31 queued + up to 32 of one probe batch
 
@@ -920,30 +917,9 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
       StsU128(a_docs, dn[0], dn[1], dn[2], dn[3]);
       IssueFilterWords(ix, flt, a_fw + 512u * ((t + 1u) & 1u), dn);
       if (ja + 2 < b1) {
-        const uint4 info_nxt2 = LdsU128(a_inf + 16u * ((t + 2u) & 3u));
-        IssueRecords(ix, a_rec + 512u * (t & 1u), info_nxt2, lane);
+        IssueRecords(ix, a_rec + 512u * (t & 1u), LdsU128(a_inf + 16u * ((t + 2u) & 3u)), lane);
         if (ja + 3 < b1 && lane == 0) CpAsync16(a_inf + 16u * ((t + 3u) & 3u), &ix.blk_info[first_a + ja + 3]);
-#ifndef WSR_NO_PREFETCH
-        // the driver list's own payload is contiguous: the two blocks after ja+2 into L2
-        if (ja + 4 < b1 && lane < 6)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(ix.payload + info_nxt2.y) + 128 * (lane + 1)));
-#endif
       }
-#ifndef WSR_NO_PREFETCH
-      // The driver walks the doc-id space upwards, so the filter words it will need are the ones
-      // just above the words of block ja+1: pull the next two blocks' worth (estimated from this
-      // block's span) into L2, one 128-byte line per lane, when that is at most 32 lines.
-      if (flt.words != nullptr && ja + 3 < b1 && (t & 1u) == 0u) {   // every other block, twice the reach
-        const uint32_t nl1 = (ShN(info_nxt.z) + 3u) >> 2;
-        const uint32_t w_lo = (__shfl_sync(kFull, dn[0], 0) - ix.doc_lo) >> flt.shift;
-        const uint32_t w_hi = (__shfl_sync(kFull, dn[3], (int)nl1 - 1) - ix.doc_lo) >> flt.shift;
-        const uint32_t span = 2u * WSR_PF_MULT * (w_hi - w_lo + 1u);
-        const uint32_t w = w_hi + 1u + 32u * (uint32_t)lane;
-        if (span <= 1024u && 32u * (uint32_t)lane < span &&
-            (size_t)(flt.words - ix.filters) + w < ix.n_filter_words)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(flt.words + w));
-      }
-#endif
     }
     CpAsyncCommit();
     // ---- Bloom pre-test of block ja, then compaction in (lane, slot) = doc order
