@@ -764,6 +764,7 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
       }
       doc = (int)h.doc;
       uint32_t tfa, tfb;
+      uint32_t nbyte = 0;
       if (q.flags & 1u) {   // phrase: query term 0 must be directly followed by term 1
         const PosRun ra = PositionsOf(ix, h.pos_a), rb = PositionsOf(ix, h.pos_b);
         keep = drv == 0 ? PhraseTwo(ra, rb, ix.pos16 != 0u) : PhraseTwo(rb, ra, ix.pos16 != 0u);
@@ -771,11 +772,14 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
         tfb = rb.n;
         WSR_STAT(st.bytes += 4ull * (ra.n + rb.n););
       } else {
+        // the norm byte first: its round trip overlaps the two blk_info -> tf word chains
+        asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(nbyte) : "l"(ix.norms + h.doc));
         tfa = TfAt(ix, h.pos_a);
         tfb = TfAt(ix, h.pos_b);
       }
       if (keep) {
-        const double cn = sh->cache[__ldg(ix.norms + h.doc)];
+        if (q.flags & 1u) nbyte = __ldg(ix.norms + h.doc);
+        const double cn = sh->cache[nbyte & 255u];
         // query order: term 0 first (scoring.h:124-145)
         s = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? tfa : tfb, cn));
         s = __dadd_rn(s, TermScore(idf1, drv == 0 ? tfb : tfa, cn));
@@ -1499,7 +1503,10 @@ template <> struct ScratchOfKernel<kClassTwo, false> { typedef ProbeScratch type
 template <> struct ScratchOfKernel<kClassTwo, true> { typedef MergeScratch type; };
 
 template <int CLASS, bool STATS, bool MERGE>
-__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? (MERGE ? 3 : 4) : CLASS == kClassMany ? 3 : CLASS == kClassOne ? 8 : 1)
+#ifndef WSR_TWO_CTAS
+#define WSR_TWO_CTAS 4   // resident CTAs per SM the two-term probe kernel is compiled for (64 registers)
+#endif
+__global__ void __launch_bounds__(kThreadsPerCta, CLASS == kClassTwo ? (MERGE ? 3 : WSR_TWO_CTAS) : CLASS == kClassMany ? 3 : CLASS == kClassOne ? 8 : 1)
 SearchKernel(const DevIndexView ix, const BatchView bv) {
   __shared__ CtaShared sh;
   typedef typename ScratchOfKernel<CLASS, MERGE>::type Scratch;

@@ -8,16 +8,22 @@
 
 namespace wsr {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef WSR_WARPS_PER_CTA
+#define WSR_WARPS_PER_CTA 8
+#endif
+constexpr int kWarpsPerCta = WSR_WARPS_PER_CTA;
 constexpr int kThreadsPerCta = kWarpsPerCta * 32;
 constexpr int kMaxFastK = 32;      // top-k held one entry per lane
 #ifndef WSR_UNIT_BLOCKS
-#define WSR_UNIT_BLOCKS 64
+#define WSR_UNIT_BLOCKS 128
 #endif
 constexpr int kUnitBlocks = WSR_UNIT_BLOCKS;      // max driver-list blocks per warp work unit
 // a unit's budget in blocks, driver + the probe-list blocks they span: unit_blocks =
 // clamp(kUnitBudget / (1 + ratio), 1, kUnitBlocks), ratio = probe blocks per driver block
-constexpr int kUnitBudget = 4 * WSR_UNIT_BLOCKS;
+#ifndef WSR_UNIT_BUDGET_MULT
+#define WSR_UNIT_BUDGET_MULT 4
+#endif
+constexpr int kUnitBudget = WSR_UNIT_BUDGET_MULT * WSR_UNIT_BLOCKS;
 
 // Read-only view of the HBM-resident index (layout: host_index.h).
 struct DevIndexView {

@@ -274,7 +274,7 @@ int PlanBatch(wsr_batch *b, const wsr_query *queries, int n, int k_stride) {
   std::vector<Part> part(T);
   b->tmp.resize((size_t)n);
   b->tmp_cls.resize((size_t)n);
-  // Small batches (the Search() serving path) cannot fill the GPU with 64-block units: one warp
+  // Small batches (the Search() serving path) cannot fill the GPU with full-size units: one warp
   // would walk a long list alone while thousands idle, and the query's latency is that walk.
   // Cap the unit size so that the batch yields about one unit per resident warp.
   uint64_t unit_cap = kUnitBlocks;
