@@ -745,7 +745,7 @@ __device__ __forceinline__ bool PhraseTwo(const PosRun a, const PosRun b, bool p
 // located, staged once, and every candidate that falls inside it is resolved in the same pass.
 // Hits are queued in shared memory and scored 32 at a time (one lane per hit) so the divergent,
 // latency-heavy tf / norm gathers and the fp64 divisions stay off the per-block path.
-template <bool COLLECT, class ST>
+template <bool COLLECT, bool PHRASE, class ST>
 __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const DevQuery &q, uint32_t qi,
                           const CtaShared *sh, uint32_t a_ws, int nq, int drv, double idf0,
                           double idf1, TopK &top, double &published, bool multi, int lane,
@@ -765,7 +765,7 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
       doc = (int)h.doc;
       uint32_t tfa, tfb;
       uint32_t nbyte = 0;
-      if (q.flags & 1u) {   // phrase: query term 0 must be directly followed by term 1
+      if constexpr (PHRASE) {   // phrase: query term 0 must be directly followed by term 1
         const PosRun ra = PositionsOf(ix, h.pos_a), rb = PositionsOf(ix, h.pos_b);
         keep = drv == 0 ? PhraseTwo(ra, rb, ix.pos16 != 0u) : PhraseTwo(rb, ra, ix.pos16 != 0u);
         tfa = ra.n;           // a posting's run length IS its tf
@@ -778,7 +778,7 @@ __device__ void FlushHits(const DevIndexView &ix, const BatchView &bv, const Dev
         tfb = TfAt(ix, h.pos_b);
       }
       if (keep) {
-        if (q.flags & 1u) nbyte = __ldg(ix.norms + h.doc);
+        if constexpr (PHRASE) nbyte = __ldg(ix.norms + h.doc);
         const double cn = sh->cache[nbyte & 255u];
         // query order: term 0 first (scoring.h:124-145)
         s = __dadd_rn(0.0, TermScore(idf0, drv == 0 ? tfa : tfb, cn));
@@ -854,7 +854,7 @@ __device__ __forceinline__ void IssueFilterWords(const DevIndexView &ix, const L
   }
 }
 
-template <bool COLLECT, class ST>
+template <bool COLLECT, bool PHRASE, class ST>
 __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const DevQuery &q,
                            uint32_t qi, uint32_t local, uint32_t b0, uint32_t b1,
                            const CtaShared *sh, uint32_t a_sh, uint32_t a_ws, int lane, ST &st) {
@@ -900,84 +900,98 @@ __device__ void ProcessTwo(const DevIndexView &ix, const BatchView &bv, const De
     IssueFilterWords(ix, flt, a_fw, d0);
     CpAsyncCommit();
   }
-  for (uint32_t ja = b0; ja < b1 && more; ja++) {
-    const uint32_t t = ja - b0;
-    CpAsyncWaitAll();
-    __syncwarp();
-    const uint4 info_cur = LdsU128(a_inf + 16u * (t & 3u));
-    const uint32_t na = ShN(info_cur.z);
-    WSR_STAT(st.decoded += na;);
-    WSR_STAT(st.bytes += AlgBytes(info_cur.z, false););
-    uint32_t d[4];
-    {
-      const uint4 dv = LdsU128(a_docs);
-      d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
-    }
-    // ---- stage: docs + filter words of block ja+1, records of ja+2, blk_info of ja+3
-    if (ja + 1 < b1) {
-      const uint4 info_nxt = LdsU128(a_inf + 16u * ((t + 1u) & 3u));
-      uint32_t dn[4];
-      DecodeRaw(info_nxt, StagedRecord(a_rec + 512u * ((t + 1u) & 1u), info_nxt.z, (uint32_t)lane), dn);
-      StsU128(a_docs, dn[0], dn[1], dn[2], dn[3]);
-      IssueFilterWords(ix, flt, a_fw + 512u * ((t + 1u) & 1u), dn);
-      if (ja + 2 < b1) {
-        IssueRecords(ix, a_rec + 512u * (t & 1u), LdsU128(a_inf + 16u * ((t + 2u) & 3u)), lane);
-        if (ja + 3 < b1 && lane == 0) CpAsync16(a_inf + 16u * ((t + 3u) & 3u), &ix.blk_info[first_a + ja + 3]);
+  // One loop with ONE call site each for the probe and for the scoring: both are several hundred
+  // instructions once inlined, and a second copy for the unit's last few survivors and hits (as in
+  // the first version of this loop) doubled the kernel's instruction footprint -- the loops of
+  // this kernel live or die by the 32 KB instruction cache. An iteration tests the next driver
+  // block when fewer than 32 survivors are queued, probes one batch of survivors when there are
+  // 32 (or the blocks are through), and scores the queued hits when there are 32 (or at the end).
+  uint32_t ja = b0;
+  int cbase = 0;   // survivors [0, cbase) have been probed
+  for (;;) {
+    if (ja < b1 && more && nc - cbase < 32) {
+      if (cbase) {   // move the unprobed survivors (< 32) to the front
+        uint2 c = make_uint2(0u, 0u);
+        const bool mv = cbase + lane < nc;
+        if (mv) c = LdsU64(a_cand + 8u * (uint32_t)(cbase + lane));
+        __syncwarp();
+        if (mv) StsU64(a_cand + 8u * (uint32_t)lane, c.x, c.y);
+        nc -= cbase;
+        cbase = 0;
+        __syncwarp();
       }
-    }
-    CpAsyncCommit();
-    // ---- Bloom pre-test of block ja, then compaction in (lane, slot) = doc order
-    uint32_t fw[4];
-    {
-      const uint4 fv = LdsU128(a_fw + 512u * (t & 1u));
-      fw[0] = fv.x; fw[1] = fv.y; fw[2] = fv.z; fw[3] = fv.w;
-    }
-    bool pass[4];
-    unsigned bm[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) pass[i] = FilterTestS(a_fpat, fw[i], d[i]);
-    if (na != 128u) {   // a list's last block: padded slots repeat the last doc
-#pragma unroll
-      for (int i = 0; i < 4; i++) pass[i] = pass[i] && 4u * lane + i < na;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) bm[i] = __ballot_sync(kFull, pass[i]);
-    const unsigned lt = (1u << lane) - 1u;
-    uint32_t at = a_cand + 8u * (uint32_t)(nc + __popc(bm[0] & lt) + __popc(bm[1] & lt) + __popc(bm[2] & lt) + __popc(bm[3] & lt));
-    const uint32_t ga = ((first_a + ja) << 7) | (4u * (uint32_t)lane);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      if (pass[i]) {
-        StsU64(at, d[i], ga | (uint32_t)i);   // CandRec {doc, pos_a}
-        at += 8u;
-      }
-    }
-    nc += __popc(bm[0]) + __popc(bm[1]) + __popc(bm[2]) + __popc(bm[3]);
-    __syncwarp();
-    // ---- exact probe, 32 survivors at a time
-    int base = 0;
-    for (; nc - base >= 32 && more; base += 32) {
-      more = ProbeBatch(ix, pb, a_ws, base, 32, nq, lane, st);
-      if (nq >= 32) {
-        FlushHits<COLLECT>(ix, bv, q, qi, sh, a_ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
-        nq = 0;
-      }
-    }
-    if (base) {   // move the leftover (< 32) to the front
-      uint2 c = make_uint2(0u, 0u);
-      const bool mv = base + lane < nc;
-      if (mv) c = LdsU64(a_cand + 8u * (uint32_t)(base + lane));
+      const uint32_t t = ja - b0;
+      CpAsyncWaitAll();
       __syncwarp();
-      if (mv) StsU64(a_cand + 8u * (uint32_t)lane, c.x, c.y);
-      nc -= base;
+      const uint4 info_cur = LdsU128(a_inf + 16u * (t & 3u));
+      const uint32_t na = ShN(info_cur.z);
+      WSR_STAT(st.decoded += na;);
+      WSR_STAT(st.bytes += AlgBytes(info_cur.z, false););
+      uint32_t d[4];
+      {
+        const uint4 dv = LdsU128(a_docs);
+        d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
+      }
+      // ---- stage: docs + filter words of block ja+1, records of ja+2, blk_info of ja+3
+      if (ja + 1 < b1) {
+        const uint4 info_nxt = LdsU128(a_inf + 16u * ((t + 1u) & 3u));
+        uint32_t dn[4];
+        DecodeRaw(info_nxt, StagedRecord(a_rec + 512u * ((t + 1u) & 1u), info_nxt.z, (uint32_t)lane), dn);
+        StsU128(a_docs, dn[0], dn[1], dn[2], dn[3]);
+        IssueFilterWords(ix, flt, a_fw + 512u * ((t + 1u) & 1u), dn);
+        if (ja + 2 < b1) {
+          IssueRecords(ix, a_rec + 512u * (t & 1u), LdsU128(a_inf + 16u * ((t + 2u) & 3u)), lane);
+          if (ja + 3 < b1 && lane == 0) CpAsync16(a_inf + 16u * ((t + 3u) & 3u), &ix.blk_info[first_a + ja + 3]);
+        }
+      }
+      CpAsyncCommit();
+      // ---- Bloom pre-test of block ja, then compaction in (lane, slot) = doc order
+      uint32_t fw[4];
+      {
+        const uint4 fv = LdsU128(a_fw + 512u * (t & 1u));
+        fw[0] = fv.x; fw[1] = fv.y; fw[2] = fv.z; fw[3] = fv.w;
+      }
+      bool pass[4];
+      unsigned bm[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) pass[i] = FilterTestS(a_fpat, fw[i], d[i]);
+      if (na != 128u) {   // a list's last block: padded slots repeat the last doc
+#pragma unroll
+        for (int i = 0; i < 4; i++) pass[i] = pass[i] && 4u * lane + i < na;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) bm[i] = __ballot_sync(kFull, pass[i]);
+      const unsigned lt = (1u << lane) - 1u;
+      uint32_t at = a_cand + 8u * (uint32_t)(nc + __popc(bm[0] & lt) + __popc(bm[1] & lt) + __popc(bm[2] & lt) + __popc(bm[3] & lt));
+      const uint32_t ga = ((first_a + ja) << 7) | (4u * (uint32_t)lane);
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (pass[i]) {
+          StsU64(at, d[i], ga | (uint32_t)i);   // CandRec {doc, pos_a}
+          at += 8u;
+        }
+      }
+      nc += __popc(bm[0]) + __popc(bm[1]) + __popc(bm[2]) + __popc(bm[3]);
       __syncwarp();
+      ja++;
     }
+    const bool through = !(ja < b1 && more);   // no driver block left to test
+    // ---- exact probe of 32 survivors (of the last few once the blocks are through)
+    if (more && (nc - cbase >= 32 || (through && nc > cbase))) {
+      const int n = min(32, nc - cbase);
+      more = ProbeBatch(ix, pb, a_ws, cbase, n, nq, lane, st);
+      cbase += n;
+    }
+    const bool fin = through && (!more || nc == cbase);
+    if (nq >= 32 || (fin && nq)) {
+      FlushHits<COLLECT, PHRASE>(ix, bv, q, qi, sh, a_ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
+      nq = 0;
+    }
+    if (fin) break;
   }
   // nothing of this unit may still be in flight when the next unit reuses the staging slots
   CpAsyncWaitAll();
   __syncwarp();
-  if (nc && more) ProbeBatch(ix, pb, a_ws, 0, nc, nq, lane, st);
-  if (nq) FlushHits<COLLECT>(ix, bv, q, qi, sh, a_ws, nq, drv, idf0, idf1, top, published, multi, lane, st);
   if (!COLLECT) EmitTopK(bv, q, local, top, lane);
 }
 
@@ -1566,12 +1580,14 @@ SearchKernel(const DevIndexView ix, const BatchView bv) {
       ProcessOneTerm<false>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
     } else if constexpr (CLASS == kClassTwo) {
       if constexpr (MERGE) ProcessTwoMerge(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
-      else ProcessTwo<false>(ix, bv, q, qi, local, b0, b1, &sh, a_sh, a_ws, lane, st);
+      else if (q.flags & kQueryPhrase) ProcessTwo<false, true>(ix, bv, q, qi, local, b0, b1, &sh, a_sh, a_ws, lane, st);
+      else ProcessTwo<false, false>(ix, bv, q, qi, local, b0, b1, &sh, a_sh, a_ws, lane, st);
     } else if constexpr (CLASS == kClassMany) {
       ProcessMulti<false>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     } else {
       if (q.n_terms == 1) ProcessOneTerm<true>(ix, bv, q, qi, local, b0, b1, &sh, lane, st);
-      else if (q.n_terms == 2) ProcessTwo<true>(ix, bv, q, qi, local, b0, b1, &sh, a_sh, a_ws, lane, st);
+      else if (q.n_terms == 2 && (q.flags & kQueryPhrase)) ProcessTwo<true, true>(ix, bv, q, qi, local, b0, b1, &sh, a_sh, a_ws, lane, st);
+      else if (q.n_terms == 2) ProcessTwo<true, false>(ix, bv, q, qi, local, b0, b1, &sh, a_sh, a_ws, lane, st);
       else ProcessMulti<true>(ix, bv, q, qi, local, b0, b1, &sh, ws, lane, st);
     }
     units++;
