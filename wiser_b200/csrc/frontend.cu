@@ -227,6 +227,27 @@ struct IsNewline {
 
 }  // namespace
 
+// Number of '\n' bytes of the log text: 16 bytes per thread, one atomic per warp.
+__global__ void CountNewlinesKernel(const char *__restrict__ text, uint32_t len, uint32_t *__restrict__ count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t at = (size_t)i * 16u;
+  uint32_t c = 0;
+  if (at + 16u <= len) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text) + i);   // cudaMalloc'd: 16-byte aligned
+    c = (uint32_t)(__popc(__vcmpeq4(v.x, 0x0a0a0a0au)) + __popc(__vcmpeq4(v.y, 0x0a0a0a0au)) +
+                   __popc(__vcmpeq4(v.z, 0x0a0a0a0au)) + __popc(__vcmpeq4(v.w, 0x0a0a0a0au))) >> 3;
+  } else {
+    for (size_t j = at; j < len; j++) c += text[j] == '\n';
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+void LaunchCountNewlines(const char *d_text, uint32_t len, uint32_t *d_count, cudaStream_t s) {
+  if (!len) return;
+  const uint32_t threads = (len + 15u) / 16u;
+  CountNewlinesKernel<<<(threads + 255u) / 256u, 256, 0, s>>>(d_text, len, d_count);
+}
+
 size_t FrontEndTempBytes(uint32_t len, uint32_t n_lines) {
   size_t a = 0, b = 0;
   thrust::counting_iterator<uint32_t> idx(0);
@@ -282,8 +303,8 @@ void LaunchFrontEnd(const char *d_text, uint32_t len, uint32_t n_nl, uint32_t n_
                     uint32_t *d_multi, PlanItem *d_totals, uint32_t *d_err, void *d_cub,
                     size_t cub_bytes, cudaStream_t s) {
   if (!n_lines) return;
-  // newline positions, ascending. Their number n_nl was counted by the host while the text was in
-  // flight (n_lines = n_nl, + 1 when the log does not end in '\n'), so no count is read back.
+  // newline positions, ascending. Their number n_nl is known (LaunchCountNewlines; n_lines = n_nl,
+  // + 1 when the log does not end in '\n'), so the select's own count is not read back.
   thrust::counting_iterator<uint32_t> idx(0);
   size_t bytes = cub_bytes;
   cub::DeviceSelect::If(d_cub, bytes, idx, d_nl, d_n_nl, (int)len, IsNewline{d_text}, s);

@@ -161,6 +161,8 @@ struct PlanItem {
   uint32_t v[kPlanWords];
 };
 size_t FrontEndTempBytes(uint32_t len, uint32_t n_lines);
+// *d_count += number of '\n' bytes in d_text[0, len)
+void LaunchCountNewlines(const char *d_text, uint32_t len, uint32_t *d_count, cudaStream_t s);
 // Enqueues: newline positions -> parse + term lookup + per-query planning -> exclusive scan ->
 // class-sorted placement. d_totals receives the batch totals, d_err bit 0: a line with more than
 // WSR_MAX_TERMS terms, bit 1: a phrase query on an index without positions.

@@ -1257,20 +1257,17 @@ int PlanLogOnDevice(wsr_batch *b, const char *text, size_t len, int k, int cap_q
     src = b->h_text.p;
   }
   CU(cudaMemcpyAsync(b->d_text.p, src, len, cudaMemcpyHostToDevice, b->stream));
-  // line count on the host while the copy is in flight (QueryLogReader semantics: every '\n'
-  // ends a line; a last line without one still counts)
-  size_t n_nl = 0;
-  {
-    const int T = HostThreads(len, 1 << 18);
-    std::vector<size_t> cnt(T, 0);
-    ParallelFor(T, [&](int t, int TT) {
-      const char *p = text + len * t / TT, *e = text + len * (t + 1) / TT;
-      size_t c = 0;
-      while (p < e && (p = (const char *)memchr(p, '\n', e - p)) != nullptr) { c++; p++; }
-      cnt[t] = c;
-    });
-    for (size_t c : cnt) n_nl += c;
-  }
+  // line count (QueryLogReader semantics: every '\n' ends a line; a last line without one still
+  // counts) by a kernel behind the copy: 4 bytes come back before the grids are sized. A host-side
+  // count over the worker pool was as fast on an idle box but made the call's latency depend on
+  // how quickly sleeping host threads wake up (plan time 0.3 - 1.0 ms in the round-2 traces).
+  CU(b->d_fe_small.Ensure(2));
+  CU(b->h_totals.Ensure(kPlanWords + 1));
+  CU(cudaMemsetAsync(b->d_fe_small.p, 0, 8, b->stream));
+  LaunchCountNewlines(b->d_text.p, (uint32_t)len, b->d_fe_small.p, b->stream);
+  CU(cudaMemcpyAsync(b->h_totals.p, b->d_fe_small.p, 4, cudaMemcpyDeviceToHost, b->stream));
+  CU(cudaStreamSynchronize(b->stream));
+  const size_t n_nl = b->h_totals.p[0];
   const size_t n_lines = n_nl + (text[len - 1] != '\n' ? 1 : 0);
   if (n_lines > (size_t)cap_q) return Fail(WSR_ERR_ARG, "result buffers too small");
   const uint32_t n = (uint32_t)n_lines;
