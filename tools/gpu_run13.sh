@@ -13,3 +13,4 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 $CMD > gpurun_out/${T}_plain2.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:SearchKernel -s 4 -c 1 -o gpurun_out/${T}_two $CMD > gpurun_out/${T}_ncu_f.log 2>&1
 timeout 300 python tools/time_decode.py > gpurun_out/${T}_k1.log 2>&1; cat gpurun_out/${T}_k1.log | tail -3
+if [ -n "$STRONG1" ]; then bash tools/gpu_run_n.sh 1; fi
