@@ -311,7 +311,10 @@ def test_search_log_device_front_end_equals_host_planner(golden_dir):
                       b"t0\r", b"\tt0 t3\t", b'"t1"', b"t1 t1", b'"t2 t2"', b"t0 t1 t2 t3 t4 t5 t6 t7"])
     for text in (base * 12 + odd + b"\n",        # > 64 KiB, ends with a newline
                  odd + b"\n" + base[:-1],        # last line without a newline
-                 b"t0", b"\n", b"\n\n t1 \n"):
+                 b"t0", b"\n", b"\n\n t1 \n",
+                 # the line count is a kernel that reads 16 bytes per thread: lengths around it
+                 b"t0\n" * 5, b"t0\n" * 5 + b"\n", b"t0\n" * 5 + b"t1", b"\n" * 31 + b"t3", b"\n" * 32,
+                 b"t1 t0\n" * 5 + b"t2", b"t0\n" * 11):
         for k in (10, 1, 32):
             q = eng.parse_query_log(text, k)                       # host parser
             h1, n1 = _host_planned(eng, q, k)                      # host planner

@@ -46,11 +46,21 @@ __device__ uint32_t DictFind(const DevDict &d, const char *s, uint32_t len) {
   }
 }
 
+// Guided scheduling: a class's unit queue is drained in log order, so the queries near the end of
+// a batch get smaller units and the persistent grid's tail is made of short units (a full
+// 128-block unit is ~0.35 ms of one warp's time). Same rule in PlanBatch (host) and PlanOne (device).
+__device__ __forceinline__ unsigned long long UnitCapAt(unsigned long long i, unsigned long long n, unsigned long long cap) {
+  // last eighth of the batch: a quarter of the size (last quarter, two levels, an eighth of the
+  // size and 192-block units with two levels all measured 0.5 - 0.8 % slower)
+  const unsigned long long c = 8 * i >= 7 * n ? cap / 4 : cap;
+  return c < 1 ? 1 : c;
+}
+
 // Validity, driver list, unit size and class of one query whose term ids are in q.term[] — the
 // device statement of the host planner's per-query work (PlanBatch in wsr_capi.cu). tmp[i] is the
 // query before placement (cand_begin holds its class, 255 = produces no work).
 __device__ __forceinline__ void PlanOne(const DevIndexView &ix, DevQuery &q, uint32_t n_terms, uint32_t flags,
-                                        uint32_t k, uint32_t i, bool resolvable, DevQuery *__restrict__ tmp,
+                                        uint32_t k, uint32_t i, uint32_t n_all, bool resolvable, DevQuery *__restrict__ tmp,
                                         PlanItem *__restrict__ item, uint32_t *__restrict__ err) {
   PlanItem it;
 #pragma unroll
@@ -72,8 +82,9 @@ __device__ __forceinline__ void PlanOne(const DevIndexView &ix, DevQuery &q, uin
     const unsigned long long probe_blocks = all_blocks - drv_blocks;
     // unit size: same rule as the host planner (PlanBatch)
     const unsigned long long ratio = drv_blocks ? (probe_blocks + drv_blocks - 1) / drv_blocks : 0;
+    const unsigned long long cap = UnitCapAt(i, n_all, kUnitBlocks);
     unsigned long long ub = (unsigned long long)kUnitBudget / (1ull + ratio);
-    ub = ub < 1 ? 1 : ub > (unsigned long long)kUnitBlocks ? (unsigned long long)kUnitBlocks : ub;
+    ub = ub < 1 ? 1 : ub > cap ? cap : ub;
     q.n_terms = (uint8_t)n_terms;
     q.flags = (flags && n_terms > 1) ? 1 : 0;              // a one-term "phrase" is a plain query
     if (q.flags && ix.positions == nullptr) atomicOr(err, 2u);
@@ -131,7 +142,7 @@ __global__ void PlanQueriesKernel(const wsr_query *__restrict__ in, uint32_t n, 
     if (id == WSR_TERM_ABSENT) resolvable = false;                      // vacuum_engine.h:213-215
     else if (id >= ix.n_terms) { atomicOr(err, 4u); resolvable = false; }
   }
-  PlanOne(ix, q, n_terms, w.flags & 1u, w.k, i, resolvable, tmp, item, err);
+  PlanOne(ix, q, n_terms, w.flags & 1u, w.k, i, n, resolvable, tmp, item, err);
 }
 
 // One thread per log line: parse -> term ids -> validity -> driver list, unit size, class.
@@ -170,7 +181,7 @@ __global__ void ParsePlanKernel(const char *__restrict__ text, uint32_t len,
     t = u;
   }
   if (too_many) atomicOr(err, 1u);
-  PlanOne(ix, q, n_terms, flags, k, i, !too_many && present, tmp, item, err);
+  PlanOne(ix, q, n_terms, flags, k, i, n_lines, !too_many && present, tmp, item, err);
 }
 
 struct PlanAdd {
