@@ -1,6 +1,9 @@
+# Developer tool: full single-GPU validation on a B200 box (under gpurun): GPU tests, smoke, reference
+# arm, default bench with trace, ncu launch list, ncu --set full of the dominant kernel, K1 timing.
+# usage: gpurun -- 'TAG=<name> [STRONG1=1] bash tools/gpu_validate.sh'
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-T=${TAG:-r2w}
+T=${TAG:-run}
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${T}_tests.log
 tail -4 gpurun_out/${T}_tests.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${T}_smoke.log; tail -2 gpurun_out/${T}_smoke.log
