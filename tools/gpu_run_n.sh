@@ -11,6 +11,7 @@ fi
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 timeout 900 $TR bench.py --gpus $N --steps 20 --warmup 3 --parity-sample 100 > gpurun_out/r2n${N}_weak.json 2> gpurun_out/r2n${N}_weak.err; echo "rc=$?" >> gpurun_out/r2n${N}_weak.err
 grep -v "^\[W\|Setting OMP" gpurun_out/r2n${N}_weak.err | tail -4 | cut -c1-300
+[ -n "$WEAK_ONLY" ] && exit 0
 timeout 900 $TR bench.py --gpus $N --scaling strong --total-parts 8 --steps 10 --warmup 3 --parity-sample 50 > gpurun_out/r2n${N}_strong8.json 2> gpurun_out/r2n${N}_strong8.err; echo "rc=$?" >> gpurun_out/r2n${N}_strong8.err
 grep -v "^\[W\|Setting OMP" gpurun_out/r2n${N}_strong8.err | tail -4 | cut -c1-300
 if [ "$N" = "2" ]; then
